@@ -1,0 +1,355 @@
+"""ctypes binding of libguido_b200.so (the C-ABI declared in include/guido_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is usable,
+every accelerated call raises.  Arrays cross the boundary as numpy buffers (plain pointers).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libguido_b200.so")
+
+OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_CAPACITY, ERR_PAM, ERR_NOMEM = range(7)
+SCAN_REGEX, SCAN_GUIDE, SCAN_STRICT = 0, 1, 2
+OT_AUTO, OT_SCAN, OT_INDEX = 0, 1, 2
+
+OT_HIT_DTYPE = np.dtype([("guide", "<u4"), ("gpos", "<u4"), ("hi", "<u4"), ("lo", "<u4")])
+
+
+class ImageInfo(ctypes.Structure):
+    _fields_ = [("n_contigs", ctypes.c_int64), ("total_bases", ctypes.c_int64),
+                ("padded_bases", ctypes.c_int64), ("n_runs", ctypes.c_int64),
+                ("shard_lo", ctypes.c_int64), ("shard_hi", ctypes.c_int64),
+                ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double),
+                ("n_sites", ctypes.c_int64), ("n_pairs", ctypes.c_int64),
+                ("n_launches", ctypes.c_int64), ("bytes_h2d", ctypes.c_int64),
+                ("bytes_d2h", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+_P = ctypes.POINTER
+_vp, _i64, _i32, _cp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_char_p
+
+_SIGNATURES = {
+    "guido_last_error": (ctypes.c_char_p, []),
+    "guido_version": (ctypes.c_int, []),
+    "guido_device_count": (ctypes.c_int, []),
+    "guido_image_from_fasta": (ctypes.c_int, [_cp, _P(_vp)]),
+    "guido_image_from_seqs": (ctypes.c_int, [_i32, _P(_cp), _P(_cp), _P(_i64), _P(_vp)]),
+    "guido_image_synth": (ctypes.c_int, [_i32, _P(_cp), _P(_i64), ctypes.c_uint64, ctypes.c_double,
+                                         _i64, _i64, _P(_vp)]),
+    "guido_image_save": (ctypes.c_int, [_vp, _cp]),
+    "guido_image_load": (ctypes.c_int, [_cp, _P(_vp)]),
+    "guido_image_free": (ctypes.c_int, [_vp]),
+    "guido_image_upload": (ctypes.c_int, [_vp, _i32, _i32, _i32]),
+    "guido_image_get_info": (ctypes.c_int, [_vp, _P(ImageInfo)]),
+    "guido_image_contig": (ctypes.c_int, [_vp, _i64, _cp, _i64, _P(_i64), _P(_i64)]),
+    "guido_image_fetch": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp]),
+    "guido_pam_scan_seq": (ctypes.c_int, [_cp, _i64, _cp, _i32, _i32, _vp, _i64, _P(_i64), _vp, _i64,
+                                          _P(_i64), _P(Stats)]),
+    "guido_pam_scan_region": (ctypes.c_int, [_vp, _i64, _i64, _i64, _cp, _i32, _vp, _i64, _P(_i64),
+                                             _vp, _i64, _P(_i64), _P(Stats)]),
+    "guido_pam_scan_genome": (ctypes.c_int, [_vp, _cp, _i32, _vp, _i64, _P(_i64), _vp, _i64,
+                                             _P(_i64), _P(Stats)]),
+    "guido_pam_scan_genome_dev": (ctypes.c_int, [_vp, _cp, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "guido_offtarget_search": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _i64,
+                                              _P(_i64), _vp, _P(Stats)]),
+    "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
+                                                  _i64, _vp, _vp]),
+    "guido_encode_guides": (ctypes.c_int, [_cp, _i64, _vp]),
+    "guido_mmej_batch": (ctypes.c_int, [_cp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _P(Stats)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `make -C guido_b200/csrc`).  guido_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().guido_last_error().decode(errors="replace")
+
+
+def check(rc):
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_PAM:
+        raise KeyError(msg.strip("'"))
+    if rc == ERR_IO:
+        raise OSError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def device_count():
+    return int(lib().guido_device_count())
+
+
+def default_device():
+    """GUIDO_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    for key in ("GUIDO_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Image:
+    """Owner of one ``guido_image`` handle (host planes + optional HBM copy of one shard)."""
+
+    def __init__(self, handle):
+        self._h = ctypes.c_void_p(handle)
+        self._contigs = None
+
+    # ---- construction -----------------------------------------------------------------
+    @classmethod
+    def from_fasta(cls, path):
+        h = ctypes.c_void_p()
+        check(lib().guido_image_from_fasta(str(path).encode(), ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_seqs(cls, contigs):
+        """contigs: iterable of (name, sequence str/bytes)."""
+        contigs = list(contigs)
+        n = len(contigs)
+        names = (ctypes.c_char_p * n)(*[str(c[0]).encode() for c in contigs])
+        blobs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
+        seqs = (ctypes.c_char_p * n)(*blobs)
+        lens = (ctypes.c_int64 * n)(*[len(b) for b in blobs])
+        h = ctypes.c_void_p()
+        check(lib().guido_image_from_seqs(n, names, seqs, lens, ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def synth(cls, lens, seed, n_frac=0.005, run_min=50, run_max=5000, names=None):
+        n = len(lens)
+        names_arr = (ctypes.c_char_p * n)(*[s.encode() for s in names]) if names else None
+        lens_arr = (ctypes.c_int64 * n)(*[int(x) for x in lens])
+        h = ctypes.c_void_p()
+        check(lib().guido_image_synth(n, names_arr, lens_arr, int(seed), float(n_frac), int(run_min),
+                                      int(run_max), ctypes.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def load(cls, path):
+        h = ctypes.c_void_p()
+        check(lib().guido_image_load(str(path).encode(), ctypes.byref(h)))
+        return cls(h.value)
+
+    def save(self, path):
+        check(lib().guido_image_save(self._h, str(path).encode()))
+
+    def close(self):
+        if self._h:
+            lib().guido_image_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- metadata ---------------------------------------------------------------------
+    def upload(self, device=None, shard_ix=0, n_shards=1):
+        check(lib().guido_image_upload(self._h, default_device() if device is None else device,
+                                       shard_ix, n_shards))
+        return self
+
+    @property
+    def info(self):
+        inf = ImageInfo()
+        check(lib().guido_image_get_info(self._h, ctypes.byref(inf)))
+        return inf
+
+    @property
+    def contigs(self):
+        """[(name, length, global_offset), ...]"""
+        if self._contigs is None:
+            out = []
+            buf = ctypes.create_string_buffer(4096)
+            ln, off = ctypes.c_int64(), ctypes.c_int64()
+            for i in range(self.info.n_contigs):
+                check(lib().guido_image_contig(self._h, i, buf, 4096, ctypes.byref(ln), ctypes.byref(off)))
+                out.append((buf.value.decode(), ln.value, off.value))
+            self._contigs = out
+        return self._contigs
+
+    def contig_index(self, name):
+        for i, c in enumerate(self.contigs):
+            if c[0] == name:
+                return i
+        raise KeyError(name)
+
+    def locate(self, gpos):
+        """global positions -> (contig index array, offset-in-contig array)."""
+        gpos = np.asarray(gpos, dtype=np.int64)
+        offs = np.array([c[2] for c in self.contigs], dtype=np.int64)
+        ix = np.searchsorted(offs, gpos, side="right") - 1
+        return ix, gpos - offs[ix]
+
+    def fetch(self, contig_ix, start0, n):
+        buf = np.empty(n, dtype=np.uint8)
+        check(lib().guido_image_fetch(self._h, contig_ix, start0, n, buf.ctypes.data))
+        return buf.tobytes().decode()
+
+    # ---- PAM scan ---------------------------------------------------------------------
+    def pam_scan_genome(self, pam, mode=SCAN_GUIDE, stats=None, cap_hint=None):
+        """Whole shard -> (fw, rv) uint32 arrays of global PAM-start positions (ascending)."""
+        span = self.info.shard_hi - self.info.shard_lo
+        cap = int(cap_hint) if cap_hint else max(1024, span // 8)
+        st = stats if stats is not None else Stats()
+        while True:
+            fw, rv = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+            nf, nr = ctypes.c_int64(), ctypes.c_int64()
+            rc = lib().guido_pam_scan_genome(self._h, pam.encode(), mode, fw.ctypes.data, cap,
+                                             ctypes.byref(nf), rv.ctypes.data, cap, ctypes.byref(nr),
+                                             ctypes.byref(st))
+            if rc == ERR_CAPACITY:
+                cap = max(nf.value, nr.value)
+                continue
+            check(rc)
+            return fw[:nf.value], rv[:nr.value]
+
+    def pam_scan_region(self, contig_ix, start0, end0, pam, mode=SCAN_REGEX, stats=None):
+        n = max(end0 - start0, 0)
+        cap = max(256, n // 6)
+        st = stats if stats is not None else Stats()
+        while True:
+            fw, rv = np.empty(cap, np.int32), np.empty(cap, np.int32)
+            nf, nr = ctypes.c_int64(), ctypes.c_int64()
+            rc = lib().guido_pam_scan_region(self._h, contig_ix, start0, end0, pam.encode(), mode,
+                                             fw.ctypes.data, cap, ctypes.byref(nf), rv.ctypes.data, cap,
+                                             ctypes.byref(nr), ctypes.byref(st))
+            if rc == ERR_CAPACITY:
+                cap = max(nf.value, nr.value)
+                continue
+            check(rc)
+            return fw[:nf.value], rv[:nr.value]
+
+    def pam_scan_genome_dev(self, pam, mode, d_fw, cap_fw, d_rv, cap_rv, d_counts, stream=0):
+        check(lib().guido_pam_scan_genome_dev(self._h, pam.encode(), mode, d_fw, cap_fw, d_rv, cap_rv,
+                                              d_counts, stream))
+
+    # ---- off-target search ------------------------------------------------------------
+    def offtarget_search(self, protos, pam="NGG", core_length=10, core_mismatches=2,
+                         total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None):
+        """protos: list of 20-nt strings (or an (n,20) uint8 array of letters).
+
+        Returns (hits structured array sorted by (guide, gpos, strand), raw_flags uint8[n] | None).
+        """
+        if isinstance(protos, np.ndarray):
+            blob = np.ascontiguousarray(protos, dtype=np.uint8).tobytes()
+            n = protos.shape[0]
+        else:
+            protos = list(protos)
+            n = len(protos)
+            for p in protos:
+                if len(p) != 20:
+                    raise ValueError(f"protospacer must be 20 nt, got {len(p)}: {p!r}")
+            blob = "".join(protos).encode()
+        flags = np.zeros(n, np.uint8) if want_raw_flags else None
+        st = stats if stats is not None else Stats()
+        cap = max(4096, 32 * n)
+        while True:
+            hits = np.empty(cap, OT_HIT_DTYPE)
+            nh = ctypes.c_int64()
+            rc = lib().guido_offtarget_search(self._h, blob, n, pam.encode(), core_length,
+                                              core_mismatches, total_mismatches, algo, hits.ctypes.data,
+                                              cap, ctypes.byref(nh), _ptr(flags), ctypes.byref(st))
+            if rc == ERR_CAPACITY:
+                cap = nh.value
+                continue
+            check(rc)
+            return hits[:nh.value], flags
+
+    def offtarget_search_dev(self, d_guides, n_guides, pam, core_length, core_mismatches,
+                             total_mismatches, algo, d_hits, cap, d_count, stream=0):
+        check(lib().guido_offtarget_search_dev(self._h, d_guides, n_guides, pam.encode(), core_length,
+                                               core_mismatches, total_mismatches, algo, d_hits, cap,
+                                               d_count, stream))
+
+
+def pam_scan_seq(seq, pam, device=None, mode=SCAN_REGEX, stats=None):
+    """(pams_fw, pams_rv): 0-based match starts in ``seq`` -- what the two re.finditer passes of
+    guido/locus.py:182-183 return, computed on the GPU."""
+    b = seq.encode() if isinstance(seq, str) else bytes(seq)
+    n = len(b)
+    cap = max(256, n // 6)
+    st = stats if stats is not None else Stats()
+    dev = default_device() if device is None else device
+    while True:
+        fw, rv = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        nf, nr = ctypes.c_int64(), ctypes.c_int64()
+        rc = lib().guido_pam_scan_seq(b, n, pam.encode(), dev, mode, fw.ctypes.data, cap, ctypes.byref(nf),
+                                      rv.ctypes.data, cap, ctypes.byref(nr), ctypes.byref(st))
+        if rc == ERR_CAPACITY:
+            cap = max(nf.value, nr.value)
+            continue
+        check(rc)
+        return fw[:nf.value], rv[:nr.value]
+
+
+def encode_guides(protos):
+    """list of 20-nt strings -> (n,2) uint32 {hi, lo} plane words (guide position order)."""
+    protos = list(protos)
+    out = np.empty((len(protos), 2), np.uint32)
+    check(lib().guido_encode_guides("".join(protos).encode(), len(protos), out.ctypes.data))
+    return out
+
+
+def mmej_batch(windows, cuts, device=None, stats=None):
+    """windows: list of str; cuts: list of int.
+
+    Returns (tuples uint32[total] packed ls|le<<8|rs<<16|re<<24, offsets int64[n+1],
+    n_cand int32[n])."""
+    n = len(windows)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum([len(w) for w in windows], out=offsets[1:])
+    blob = "".join(windows).encode()
+    cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+    out_off = np.zeros(n + 1, np.int64)
+    n_cand = np.zeros(n, np.int32)
+    st = stats if stats is not None else Stats()
+    dev = default_device() if device is None else device
+    cap = max(1024, 512 * n)
+    while True:
+        out = np.empty(cap, np.uint32)
+        rc = lib().guido_mmej_batch(blob, offsets.ctypes.data, cuts.ctypes.data, n, dev, out.ctypes.data,
+                                    cap, out_off.ctypes.data, n_cand.ctypes.data, ctypes.byref(st))
+        if rc == ERR_CAPACITY:
+            cap = int(out_off[n])
+            continue
+        check(rc)
+        return out[:out_off[n]], out_off, n_cand

@@ -1,0 +1,419 @@
+// capi.cu -- the extern "C" entry points that touch the device (see include/guido_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "device.cuh"
+
+namespace guido {
+
+int ensure_bytes(void **p, int64_t *cap, int64_t need) {
+    if (need <= *cap) return GUIDO_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    int64_t want = std::max<int64_t>(need, 1 << 16);
+    GUIDO_CUDA(cudaMalloc(p, (size_t)want));
+    *cap = want;
+    return GUIDO_OK;
+}
+
+int ensure_pinned(DeviceState *ds, int64_t need) {
+    if (need <= ds->pinned_cap) return GUIDO_OK;
+    if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
+    ds->h_pinned = nullptr; ds->pinned_cap = 0;
+    int64_t want = std::max<int64_t>(need, 1 << 20);
+    GUIDO_CUDA(cudaMallocHost(&ds->h_pinned, (size_t)want));
+    ds->pinned_cap = want;
+    return GUIDO_OK;
+}
+
+int device_init(DeviceState *ds, int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        set_error("no CUDA device: guido_b200 has no CPU fallback");
+        return GUIDO_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return GUIDO_ERR_ARG; }
+    GUIDO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GUIDO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return GUIDO_ERR_CUDA;
+    }
+    ds->device = device;
+    ds->sm_count = prop.multiProcessorCount;
+    GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    for (auto &e : ds->ev) GUIDO_CUDA(cudaEventCreate(&e));
+    GUIDO_CUDA(cudaMalloc(&ds->d_counts, 8 * sizeof(unsigned long long)));
+    GUIDO_CUDA(cudaMalloc(&ds->d_tile_counter, 4 * sizeof(unsigned int)));
+    return GUIDO_OK;
+}
+
+void device_release(guido_image *img) {
+    DeviceState *ds = img->dev;
+    if (!ds) return;
+    if (ds->device >= 0) {
+        cudaSetDevice(ds->device);
+        if (ds->stream) cudaStreamSynchronize(ds->stream);
+        cudaFree(ds->d_planes); cudaFree(ds->d_run_start); cudaFree(ds->d_run_end); cudaFree(ds->d_run_kind);
+        cudaFree(ds->d_desc); cudaFree(ds->d_counts); cudaFree(ds->d_tile_counter);
+        cudaFree(ds->d_out[0]); cudaFree(ds->d_out[1]); cudaFree(ds->d_guides); cudaFree(ds->d_flags);
+        cudaFree(ds->d_index); cudaFree(ds->d_bucket);
+        if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
+        for (auto &e : ds->ev) if (e) cudaEventDestroy(e);
+        if (ds->stream) cudaStreamDestroy(ds->stream);
+    }
+    delete ds;
+    img->dev = nullptr;
+}
+
+static PlanesView view_of(const DeviceState *ds) {
+    PlanesView pv;
+    pv.planes = ds->d_planes; pv.blk_lo = ds->blk_lo; pv.blk_n = ds->blk_n;
+    pv.run_start = ds->d_run_start; pv.run_end = ds->d_run_end; pv.run_kind = ds->d_run_kind;
+    pv.n_runs = ds->n_runs;
+    return pv;
+}
+
+static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards) {
+    if (!img || n_shards < 1 || shard_ix < 0 || shard_ix >= n_shards) { set_error("bad shard arguments"); return GUIDO_ERR_ARG; }
+    device_release(img);
+    auto *ds = new DeviceState();
+    img->dev = ds;
+    int rc = device_init(ds, device);
+    if (rc) { device_release(img); return rc; }
+    // contiguous shards with equal block counts; a shard owns the PAM starts inside it
+    int64_t per = (img->n_blocks + n_shards - 1) / n_shards;
+    int64_t b0 = std::min<int64_t>(per * shard_ix, img->n_blocks), b1 = std::min<int64_t>(b0 + per, img->n_blocks);
+    ds->shard_lo = b0 * 64; ds->shard_hi = b1 * 64;
+    ds->blk_lo = std::max<int64_t>(b0 - 1, 0);
+    int64_t blk_hi = std::min<int64_t>(b1 + 1, img->n_blocks);
+    ds->blk_n = blk_hi - ds->blk_lo;
+    GUIDO_CUDA(cudaMalloc(&ds->d_planes, (size_t)(ds->blk_n + 1) * sizeof(ulonglong2)));
+    GUIDO_CUDA(cudaMemsetAsync(ds->d_planes + ds->blk_n, 0, sizeof(ulonglong2), ds->stream));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_planes, img->planes.data() + 2 * ds->blk_lo,
+                               (size_t)ds->blk_n * sizeof(ulonglong2), cudaMemcpyHostToDevice, ds->stream));
+    ds->n_runs = (int)img->runs.size();
+    std::vector<uint32_t> rs(ds->n_runs), re(ds->n_runs);
+    std::vector<uint8_t> rk(ds->n_runs);
+    for (int i = 0; i < ds->n_runs; i++) { rs[i] = img->runs[i].start; re[i] = img->runs[i].end; rk[i] = img->runs[i].kind; }
+    size_t nr = (size_t)std::max(ds->n_runs, 1);
+    GUIDO_CUDA(cudaMalloc(&ds->d_run_start, nr * 4));
+    GUIDO_CUDA(cudaMalloc(&ds->d_run_end, nr * 4));
+    GUIDO_CUDA(cudaMalloc(&ds->d_run_kind, nr));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_start, rs.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_end, re.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_kind, rk.data(), (size_t)ds->n_runs, cudaMemcpyHostToDevice, ds->stream));
+    GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
+    return GUIDO_OK;
+}
+
+static int need_device(guido_image *img) {
+    if (!img || !img->dev || img->dev->device < 0) {
+        set_error("image is not uploaded to a device (call guido_image_upload); there is no CPU fallback");
+        return GUIDO_ERR_CUDA;
+    }
+    GUIDO_CUDA(cudaSetDevice(img->dev->device));
+    return GUIDO_OK;
+}
+
+// run one scan, copy counts (and as many positions as fit) back to the host
+static int scan_to_host(guido_image *img, const PamSpec &pam, int mode, const ScanRange &r,
+                        uint32_t *fw, int64_t cap_fw, int64_t *n_fw, uint32_t *rv, int64_t cap_rv,
+                        int64_t *n_rv, guido_stats *stats) {
+    DeviceState *ds = img->dev;
+    int rc;
+    int64_t span = (int64_t)r.hi - (int64_t)r.lo;
+    int64_t dcap_f = std::min<int64_t>(std::max<int64_t>(cap_fw, 0), span), dcap_r = std::min<int64_t>(std::max<int64_t>(cap_rv, 0), span);
+    if ((rc = ensure_bytes(&ds->d_out[0], &ds->out_cap[0], dcap_f * 4))) return rc;
+    if ((rc = ensure_bytes(&ds->d_out[1], &ds->out_cap[1], dcap_r * 4))) return rc;
+    int launches = 0;
+    GUIDO_CUDA(cudaEventRecord(ds->ev[0], ds->stream));
+    rc = launch_pam_scan(ds, view_of(ds), pam, mode, r, (uint32_t *)ds->d_out[0], (uint64_t)dcap_f,
+                         (uint32_t *)ds->d_out[1], (uint64_t)dcap_r, ds->d_counts, ds->stream, &launches);
+    if (rc) return rc;
+    GUIDO_CUDA(cudaEventRecord(ds->ev[1], ds->stream));
+    unsigned long long counts[2];
+    GUIDO_CUDA(cudaMemcpyAsync(counts, ds->d_counts, sizeof counts, cudaMemcpyDeviceToHost, ds->stream));
+    GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
+    *n_fw = (int64_t)counts[0];
+    *n_rv = (int64_t)counts[1];
+    int64_t cf = std::min<int64_t>(*n_fw, dcap_f), cr = std::min<int64_t>(*n_rv, dcap_r);
+    if (cf) GUIDO_CUDA(cudaMemcpyAsync(fw, ds->d_out[0], (size_t)cf * 4, cudaMemcpyDeviceToHost, ds->stream));
+    if (cr) GUIDO_CUDA(cudaMemcpyAsync(rv, ds->d_out[1], (size_t)cr * 4, cudaMemcpyDeviceToHost, ds->stream));
+    GUIDO_CUDA(cudaEventRecord(ds->ev[2], ds->stream));
+    GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
+    if (stats) {
+        float k = 0, t = 0;
+        cudaEventElapsedTime(&k, ds->ev[0], ds->ev[1]);
+        cudaEventElapsedTime(&t, ds->ev[0], ds->ev[2]);
+        stats->kernel_ms = k; stats->total_ms = t; stats->n_launches = launches;
+        stats->n_sites = *n_fw + *n_rv; stats->n_pairs = 0;
+        stats->bytes_h2d = 0; stats->bytes_d2h = 16 + (cf + cr) * 4;
+    }
+    if (*n_fw > cap_fw || *n_rv > cap_rv) {
+        set_error("output capacity too small: need %lld fw / %lld rv", (long long)*n_fw, (long long)*n_rv);
+        return GUIDO_ERR_CAPACITY;
+    }
+    return GUIDO_OK;
+}
+
+}  // namespace guido
+
+using namespace guido;
+
+extern "C" {
+
+int guido_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ok++;
+    }
+    return ok;
+}
+
+int guido_image_upload(guido_image *img, int32_t device, int32_t shard_ix, int32_t n_shards) {
+    return upload_impl(img, device, shard_ix, n_shards);
+}
+
+int guido_image_get_info(const guido_image *img, guido_image_info *info) {
+    if (!img || !info) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    info->n_contigs = (int64_t)img->contigs.size();
+    info->total_bases = img->total_bases;
+    info->padded_bases = img->padded_bases;
+    info->n_runs = (int64_t)img->runs.size();
+    info->device = img->dev ? img->dev->device : -1;
+    info->shard_lo = img->dev ? img->dev->shard_lo : 0;
+    info->shard_hi = img->dev ? img->dev->shard_hi : img->padded_bases;
+    info->reserved = 0;
+    return GUIDO_OK;
+}
+
+int guido_pam_scan_genome(guido_image *img, const char *pam, int32_t mode, uint32_t *fw, int64_t cap_fw,
+                          int64_t *n_fw, uint32_t *rv, int64_t cap_rv, int64_t *n_rv, guido_stats *stats) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    PamSpec ps;
+    if ((rc = parse_pam(pam, &ps))) return rc;
+    if (mode < GUIDO_SCAN_REGEX || mode > GUIDO_SCAN_STRICT) { set_error("bad scan mode %d", mode); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    return scan_to_host(img, ps, mode, r, fw, cap_fw, n_fw, rv, cap_rv, n_rv, stats);
+}
+
+int guido_pam_scan_genome_dev(guido_image *img, const char *pam, int32_t mode, void *d_fw, int64_t cap_fw,
+                              void *d_rv, int64_t cap_rv, void *d_counts, void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    PamSpec ps;
+    if ((rc = parse_pam(pam, &ps))) return rc;
+    if (mode < GUIDO_SCAN_REGEX || mode > GUIDO_SCAN_STRICT) { set_error("bad scan mode %d", mode); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    return launch_pam_scan(ds, view_of(ds), ps, mode, r, (uint32_t *)d_fw, (uint64_t)cap_fw, (uint32_t *)d_rv,
+                           (uint64_t)cap_rv, (unsigned long long *)d_counts, (cudaStream_t)stream, nullptr);
+}
+
+int guido_pam_scan_region(guido_image *img, int64_t contig_ix, int64_t start0, int64_t end0, const char *pam,
+                          int32_t mode, int32_t *fw, int64_t cap_fw, int64_t *n_fw, int32_t *rv,
+                          int64_t cap_rv, int64_t *n_rv, guido_stats *stats) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    PamSpec ps;
+    if ((rc = parse_pam(pam, &ps))) return rc;
+    if (contig_ix < 0 || contig_ix >= (int64_t)img->contigs.size()) { set_error("contig index out of range"); return GUIDO_ERR_ARG; }
+    const Contig &c = img->contigs[(size_t)contig_ix];
+    if (start0 < 0 || end0 < start0 || end0 > c.len) { set_error("region outside contig"); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    int64_t lo = c.goff + start0, hi = c.goff + end0;
+    if (lo < ds->shard_lo || hi > ds->shard_hi) { set_error("region is outside this handle's shard"); return GUIDO_ERR_ARG; }
+    ScanRange r{(uint32_t)lo, (uint32_t)hi, (uint32_t)hi, (uint32_t)lo};
+    return scan_to_host(img, ps, mode, r, (uint32_t *)fw, cap_fw, n_fw, (uint32_t *)rv, cap_rv, n_rv, stats);
+}
+
+int guido_pam_scan_seq(const char *seq, int64_t n, const char *pam, int32_t device, int32_t mode,
+                       int32_t *fw, int64_t cap_fw, int64_t *n_fw, int32_t *rv, int64_t cap_rv,
+                       int64_t *n_rv, guido_stats *stats) {
+    PamSpec ps;
+    int rc = parse_pam(pam, &ps);
+    if (rc) return rc;
+    if (n < 0 || !seq) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    guido_image *img = nullptr;
+    const char *name = "seq";
+    if ((rc = guido_image_from_seqs(1, &name, &seq, &n, &img))) return rc;
+    rc = guido_image_upload(img, device, 0, 1);
+    if (rc == GUIDO_OK)
+        rc = guido_pam_scan_region(img, 0, 0, n, pam, mode, fw, cap_fw, n_fw, rv, cap_rv, n_rv, stats);
+    if (stats && rc == GUIDO_OK) stats->bytes_h2d = img->dev->blk_n * 16;
+    guido_image_free(img);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------- off-targets
+
+static int make_ot_params(const char *pam, int core_len, int core_mm, int total_mm, bool raw, OtParams *op) {
+    int rc = parse_pam(pam, &op->pam);
+    if (rc) return rc;
+    const int nN = op->pam.n_ambiguous;
+    // same argument checks, same messages as guido/off_targets.py:141-149
+    if (core_mm + nN > 3) {
+        set_error("The value for the parameter core_mismatches is not valid: %d", core_mm);
+        return GUIDO_ERR_ARG;
+    }
+    if (core_mm > total_mm) {
+        set_error("The value for core_mismatches cannot be greater than total_mismatches: %d > %d", core_mm, total_mm);
+        return GUIDO_ERR_ARG;
+    }
+    if (core_len < 0 || core_mm < 0) { set_error("negative core arguments"); return GUIDO_ERR_ARG; }
+    // bowtie seed = first core_len + P read bases = PAM + PAM-proximal protospacer bases
+    int cl = std::min(core_len, kProto);
+    op->core_len = cl;
+    uint32_t proto_mask = (1u << kProto) - 1;
+    op->core_mask = cl ? (((1u << cl) - 1) << (kProto - cl)) : 0;
+    op->cmp_mask = proto_mask;
+    if (raw) {
+        op->core_mask |= op->pam.fixed_mask << kProto;
+        op->cmp_mask |= op->pam.fixed_mask << kProto;
+    }
+    op->core_max = core_mm;
+    op->total_max = total_mm + 1 - nN;
+    op->raw_mode = raw ? 1 : 0;
+    return GUIDO_OK;
+}
+
+int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides, const char *pam,
+                               int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                               void *d_hits, int64_t cap, void *d_count, void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    OtParams op;
+    if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, false, &op))) return rc;
+    DeviceState *ds = img->dev;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    GUIDO_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    if (algo == GUIDO_OT_INDEX)
+        return launch_ot_index(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
+                               (uint64_t)cap, (unsigned long long *)d_count, nullptr, st, nullptr);
+    return launch_ot_scan(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
+                          (uint64_t)cap, (unsigned long long *)d_count, nullptr, nullptr, st, nullptr);
+}
+
+int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                           int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                           guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                           guido_stats *stats) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    OtParams op;
+    if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, false, &op))) return rc;
+    if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    cudaStream_t st = ds->stream;
+    std::vector<uint32_t> enc((size_t)(2 * n_guides));
+    if ((rc = guido_encode_guides(protos, n_guides, enc.data()))) return rc;
+    if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, std::max<int64_t>(8 * n_guides, 8)))) return rc;
+    const bool use_index = algo == GUIDO_OT_INDEX;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    int launches = 0;
+    GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, enc.data(), (size_t)(8 * n_guides), cudaMemcpyHostToDevice, st));
+    int64_t dcap = std::max<int64_t>(std::max<int64_t>(cap, 64 * n_guides), 1 << 16);
+    unsigned long long found = 0, sites = 0;
+    float kernel_ms = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = ensure_bytes(&ds->d_out[0], &ds->out_cap[0], dcap * (int64_t)sizeof(guido_ot_hit)))) return rc;
+        GUIDO_CUDA(cudaMemsetAsync(ds->d_counts, 0, 4 * sizeof(unsigned long long), st));
+        GUIDO_CUDA(cudaEventRecord(ds->ev[1], st));
+        if (use_index)
+            rc = launch_ot_index(ds, view_of(ds), op, r, (const uint2 *)ds->d_guides, n_guides,
+                                 (guido_ot_hit *)ds->d_out[0], (uint64_t)dcap, ds->d_counts, ds->d_counts + 1, st, &launches);
+        else
+            rc = launch_ot_scan(ds, view_of(ds), op, r, (const uint2 *)ds->d_guides, n_guides,
+                                (guido_ot_hit *)ds->d_out[0], (uint64_t)dcap, ds->d_counts, nullptr,
+                                ds->d_counts + 1, st, &launches);
+        if (rc) return rc;
+        GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
+        unsigned long long c2[2];
+        GUIDO_CUDA(cudaMemcpyAsync(c2, ds->d_counts, sizeof c2, cudaMemcpyDeviceToHost, st));
+        GUIDO_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
+        kernel_ms += ms;
+        found = c2[0]; sites = c2[1];
+        if ((int64_t)found <= dcap) break;
+        dcap = (int64_t)found;  // exact size known now: one more pass
+    }
+    *n_hits = (int64_t)found;
+    std::vector<guido_ot_hit> tmp((size_t)found);
+    if (found) GUIDO_CUDA(cudaMemcpyAsync(tmp.data(), ds->d_out[0], (size_t)found * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
+    GUIDO_CUDA(cudaEventRecord(ds->ev[3], st));
+    GUIDO_CUDA(cudaStreamSynchronize(st));
+    std::sort(tmp.begin(), tmp.end(), [](const guido_ot_hit &a, const guido_ot_hit &b) {
+        if (a.guide != b.guide) return a.guide < b.guide;
+        if (a.gpos != b.gpos) return a.gpos < b.gpos;
+        return (a.hi >> 31) < (b.hi >> 31);
+    });
+    int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
+    if (ncopy) memcpy(hits, tmp.data(), (size_t)ncopy * sizeof(guido_ot_hit));
+    int64_t d2h = 16 + (int64_t)found * 16, h2d = 8 * n_guides;
+
+    if (raw_flags) {
+        // key presence (off_targets.py:183-184): any raw bowtie alignment, PAM mismatches allowed
+        // inside the seed budget.  A valid hit is a raw alignment, so only guides without one
+        // need the relaxed all-window pass.
+        memset(raw_flags, 0, (size_t)n_guides);
+        for (auto &h : tmp) raw_flags[h.guide] = 1;
+        std::vector<int64_t> todo;
+        for (int64_t g = 0; g < n_guides; g++) if (!raw_flags[g]) todo.push_back(g);
+        if (!todo.empty()) {
+            OtParams rp;
+            if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, true, &rp))) return rc;
+            std::vector<uint32_t> sub(2 * todo.size());
+            for (size_t i = 0; i < todo.size(); i++) {
+                uint32_t hi = enc[(size_t)(2 * todo[i])], lo = enc[(size_t)(2 * todo[i] + 1)];
+                for (int k = 0; k < rp.pam.len; k++)
+                    if (rp.pam.fixed_mask & (1u << k)) {
+                        hi |= (uint32_t)(rp.pam.code[k] >> 1) << (kProto + k);
+                        lo |= (uint32_t)(rp.pam.code[k] & 1) << (kProto + k);
+                    }
+                sub[2 * i] = hi; sub[2 * i + 1] = lo;
+            }
+            if ((rc = ensure_bytes(&ds->d_flags, &ds->flags_cap, (int64_t)todo.size()))) return rc;
+            GUIDO_CUDA(cudaMemsetAsync(ds->d_flags, 0, todo.size(), st));
+            GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, sub.data(), sub.size() * 4, cudaMemcpyHostToDevice, st));
+            GUIDO_CUDA(cudaEventRecord(ds->ev[1], st));
+            rc = launch_ot_scan(ds, view_of(ds), rp, r, (const uint2 *)ds->d_guides, (int64_t)todo.size(), nullptr, 0,
+                                ds->d_counts, (uint8_t *)ds->d_flags, nullptr, st, &launches);
+            if (rc) return rc;
+            GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
+            std::vector<uint8_t> fl(todo.size());
+            GUIDO_CUDA(cudaMemcpyAsync(fl.data(), ds->d_flags, todo.size(), cudaMemcpyDeviceToHost, st));
+            GUIDO_CUDA(cudaStreamSynchronize(st));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
+            kernel_ms += ms;
+            for (size_t i = 0; i < todo.size(); i++) raw_flags[todo[i]] = fl[i];
+            h2d += (int64_t)sub.size() * 4; d2h += (int64_t)todo.size();
+        }
+    }
+    if (stats) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ds->ev[0], ds->ev[3]);
+        stats->kernel_ms = kernel_ms; stats->total_ms = t; stats->n_launches = launches;
+        stats->n_sites = (int64_t)sites;
+        stats->n_pairs = use_index ? 0 : (int64_t)sites * n_guides;
+        stats->bytes_h2d = h2d; stats->bytes_d2h = d2h;
+    }
+    if ((int64_t)found > cap) {
+        set_error("output capacity too small: need %lld hits", (long long)found);
+        return GUIDO_ERR_CAPACITY;
+    }
+    return GUIDO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// device.cuh -- device-side state of an uploaded genome image and helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "internal.h"
+
+namespace guido {
+
+#define GUIDO_CUDA(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                      cudaGetErrorString(e_));                                             \
+            return GUIDO_ERR_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+struct DeviceState {
+    int device = -1;
+    int sm_count = 0;
+    int64_t blk_lo = 0;  // first resident block (global block index), includes the halo
+    int64_t blk_n = 0;   // resident blocks (+1 spare at the end so `next` loads stay in bounds)
+    ulonglong2 *d_planes = nullptr;
+    uint32_t *d_run_start = nullptr, *d_run_end = nullptr;
+    uint8_t *d_run_kind = nullptr;
+    int n_runs = 0;
+    int64_t shard_lo = 0, shard_hi = 0;  // owned global positions (PAM starts), 64-aligned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // scratch (grown on demand, reused between calls)
+    unsigned long long *d_desc = nullptr;  int64_t desc_cap = 0;     // look-back descriptors
+    unsigned long long *d_counts = nullptr;                          // 8 x u64 counters
+    unsigned int *d_tile_counter = nullptr;
+    void *d_out[2] = {nullptr, nullptr};   int64_t out_cap[2] = {0, 0};  // bytes
+    void *d_guides = nullptr;              int64_t guides_cap = 0;       // bytes
+    void *d_flags = nullptr;               int64_t flags_cap = 0;
+    void *d_index = nullptr;               int64_t index_cap = 0;        // OT seed index entries
+    void *d_bucket = nullptr;              int64_t bucket_cap = 0;       // OT seed index offsets
+    void *h_pinned = nullptr;              int64_t pinned_cap = 0;
+};
+
+int device_init(DeviceState *ds, int device);
+int ensure_bytes(void **p, int64_t *cap, int64_t need);
+int ensure_pinned(DeviceState *ds, int64_t need);
+
+// launch description of one scan over global PAM-start positions [lo, hi)
+struct ScanRange {
+    uint32_t lo, hi;     // PAM start p must satisfy lo <= p < hi
+    uint32_t limit;      // and p + P <= limit
+    uint32_t out_base;   // subtracted from reported positions
+};
+
+struct PlanesView {
+    const ulonglong2 *planes;  // planes[b - blk_lo], valid for blk_lo <= b < blk_lo + blk_n
+    int64_t blk_lo;
+    int64_t blk_n;
+    const uint32_t *run_start, *run_end;
+    const uint8_t *run_kind;
+    int n_runs;
+};
+
+int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, int mode,
+                    const ScanRange &r, uint32_t *d_fw, uint64_t cap_fw, uint32_t *d_rv,
+                    uint64_t cap_rv, unsigned long long *d_counts, cudaStream_t stream,
+                    int *n_launches);
+
+struct OtParams {
+    PamSpec pam;
+    uint32_t core_mask;   // compare positions counted against core_max (incl. fixed PAM in raw mode)
+    uint32_t cmp_mask;    // compare positions at all
+    int32_t core_max, total_max;
+    int32_t core_len;
+    int32_t raw_mode;     // 0: PAM-exact sites -> hit records; 1: every window -> per-guide flags
+};
+
+int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                   const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                   unsigned long long *d_count, uint8_t *d_flags, unsigned long long *d_site_count,
+                   cudaStream_t stream, int *n_launches);
+
+int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                    unsigned long long *d_count, unsigned long long *d_site_count,
+                    cudaStream_t stream, int *n_launches);
+
+}  // namespace guido

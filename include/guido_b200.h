@@ -1,0 +1,170 @@
+/*
+ * guido_b200.h -- C-ABI of the B200-native guido hot path (libguido_b200.so).
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types cross this boundary.  The reference
+ * (nkran/guido, pure Python) has no FFI of its own: the boundary is the set of pure functions its
+ * public API calls on the hot path.  Each entry point names the reference interface it sits under
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - every function returns GUIDO_OK (0) or a GUIDO_ERR_* code; guido_last_error() gives the text
+ *    (thread-local).  GUIDO_ERR_ARG maps to the ValueError the reference raises for bad arguments,
+ *    GUIDO_ERR_PAM to the KeyError of guido/locus.py:178 for a letter outside the IUPAC table.
+ *  - output buffers are caller-allocated with a capacity; counts are always exact, and
+ *    GUIDO_ERR_CAPACITY means "call again with at least *n elements".
+ *  - positions are 0-based.  "global" positions index the concatenated genome coordinate of an
+ *    image (see guido_image_contig for the per-contig offsets).
+ *  - there is NO CPU fallback: every scan/search entry point fails with GUIDO_ERR_CUDA when no
+ *    sm_100 device is usable.
+ *  - a handle may be used from one thread at a time.
+ */
+#ifndef GUIDO_B200_H
+#define GUIDO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GUIDO_OK 0
+#define GUIDO_ERR_ARG 1
+#define GUIDO_ERR_IO 2
+#define GUIDO_ERR_CUDA 3
+#define GUIDO_ERR_CAPACITY 4
+#define GUIDO_ERR_PAM 5
+#define GUIDO_ERR_NOMEM 6
+
+/* which windows a PAM scan keeps */
+#define GUIDO_SCAN_REGEX 0  /* every PAM match, like re.finditer at guido/locus.py:182-183          */
+#define GUIDO_SCAN_GUIDE 1  /* + the 20+P window lies inside its contig and survives the reference's
+                               'N' filter (locus.py:208-210,316): '+' drops literal N only, '-' drops
+                               any non-ACGT letter (helpers.py:24-26 turns them into N)            */
+#define GUIDO_SCAN_STRICT 2 /* + window free of ANY non-ACGT letter on both strands (bowtie's rule
+                               for reference positions, used for off-target sites)                  */
+
+/* off-target search algorithm */
+#define GUIDO_OT_AUTO 0
+#define GUIDO_OT_SCAN 1  /* brute-force: every PAM-valid window against every guide (XOR + popc)     */
+#define GUIDO_OT_INDEX 2 /* guide-side seed index: windows look up their core k-mer                  */
+
+typedef struct guido_image guido_image;
+
+typedef struct {
+    int64_t n_contigs;
+    int64_t total_bases;  /* sum of contig lengths                                   */
+    int64_t padded_bases; /* extent of the global coordinate (contigs + pad runs)    */
+    int64_t n_runs;       /* non-ACGT runs incl. the pad runs between contigs        */
+    int64_t shard_lo;     /* global range whose windows this handle owns on device   */
+    int64_t shard_hi;
+    int32_t device;       /* -1 while host-only                                      */
+    int32_t reserved;
+} guido_image_info;
+
+/* one off-target hit, 16 bytes.  hi/lo hold the genomic window in GUIDE orientation as two bit
+ * planes (base code A=0,C=1,G=2,T=3; lo = code&1, hi = code>>1): bit i <-> guide position i+1
+ * (bits 0..19 protospacer, bits 20.. the genomic PAM).  Bit 31 of `hi` is the guido strand
+ * (0 '+', 1 '-').  gpos is the global 0-based position of the window's leftmost base on the
+ * forward strand (what bowtie prints as offset, plus the contig's global offset). */
+typedef struct {
+    uint32_t guide;
+    uint32_t gpos;
+    uint32_t hi;
+    uint32_t lo;
+} guido_ot_hit;
+
+typedef struct {
+    double kernel_ms;   /* device time of the dominant kernel(s), CUDA events           */
+    double total_ms;    /* device time of the whole call incl. copies                   */
+    int64_t n_sites;    /* windows examined (PAM-valid, both strands)                   */
+    int64_t n_pairs;    /* (window, guide) pairs compared or index entries visited      */
+    int64_t n_launches; /* kernels launched by this call                                */
+    int64_t bytes_h2d;
+    int64_t bytes_d2h;
+} guido_stats;
+
+const char *guido_last_error(void);
+int guido_version(void);
+/* number of usable sm_100 devices (0 when there is none) */
+int guido_device_count(void);
+
+/* ---- genome image: replaces `bowtie-build` in Genome.build (guido/genome.py:156-171) --------- */
+/* FASTA -> two bit planes (1 bit/base each, interleaved per 64 bases) + sorted list of non-ACGT
+ * runs + contig table.  Sequence names are the header up to the first whitespace.            */
+int guido_image_from_fasta(const char *fasta_path, guido_image **out);
+int guido_image_from_seqs(int32_t n, const char *const *names, const char *const *seqs,
+                          const int64_t *lens, guido_image **out);
+/* seeded synthetic genome (uniform ACGT; n_frac of each contig covered by N runs of
+ * run_min..run_max bases).  Bench / test utility; same bytes on every platform. */
+int guido_image_synth(int32_t n, const char *const *names, const int64_t *lens, uint64_t seed,
+                      double n_frac, int64_t run_min, int64_t run_max, guido_image **out);
+int guido_image_save(const guido_image *img, const char *path);
+int guido_image_load(const char *path, guido_image **out);
+int guido_image_free(guido_image *img);
+/* copy shard `shard_ix` of `n_shards` (contiguous, equal block counts, +1 block halo each side)
+ * to HBM of `device`; afterwards scans/searches on this handle cover that shard only. */
+int guido_image_upload(guido_image *img, int32_t device, int32_t shard_ix, int32_t n_shards);
+int guido_image_get_info(const guido_image *img, guido_image_info *info);
+int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t name_cap,
+                       int64_t *len, int64_t *global_offset);
+/* decode bases [start0, start0+n) of contig ix to upper-case letters (host copy of the image;
+ * non-ACGT letters come back as stored in the run list).  Under Genome.sequence / the FASTA
+ * fetch of guido/locus.py:773,853. */
+int guido_image_fetch(const guido_image *img, int64_t contig_ix, int64_t start0, int64_t n,
+                      char *out);
+
+/* ---- PAM scan: under Locus._find_guides_in_interval (guido/locus.py:158-183) ------------------ */
+/* host string in, match starts out (ascending; relative to seq[0]); `device` is the CUDA device. */
+int guido_pam_scan_seq(const char *seq, int64_t n, const char *pam, int32_t device, int32_t mode,
+                       int32_t *fw, int64_t cap_fw, int64_t *n_fw,
+                       int32_t *rv, int64_t cap_rv, int64_t *n_rv, guido_stats *stats);
+/* same over bases [start0,end0) of a contig of an uploaded image, no sequence upload */
+int guido_pam_scan_region(guido_image *img, int64_t contig_ix, int64_t start0, int64_t end0,
+                          const char *pam, int32_t mode,
+                          int32_t *fw, int64_t cap_fw, int64_t *n_fw,
+                          int32_t *rv, int64_t cap_rv, int64_t *n_rv, guido_stats *stats);
+/* whole shard, global u32 positions into host buffers */
+int guido_pam_scan_genome(guido_image *img, const char *pam, int32_t mode,
+                          uint32_t *fw, int64_t cap_fw, int64_t *n_fw,
+                          uint32_t *rv, int64_t cap_rv, int64_t *n_rv, guido_stats *stats);
+/* whole shard, results stay in HBM: d_fw/d_rv are device pointers (u32 each), d_counts a device
+ * pointer to 2 x u64 {n_fw, n_rv}; `stream` is a cudaStream_t (NULL = default).  Asynchronous. */
+int guido_pam_scan_genome_dev(guido_image *img, const char *pam, int32_t mode,
+                              void *d_fw, int64_t cap_fw, void *d_rv, int64_t cap_rv,
+                              void *d_counts, void *stream);
+
+/* ---- off-target search: under run_bowtie (guido/off_targets.py:89-227) ------------------------ */
+/* protos: n_guides * 20 letters (the 20-nt protospacers, guide orientation, A/C/G/T).
+ * Reports every window w (both strands, inside one contig, free of non-ACGT) whose PAM matches
+ * the fixed letters of `pam` exactly and whose protospacer has <= core_mm mismatches in the
+ * core_len PAM-proximal bases and <= total_mm + 1 - (#N-like letters of pam) in total -- i.e. the
+ * alignments bowtie -n/-l/-e reports that survive guido's PAM filter (off_targets.py:169-198).
+ * raw_flags (n_guides bytes, may be NULL) receives 1 for every guide with at least one RAW bowtie
+ * alignment (PAM mismatches allowed inside the seed budget): the reference creates the guide's
+ * dict key from those (off_targets.py:183-184).  Hits come back sorted by (guide, gpos, strand). */
+int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                           int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                           guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                           guido_stats *stats);
+/* device-resident variant: d_guides = n_guides x {u32 hi, u32 lo} plane words (guide position
+ * order, see guido_ot_hit), d_hits = cap x guido_ot_hit, d_count = 1 x u64; unsorted; async. */
+int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides,
+                               const char *pam, int32_t core_len, int32_t core_mm, int32_t total_mm,
+                               int32_t algo, void *d_hits, int64_t cap, void *d_count, void *stream);
+/* encode n x 20 letters into the {hi, lo} plane words the _dev call takes (host helper) */
+int guido_encode_guides(const char *protos, int64_t n_guides, uint32_t *out_hi_lo);
+
+/* ---- MMEJ: under generate_mmej_patterns (guido/mmej.py:8-64) ---------------------------------- */
+/* windows: concatenated upper-case letters, offsets[n+1]; cuts[n] relative cut positions.
+ * out_tuples receives the kept candidates per window, in the reference's order, packed
+ * left_start | left_end<<8 | right_start<<16 | right_end<<24; out_offsets[n+1] delimits them.
+ * n_cand[n] (may be NULL) = candidates before nested-pattern elimination (0 => the reference
+ * returns None).  Each side of the cut may be at most 255 letters. */
+int guido_mmej_batch(const char *windows, const int64_t *offsets, const int32_t *cuts, int64_t n,
+                     int32_t device, uint32_t *out_tuples, int64_t cap, int64_t *out_offsets,
+                     int32_t *n_cand, guido_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUIDO_B200_H */

@@ -1,0 +1,175 @@
+"""GPU parity of the raw kernels against the CPU oracle (through the C-ABI, via ctypes)."""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+PAMS = ["NGG", "NAG", "TTTV", "NNGRRT", "YTN", "N", "GG", "NNNNGATT"]
+
+
+@pytest.mark.parametrize("pam", PAMS)
+def test_pam_scan_seq_matches_regex_oracle(native, oracle, pam):
+    contigs = util.synthetic_contigs(11, [5000], n_runs=4, iupac=6)
+    seq = contigs[0][1]
+    fw, rv = native.pam_scan_seq(seq, pam)
+    ofw, orv = oracle.pam_scan(seq, pam)
+    assert np.array_equal(fw, ofw) and np.array_equal(rv, orv)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 22, 23, 63, 64, 65, 127, 128, 129, 16383, 16384, 16385, 40000])
+def test_pam_scan_seq_sizes(native, oracle, n):
+    rng = np.random.default_rng(n)
+    seq = util.random_dna(rng, n)
+    for pam in ("NGG", "GG", "TTTV"):
+        fw, rv = native.pam_scan_seq(seq, pam)
+        ofw, orv = oracle.pam_scan(seq, pam)
+        assert np.array_equal(fw, ofw) and np.array_equal(rv, orv), (n, pam)
+
+
+def test_pam_scan_bad_letter(native):
+    with pytest.raises(KeyError):
+        native.pam_scan_seq("ACGTACGT", "NGX")
+
+
+def test_pam_scan_dense_tiles(native, oracle):
+    # all-G sequence: every position matches NGG -> exercises the unstaged (dense) write path
+    seq = "G" * 50000
+    fw, rv = native.pam_scan_seq(seq, "NGG")
+    ofw, orv = oracle.pam_scan(seq, "NGG")
+    assert np.array_equal(fw, ofw) and np.array_equal(rv, orv)
+    seq = "C" * 33000 + "G" * 33000
+    fw, rv = native.pam_scan_seq(seq, "NGG")
+    ofw, orv = oracle.pam_scan(seq, "NGG")
+    assert np.array_equal(fw, ofw) and np.array_equal(rv, orv)
+
+
+def _expected_genome_scan(oracle, contigs, offsets, pam, mode):
+    """oracle positions -> global coordinates, with the mode's window filter applied on host"""
+    P = len(pam)
+    efw, erv = [], []
+    for (name, seq), goff in zip(contigs, offsets):
+        S = seq.upper()
+        fw, rv = oracle.pam_scan(S, pam)
+        for p in fw.tolist():
+            if mode:
+                w = S[p - 20:p + P] if p >= 20 else ""
+                if len(w) != 20 + P:
+                    continue
+                if mode == 1 and "N" in w:
+                    continue
+                if mode == 2 and set(w) - set("ACGT"):
+                    continue
+            efw.append(goff + p)
+        for p in rv.tolist():
+            if mode:
+                w = S[p:p + P + 20]
+                if len(w) != 20 + P or set(w) - set("ACGT"):
+                    continue
+            erv.append(goff + p)
+    return np.array(efw, np.uint32), np.array(erv, np.uint32)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("pam", ["NGG", "TTTV", "NAA"])
+def test_pam_scan_genome_modes(native, oracle, pam, mode):
+    contigs = util.synthetic_contigs(5, [30000, 777, 64, 20001, 10], n_runs=5, iupac=8)
+    img = native.Image.from_seqs(contigs).upload()
+    fw, rv = img.pam_scan_genome(pam, mode)
+    efw, erv = _expected_genome_scan(oracle, contigs, [c[2] for c in img.contigs], pam, mode)
+    assert np.array_equal(fw, efw)
+    assert np.array_equal(rv, erv)
+
+
+def test_pam_scan_region_equals_seq(native, oracle):
+    contigs = util.synthetic_contigs(6, [50000, 3000], n_runs=4)
+    img = native.Image.from_seqs(contigs).upload()
+    for ci, a, b in [(0, 0, 50000), (0, 1234, 40001), (0, 49990, 50000), (1, 5, 5), (1, 100, 164), (0, 16384, 32768)]:
+        fw, rv = img.pam_scan_region(ci, a, b, "NGG")
+        ofw, orv = oracle.pam_scan(contigs[ci][1][a:b], "NGG")
+        assert np.array_equal(fw, ofw) and np.array_equal(rv, orv), (ci, a, b)
+
+
+def test_pam_scan_sharded_union(native):
+    contigs = util.synthetic_contigs(8, [70000, 30000], n_runs=3)
+    whole = native.Image.from_seqs(contigs).upload()
+    fw, rv = whole.pam_scan_genome("NGG", 1)
+    for n_shards in (2, 3, 8):
+        parts = [native.Image.from_seqs(contigs).upload(shard_ix=i, n_shards=n_shards).pam_scan_genome("NGG", 1)
+                 for i in range(n_shards)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), fw)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), rv)
+
+
+def _protos_from_genome(rng, contigs, n, mutate=3):
+    """guides sampled from NGG sites of the genome, with a few random substitutions"""
+    out = []
+    seqs = [s.upper() for _, s in contigs]
+    while len(out) < n:
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        if len(s) < 40:
+            continue
+        p = int(rng.integers(0, len(s) - 23))
+        w = s[p:p + 20]
+        if set(w) - set("ACGT"):
+            continue
+        w = list(w)
+        for _ in range(int(rng.integers(0, mutate + 1))):
+            w[int(rng.integers(0, 20))] = "ACGT"[int(rng.integers(0, 4))]
+        out.append("".join(w))
+    return out
+
+
+@pytest.mark.parametrize("pam,kw", [
+    ("NGG", {}),
+    ("NGG", dict(core_length=10, core_mismatches=2, total_mismatches=3)),
+    ("NGG", dict(core_length=12, core_mismatches=1, total_mismatches=5)),
+    ("NGG", dict(core_length=10, core_mismatches=0, total_mismatches=0)),
+    ("NAG", {}),
+    ("NRG", dict(core_mismatches=1)),
+    ("TGG", dict(core_mismatches=3, total_mismatches=4)),
+])
+def test_offtarget_scan_matches_oracle(native, oracle, pam, kw):
+    contigs = util.synthetic_contigs(21, [60000, 25000, 300], n_runs=4, iupac=5)
+    rng = np.random.default_rng(3)
+    protos = _protos_from_genome(rng, contigs, 60)
+    img = native.Image.from_seqs(contigs).upload()
+    hits, flags = img.offtarget_search(protos, pam=pam, algo=native.OT_SCAN, **kw)
+    valid, keys = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
+    assert util.gpu_hit_set(img, hits) == valid
+    assert len(hits) == len(valid)
+    assert set(np.nonzero(flags)[0].tolist()) == keys
+
+
+def test_offtarget_hit_payload(native, oracle):
+    """hi/lo planes of a hit decode to the genomic 23-mer in guide orientation"""
+    contigs = util.synthetic_contigs(22, [40000], n_runs=2)
+    rng = np.random.default_rng(4)
+    protos = _protos_from_genome(rng, contigs, 40, mutate=2)
+    img = native.Image.from_seqs(contigs).upload()
+    hits, _ = img.offtarget_search(protos, algo=native.OT_SCAN)
+    assert len(hits) > 0
+    S = contigs[0][1].upper()
+    ix, off = img.locate(hits["gpos"])
+    for h, o in zip(hits, off):
+        w = S[int(o):int(o) + 23]
+        if int(h["hi"]) >> 31:
+            w = oracle.rev_comp(w)
+        dec = "".join("ACGT"[((int(h["lo"]) >> i) & 1) | (((int(h["hi"]) >> i) & 1) << 1)] for i in range(23))
+        assert dec == w
+
+
+def test_offtarget_sharded_union(native):
+    contigs = util.synthetic_contigs(23, [50000, 50000], n_runs=3)
+    rng = np.random.default_rng(5)
+    protos = _protos_from_genome(rng, contigs, 50)
+    whole, _ = native.Image.from_seqs(contigs).upload().offtarget_search(protos, algo=native.OT_SCAN)
+    parts = []
+    for i in range(4):
+        h, _ = native.Image.from_seqs(contigs).upload(shard_ix=i, n_shards=4).offtarget_search(
+            protos, algo=native.OT_SCAN, want_raw_flags=False)
+        parts.append(h)
+    merged = np.concatenate(parts)
+    merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+    assert np.array_equal(merged, whole)
