@@ -54,6 +54,7 @@ _SIGNATURES = {
     "guido_image_get_info": (ctypes.c_int, [_vp, _P(ImageInfo)]),
     "guido_image_contig": (ctypes.c_int, [_vp, _i64, _cp, _i64, _P(_i64), _P(_i64)]),
     "guido_image_fetch": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp]),
+    "guido_image_fetch_windows": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "guido_pam_scan_seq": (ctypes.c_int, [_cp, _i64, _cp, _i32, _i32, _vp, _i64, _P(_i64), _vp, _i64,
                                           _P(_i64), _P(Stats)]),
     "guido_pam_scan_region": (ctypes.c_int, [_vp, _i64, _i64, _i64, _cp, _i32, _vp, _i64, _P(_i64),
@@ -223,6 +224,13 @@ class Image:
         buf = np.empty(n, dtype=np.uint8)
         check(lib().guido_image_fetch(self._h, contig_ix, start0, n, buf.ctypes.data))
         return buf.tobytes().decode()
+
+    def fetch_windows(self, gpos, width):
+        """(n, width) uint8 array of letters for windows starting at global positions gpos."""
+        gpos = np.ascontiguousarray(gpos, dtype=np.int64)
+        out = np.empty((len(gpos), width), np.uint8)
+        check(lib().guido_image_fetch_windows(self._h, gpos.ctypes.data, len(gpos), width, out.ctypes.data))
+        return out
 
     # ---- PAM scan ---------------------------------------------------------------------
     def pam_scan_genome(self, pam, mode=SCAN_GUIDE, stats=None, cap_hint=None):

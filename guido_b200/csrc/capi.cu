@@ -259,6 +259,15 @@ static int make_ot_params(const char *pam, int core_len, int core_mm, int total_
     int rc = parse_pam(pam, &op->pam);
     if (rc) return rc;
     const int nN = op->pam.n_ambiguous;
+    // In the bowtie read every non-ACGT PAM letter is an 'N' (helpers.py:24-26) and guido only
+    // rejects mismatches at the A/C/G/T letters (off_targets.py:169-171), so for the off-target
+    // site scan an IUPAC letter such as R constrains nothing: treat it as N.
+    for (int i = 0; i < op->pam.len; i++)
+        if (!(op->pam.fixed_mask & (1u << i))) op->pam.fw[i] = 15;
+    for (int i = 0; i < op->pam.len; i++) {
+        int s = op->pam.fw[op->pam.len - 1 - i];
+        op->pam.rv[i] = (uint8_t)(((s & 1) << 3) | ((s & 2) << 1) | ((s & 4) >> 1) | ((s & 8) >> 3));
+    }
     // same argument checks, same messages as guido/off_targets.py:141-149
     if (core_mm + nN > 3) {
         set_error("The value for the parameter core_mismatches is not valid: %d", core_mm);

@@ -429,6 +429,27 @@ int guido_image_fetch(const guido_image *img, int64_t ix, int64_t start0, int64_
     return GUIDO_OK;
 }
 
+int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64_t n, int32_t width, char *out) {
+    if (!img || width < 0 || n < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    static const char L[4] = {'A', 'C', 'G', 'T'};
+    for (int64_t w = 0; w < n; w++) {
+        char *o = out + w * width;
+        int64_t a = gpos[w], b = a + width;
+        for (int64_t g = a; g < b; g++) {
+            if (g < 0 || g >= img->padded_bases) { o[g - a] = 'N'; continue; }
+            uint64_t lo = img->planes[(size_t)(2 * (g >> 6))], hi = img->planes[(size_t)(2 * (g >> 6) + 1)];
+            int s = (int)(g & 63);
+            o[g - a] = L[((lo >> s) & 1) | (((hi >> s) & 1) << 1)];
+        }
+        uint32_t ua = (uint32_t)std::max<int64_t>(a, 0), ub = (uint32_t)std::min<int64_t>(b, img->padded_bases);
+        auto it = std::upper_bound(img->runs.begin(), img->runs.end(), ua,
+                                   [](uint32_t v, const Run &r) { return v < r.end; });
+        for (; it != img->runs.end() && it->start < ub; ++it)
+            for (uint32_t p = std::max(ua, it->start); p < std::min(ub, it->end); p++) o[(int64_t)p - a] = it->letter ? it->letter : 'N';
+    }
+    return GUIDO_OK;
+}
+
 int guido_encode_guides(const char *protos, int64_t n, uint32_t *out) {
     for (int64_t g = 0; g < n; g++) {
         uint32_t hi = 0, lo = 0;

@@ -12,6 +12,8 @@
 // orientation, the per-position mismatch mask of all 20 positions is two LOP3s:
 //     m = (A_w ^ A_g) | (B_w ^ B_g)
 // and the mismatch count is one POPC -- no 2-bit fold, no shifts in the inner loop.
+#include <algorithm>
+
 #include "scan_common.cuh"
 
 namespace guido {
@@ -198,13 +200,11 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     a.n_tiles = (uint32_t)((last_block - a.first_block + 1 + kThreads - 1) / kThreads);
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
-    static bool attr_set = false;
     const int smem = 3 * kRing * (int)sizeof(uint32_t);
-    if (!attr_set) {
-        GUIDO_CUDA(cudaFuncSetAttribute(ot_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    int grid = ds->sm_count * 4;
+    GUIDO_CUDA(cudaFuncSetAttribute(ot_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_scan_kernel, kThreads, smem));
+    int grid = ds->sm_count * std::max(per_sm, 1);
     if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
     ot_scan_kernel<<<grid, kThreads, smem, stream>>>(a);
     GUIDO_CUDA(cudaGetLastError());

@@ -14,6 +14,8 @@
 //   5. hits staged in shared memory and written as coalesced 4-byte stores.
 //
 // HBM traffic per launch (algorithmic): 0.25 B/base read + 4 B per hit written.
+#include <algorithm>
+
 #include "scan_common.cuh"
 
 namespace guido {
@@ -185,7 +187,9 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
     a.ticket = ds->d_tile_counter;
     GUIDO_CUDA(cudaMemsetAsync(ds->d_desc, 0, (size_t)need * sizeof(unsigned long long), stream));
     GUIDO_CUDA(cudaMemsetAsync(ds->d_tile_counter, 0, sizeof(unsigned int), stream));
-    int grid = ds->sm_count * 8;
+    int per_sm = 0;
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_scan_kernel, kThreads, 0));
+    int grid = ds->sm_count * std::max(per_sm, 1);
     if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
     pam_scan_kernel<<<grid, kThreads, 0, stream>>>(a);
     GUIDO_CUDA(cudaGetLastError());

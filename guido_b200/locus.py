@@ -1,0 +1,267 @@
+"""``Locus`` and the locus factories (drop-in for guido.locus, reference guido/locus.py).
+
+Public names, signatures, coordinate conventions and returned records follow the reference; the
+PAM scan (``re.finditer`` x2 at locus.py:182-183), the MMEJ enumeration and the off-target search
+are delegated to the GPU through the C-ABI.  ``find_guides`` scans the locus ONCE on the device and
+derives every interval's matches from that single hit list (a look-ahead regex match inside a
+substring is the same match inside the whole string, as long as it fits the substring).
+
+Out of scope here: data layers / variation statistics / TOPSIS ranking
+(locus.py:409-688) and the Jinja report -- they work on <=10^3 guides and need scikit-allel / mcdm.
+"""
+import numpy as np
+import pandas as pd
+
+from . import _native
+from . import mmej as _mmej
+from .annotation import intersect, read_annotation, renamed
+from .guides import Guide, guide_geometry
+from .helpers import (_guides_to_bed, _guides_to_csv, _guides_to_dataframe, load_cfd_scoring_matrix,
+                      rev_comp_fast)
+from .off_targets import get_off_targets_string, run_bowtie
+from .sequence import FastaFile, Sequence, is_sequence_like
+
+
+class Locus:
+    def __init__(self, sequence, name=None, start=1, end=None, genome=None, annotation=None, **kwargs):
+        """A genomic locus in which gRNAs are searched.
+
+        sequence: ``Sequence`` record (name/seq/start/end) or plain ``str``; name: contig name;
+        start/end: 1-based coordinates of the locus; genome: ``Genome`` used by default for the
+        off-target search; annotation: DataFrame of features (pyranges-style columns).
+        """
+        self.sequence = sequence
+        self.chromosome = name
+        self.start = start
+        self.intervals = []
+        self.genome = genome
+        self.annotation = annotation
+        self.pam = ""
+        self.guides = []
+        self._layers = {}
+
+        if is_sequence_like(sequence):
+            self.start = sequence.start
+            self.end = sequence.end
+            self.chromosome = sequence.name
+        else:
+            self.sequence = Sequence(seq=sequence, start=start, end=end, name=name, **kwargs)
+            if end and isinstance(end, int):
+                self.end = end
+            elif not end:
+                self.end = self.start + len(self.sequence.seq)  # one past the last base, as upstream
+        self.length = len(self.sequence)
+
+    def __repr__(self):
+        return f"Locus({self.chromosome}:{self.start}-{self.end})"
+
+    def to_dict(self):
+        return self.__dict__
+
+    def guide(self, ix):
+        """Guide by position (int) or by id ("gRNA-3")."""
+        if isinstance(ix, str):
+            for g in self.guides:
+                if g.id == ix:
+                    return g
+            raise ValueError("Provided gRNA index is not valid.")
+        if isinstance(ix, int):
+            return self.guides[ix]
+        raise ValueError("Provided gRNA index is not valid.")
+
+    @property
+    def layers(self):
+        return self._layers
+
+    # ------------------------------------------------------------------ intervals
+    def _flatten_intervals(self, intervals):
+        """Union of adjacent / overlapping [start, end] pairs, clamped to the locus (locus.py:144-156;
+        only the first interval of a merged group is clamped, as upstream)."""
+        merged = []
+        for start, end in intervals:
+            if merged and merged[-1][1] >= start - 1:
+                merged[-1][1] = max(merged[-1][1], end)
+                continue
+            merged.append([max(start, self.start), min(end, self.end)])
+        return merged
+
+    # ------------------------------------------------------------------ PAM scan -> guides
+    def _guides_from_pam_positions(self, fwd_seq, start, pam, pams_fw, pams_rv, keep=None):
+        """Build Guide records for PAM starts (relative to ``fwd_seq``), forward strand first.
+        ``keep`` optionally pre-filters (strand, position) pairs that find_guides would drop anyway."""
+        P = len(pam)
+        rc_seq = rev_comp_fast(fwd_seq) if len(pams_rv) else None
+        chrom = self.chromosome
+        out = []
+        for strand, positions, rc in (("+", pams_fw, None), ("-", pams_rv, rc_seq)):
+            for p in positions:
+                if keep is not None and not keep(strand, p):
+                    continue
+                geo = guide_geometry(fwd_seq, p, P, strand, start=start, rc_sequence=rc)
+                if "N" in geo["guide_seq"]:
+                    continue
+                out.append(Guide._from_geometry(geo, chrom, strand))
+        return out
+
+    def _find_guides_in_interval(self, sequence, start, pam):
+        """Every guide whose PAM lies in ``sequence`` (coordinate of sequence[0] = ``start``):
+        forward-strand guides by ascending PAM position, then reverse-strand ones; guides whose
+        23-mer holds an N are dropped (locus.py:158-211).  The PAM scan runs on the GPU."""
+        fwd_seq = sequence.upper()
+        pams_fw, pams_rv = _native.pam_scan_seq(fwd_seq, pam)
+        return self._guides_from_pam_positions(fwd_seq, start, pam, pams_fw.tolist(), pams_rv.tolist())
+
+    def find_guides(self, pam="NGG", min_flanking_length=0, selected_features="all"):
+        """Find gRNAs in the locus (both strands), sorted by cut position and named gRNA-1..n.
+
+        pam: IUPAC PAM (3' of a 20-nt protospacer); min_flanking_length: flank around each interval
+        that is searched but in which cut sites are ignored; selected_features: restrict the search
+        to annotation features of that type (``"all"`` = whole locus).
+        """
+        self.pam = pam
+        self.guides = []
+        self.intervals = [[self.start, self.end]]
+
+        if "all" not in selected_features and isinstance(self.annotation, pd.DataFrame):
+            ann = self.annotation
+            feature_ok = (ann["Feature"].isin(list(selected_features)) if isinstance(selected_features, (list, set, tuple))
+                          else ann["Feature"] == selected_features)
+            inside = (((ann["Start"] >= self.start) & (ann["Start"] <= self.end))
+                      | ((ann["End"] >= self.start) & (ann["End"] <= self.end)))
+            rows = ann[feature_ok & (ann["Chromosome"] == self.chromosome) & inside].sort_values("Start")
+            if len(rows) > 0:
+                self.intervals = self._flatten_intervals(
+                    [[s, e] for s, e in rows[["Start", "End"]].values])
+
+        whole = self.sequence.seq
+        n = len(whole)
+        P = len(pam)
+        upper = whole.upper()
+        # one device scan for the whole locus; every interval slices the sorted hit lists
+        all_fw, all_rv = _native.pam_scan_seq(upper, pam)
+
+        for interval_start, interval_end in self.intervals:
+            a = max(interval_start - min_flanking_length - self.start, 0)
+            b = min(interval_end + min_flanking_length - self.start, n)
+            seq_start = interval_start - min_flanking_length  # NOT clamped, as upstream (locus.py:309)
+            sub = upper[a:b]
+            m = len(sub)
+
+            def rel(arr):
+                if m < P:
+                    return []
+                lo = np.searchsorted(arr, a, side="left")
+                hi = np.searchsorted(arr, a + m - P, side="right")
+                return (arr[lo:hi] - a).tolist()
+
+            def keep(strand, p, _s=seq_start, _lo=interval_start, _hi=interval_end, _m=m):
+                # exactly the post-filter of locus.py:313-319, evaluated before building the record
+                if strand == "+":
+                    return p >= 20 and _lo <= _s + p - 3 <= _hi
+                return p + P + 20 <= _m and _lo <= _s + p + P + 3 <= _hi
+
+            found = self._guides_from_pam_positions(sub, seq_start, pam, rel(all_fw), rel(all_rv), keep)
+            self.guides.extend(g for g in found
+                               if len(g.guide_seq) == 23 and interval_start <= g.absolute_cut_pos <= interval_end)
+
+        ordered = sorted(self.guides, key=lambda g: g.absolute_cut_pos)
+        for i, g in enumerate(ordered):
+            g.id = f"gRNA-{i + 1}"
+        self.guides = ordered
+        return ordered
+
+    # ------------------------------------------------------------------ MMEJ
+    def simulate_end_joining(self, n_patterns=5, length_weight=20):
+        """MMEJ deletion patterns for every gRNA -- one batched GPU call for the whole locus."""
+        if len(self.guides) == 0:
+            raise ValueError("No gRNAs saved yet.")
+        todo = [g for g in self.guides if "N" not in g.locus_seq]
+        results = _mmej.generate_mmej_patterns_batch([g.relative_cut_pos for g in todo],
+                                                     [g.locus_seq for g in todo], length_weight)
+        by_guide = {id(g): r for g, r in zip(todo, results)}
+        for g in self.guides:  # in order, so an upstream-style TypeError leaves later guides untouched
+            if id(g) in by_guide:
+                g._finish_end_joining(by_guide[id(g)], n_patterns)
+            else:
+                g._skip_end_joining()
+
+    # ------------------------------------------------------------------ off-targets
+    def find_off_targets(self, external_genome=None, **kwargs):
+        """Off-targets of every gRNA in ``external_genome`` (or the locus' own genome); attaches the
+        hits, ``ot_sum_score`` and the CFD layers, and returns ``{guide index: [off-target, ...]}``."""
+        if external_genome:
+            index_path = external_genome.bowtie_index
+        elif self.genome:
+            index_path = self.genome.bowtie_index
+        else:
+            raise ValueError("No genome / locus specified.")
+        if not index_path:
+            raise ValueError("Bowtie index is not built for the genome / locus.")
+
+        found = run_bowtie(guides=self.guides, pam=self.pam, genome_index_path=index_path, **kwargs)
+        mm_scores, pam_scores = load_cfd_scoring_matrix()
+        for ix, G in enumerate(self.guides):
+            if ix in found:
+                G.off_target_str = get_off_targets_string(found[ix])
+                G._attach_off_targets(found[ix], mm_scores, pam_scores, nan_if_empty=True)
+        return found
+
+    # ------------------------------------------------------------------ exports (thin)
+    def guides_to_dataframe(self):
+        return _guides_to_dataframe(self.guides)
+
+    def guides_to_csv(self, filename):
+        _guides_to_csv(self.guides, filename)
+
+    def guides_to_bed(self, filename):
+        _guides_to_bed(self.guides, filename)
+
+
+# ---------------------------------------------------------------------- locus factories
+
+def _prepare_annotation(annotation_file_abspath, as_df=True):
+    """Annotation table with the reference's renames (GTF gene_id->ID, exon_number->Exon; GFF3
+    Name->Exon)."""
+    return renamed(read_annotation(annotation_file_abspath), annotation_file_abspath)
+
+
+def locus_from_coordinates(genome, chromosome, start, end):
+    """Locus for ``chromosome:start-end`` (1-based, inclusive); annotated when the genome has a
+    GTF/GFF3 (features clipped to the region, pyranges ``intersect`` conventions)."""
+    locus_sequence = FastaFile(str(genome.genome_file_abspath)).get_seq(chromosome, start, end)
+    ann_path = genome.annotation_file_abspath
+    if ann_path and ann_path.exists():
+        table = intersect(read_annotation(ann_path), chromosome, start, end)
+        table = renamed(table, ann_path)
+        if len(table) > 0:
+            return Locus(genome=genome, sequence=locus_sequence, annotation=table)
+    return Locus(genome=genome, sequence=locus_sequence, annotation=None)
+
+
+def locus_from_sequence(sequence, sequence_name=None):
+    return Locus(sequence=sequence, name=sequence_name)
+
+
+def locus_from_gene(genome, gene_name):
+    """Locus spanning gene ``gene_name`` of the genome's annotation."""
+    if not genome.annotation_file_abspath.exists():
+        raise ValueError("Annotation file not valid.")
+    try:
+        ann = _prepare_annotation(genome.annotation_file_abspath)
+        gene = ann[(ann["ID"] == gene_name) & ann["Feature"].isin(["protein_coding_gene", "gene"])]
+        chromosome = gene.Chromosome.values[0]
+        if len(gene) != 1:
+            raise TypeError("cannot convert the series to <class 'int'>")  # upstream: int(Series)
+        start = int(gene.Start.iloc[0]) + 1  # table starts are 0-based
+        end = int(gene.End.iloc[0])
+        related = ann["ID"] == gene_name
+        for col in ("Parent", "gene_id"):
+            if col not in ann.columns:
+                raise KeyError(col)  # upstream's query fails on a missing column
+            related |= ann[col] == gene_name
+        inside = (((ann["Start"] >= start) & (ann["Start"] <= end)) | ((ann["End"] >= start) & (ann["End"] <= end)))
+        locus_annotation = ann[related & (ann["Chromosome"] == chromosome) & inside]
+        locus_sequence = FastaFile(str(genome.genome_file_abspath)).get_seq(chromosome, start, end)
+        return Locus(genome=genome, sequence=locus_sequence, annotation=locus_annotation)
+    except Exception as e:
+        raise ValueError(f"Gene {gene_name} not found. (Error: {e})")

@@ -1,0 +1,73 @@
+"""MMEJ deletion patterns (drop-in for guido.mmej, reference guido/mmej.py:8-120).
+
+The candidate enumeration and nested-pattern elimination run on the GPU (one warp per cut site,
+``guido_mmej_batch``); this module turns the kept ``(left_start, left_end, right_start, right_end)``
+tuples into the reference's pattern dicts.  The score is a float64 function of three small
+integers and is evaluated here with the reference's exact expression and operation order
+(mmej.py:86-91), so scores are bit-identical to the reference (e.g. 230.79999999999998).
+"""
+import math
+
+import numpy as np
+
+from . import _native
+
+
+def _pattern_dict(left_seq, right_seq, ls, le, rs, length_weight):
+    pattern = left_seq[ls:le]
+    gc = pattern.count("G") + pattern.count("C")
+    left_del = len(left_seq) - ls
+    del_len = left_del + rs
+    deletion = left_seq[ls:] + right_seq[:rs]
+    length_factor = round(1 / math.exp(del_len / length_weight), 3)
+    score = 100 * length_factor * ((len(pattern) - gc) + (gc * 2))
+    return {
+        "left": left_seq[:ls] + "-" * left_del,
+        "left_seq": left_seq[:ls],
+        "left_seq_position": ls,
+        "right": "+" * rs + right_seq[rs:],
+        "right_seq": right_seq[rs:],
+        "right_seq_position": rs + len(deletion),
+        "pattern": pattern,
+        "pattern_len": len(pattern),
+        "pattern_score": score,
+        "deletion_seq": deletion,
+        "frame_shift": "-" if del_len % 3 == 0 else "+",
+    }
+
+
+def _unpack(tuples):
+    t = np.asarray(tuples, dtype=np.uint32)
+    # np.int64 positions, like the rows of the reference's combinations_array
+    return (t & 255).astype(np.int64), ((t >> 8) & 255).astype(np.int64), ((t >> 16) & 255).astype(np.int64)
+
+
+def patterns_from_tuples(rel_cut_position, sequence, tuples, length_weight):
+    left_seq, right_seq = sequence[:rel_cut_position], sequence[rel_cut_position:]
+    ls, le, rs = _unpack(tuples)
+    return [_pattern_dict(left_seq, right_seq, a, b, c, length_weight) for a, b, c in zip(ls, le, rs)]
+
+
+def generate_mmej_patterns_batch(rel_cut_positions, sequences, length_weight, device=None, stats=None):
+    """One GPU call for many cut sites; returns a list with, per site, the reference's result of
+    ``generate_mmej_patterns`` (a list of pattern dicts, or None when there is no candidate)."""
+    sequences = list(sequences)
+    cuts = [int(c) for c in rel_cut_positions]
+    if not sequences:
+        return []
+    for c in cuts:
+        if c < 0:
+            raise ValueError("negative cut positions are not supported")
+    tuples, offsets, n_cand = _native.mmej_batch(sequences, cuts, device=device, stats=stats)
+    out = []
+    for g, (seq, cut) in enumerate(zip(sequences, cuts)):
+        if n_cand[g] == 0:
+            out.append(None)
+        else:
+            out.append(patterns_from_tuples(cut, seq, tuples[offsets[g]:offsets[g + 1]], length_weight))
+    return out
+
+
+def generate_mmej_patterns(rel_cut_position, sequence, length_weight):
+    """All MMEJ patterns around ``rel_cut_position`` of ``sequence`` (list of dicts or None)."""
+    return generate_mmej_patterns_batch([rel_cut_position], [sequence], length_weight)[0]

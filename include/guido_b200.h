@@ -113,6 +113,11 @@ int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t n
 int guido_image_fetch(const guido_image *img, int64_t contig_ix, int64_t start0, int64_t n,
                       char *out);
 
+/* decode n_windows windows of `width` letters starting at the given GLOBAL positions (host copy);
+ * letters outside any contig come back as 'N'.  out: n_windows * width bytes. */
+int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64_t n_windows,
+                              int32_t width, char *out);
+
 /* ---- PAM scan: under Locus._find_guides_in_interval (guido/locus.py:158-183) ------------------ */
 /* host string in, match starts out (ascending; relative to seq[0]); `device` is the CUDA device. */
 int guido_pam_scan_seq(const char *seq, int64_t n, const char *pam, int32_t device, int32_t mode,

@@ -274,6 +274,10 @@ def off_target_records(guides, contigs, pam="NGG", core_length=10, core_mismatch
             strand, t_seq = "-", rev_comp(reads[ix])
         # NB: bowtie prints the read reverse-complemented for '-' rows; the reference then
         # rev_comps the '+' rows, so t_seq is the read in guide orientation either way.
+        if not h["mm"]:
+            # bowtie prints an empty descriptor field for a perfect alignment (only possible when
+            # the PAM pattern has no N); _parse_mismatches("") then fails at off_targets.py:73
+            raise ValueError("not enough values to unpack (expected 2, got 1)")
         mm = {}
         for off, ref, _ in h["mm"]:  # off_targets.py:64-80
             mm[R - off] = rev_comp(ref) if strand == "-" else ref

@@ -1,0 +1,236 @@
+"""Host-side logic of the package (record building, filters, I/O conventions) on a box WITHOUT a GPU.
+
+The three device entry points are replaced by oracle-backed fakes (tests/fakes.py); everything
+above the C-ABI is the shipped code and is compared with the golden fixtures generated from the
+reference.  The same comparisons run against the real kernels in tests/test_gpu_api.py.
+"""
+import math
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import guido_b200 as guido
+from guido_b200 import _native, off_targets
+from tests import fakes, util
+
+GUIDE_ATTRS = ["id", "guide_seq", "guide_long_seq", "guide_pam", "guide_chrom", "guide_start", "guide_end",
+               "guide_strand", "relative_cut_pos", "absolute_cut_pos", "locus_seq"]
+
+
+@pytest.fixture
+def cpu_fakes(monkeypatch):
+    monkeypatch.setattr(_native, "pam_scan_seq", fakes.fake_pam_scan_seq)
+    monkeypatch.setattr(_native, "mmej_batch", fakes.fake_mmej_batch)
+
+
+def same_guides(guides, golden, attrs=GUIDE_ATTRS):
+    assert len(guides) == len(golden)
+    for g, b in zip(guides, golden):
+        for k in attrs:
+            assert getattr(g, k) == b[k], (k, getattr(g, k), b[k])
+
+
+def same_layers(mine, golden):
+    assert set(mine) == set(golden)
+    for k, v in golden.items():
+        if isinstance(v, float) and math.isnan(v):
+            assert math.isnan(mine[k]), k
+        else:
+            assert mine[k] == v, (k, mine[k], v)
+
+
+def test_kat_loci(cpu_fakes):
+    kat = fakes.load_golden("kat.json")
+    for key in ("locus101", "locus126", "locus490", "agap005958"):
+        c = kat[key]
+        loc = guido.Locus(sequence=c["seq"], name=c["name"], start=c["start"], end=c.get("end"))
+        same_guides(loc.find_guides(), c["guides"])
+    assert repr(loc.guides[0]).startswith("gRNA-1(")
+    assert loc.guide("gRNA-2") is loc.guides[1] and loc.guide(0) is loc.guides[0]
+    with pytest.raises(ValueError):
+        loc.guide("nope")
+
+
+def test_kat_mmej(cpu_fakes):
+    kat = fakes.load_golden("kat.json")["agap005958"]
+    loc = guido.Locus(sequence=kat["seq"], name=kat["name"], start=kat["start"], end=kat["end"])
+    loc.find_guides()
+    loc.simulate_end_joining()
+    assert loc.guide(5).mmej_patterns == kat["stored_mmej_guide5"]
+    for g, m in zip(loc.guides, kat["mmej"]):
+        assert g.mmej_patterns == m["patterns"] and g.mmej_str == m["mmej_str"]
+        same_layers(g.layers, m["layers"])
+    # per-guide entry point gives the same answer as the batched one
+    g = loc.guides[7]
+    before = (g.mmej_patterns, dict(g.layers))
+    g.simulate_end_joining()
+    assert (g.mmej_patterns, dict(g.layers)) == before
+
+
+def test_synthetic_find_guides(cpu_fakes):
+    for c in fakes.load_golden("guides_synth.json.gz"):
+        ann = pd.DataFrame(c["annotation"]) if c["annotation"] else None
+        loc = guido.Locus(sequence=c["seq"], name="chrS", start=c["start"], annotation=ann)
+        guides = loc.find_guides(pam=c["pam"], min_flanking_length=c["min_flanking_length"],
+                                 selected_features=c["selected_features"] or "all")
+        assert [list(map(int, i)) for i in loc.intervals] == c["intervals"]
+        same_guides(guides, c["guides"])
+        raw = loc._find_guides_in_interval(c["seq"][:c["interval_prefix"]], c["start"], c["pam"])
+        same_guides(raw, c["interval_guides"], [a for a in GUIDE_ATTRS if a != "id"])
+
+
+def test_guide_constructor_matches_fast_path(cpu_fakes):
+    seq = util.synthetic_contigs(3, [500], n_runs=1)[0][1].upper()
+    loc = guido.Locus(sequence=seq, name="c", start=100)
+    for g in loc._find_guides_in_interval(seq, 100, "NGG"):
+        p = (g.absolute_cut_pos - 100 + 3) if g.guide_strand == "+" else (g.absolute_cut_pos - 100 - 6)
+        h = guido.Guide(seq, p, 3, strand=g.guide_strand, chromosome="c", start=100)
+        assert h.__dict__ == g.__dict__
+    with pytest.raises(TypeError):
+        g.no_such_attribute
+    with pytest.raises(ValueError):
+        g.layer("missing")
+
+
+def test_synthetic_mmej(cpu_fakes):
+    from guido_b200.mmej import generate_mmej_patterns
+    for c in fakes.load_golden("mmej_synth.json.gz"):
+        got = generate_mmej_patterns(c["cut"], c["seq"], c["length_weight"])
+        assert got == c["patterns"]
+        if got:
+            assert isinstance(got[0]["left_seq_position"], np.int64)  # as the reference's numpy rows
+
+
+def test_mmej_none_raises_like_reference(cpu_fakes):
+    loc = guido.Locus(sequence="ACGT" * 5 + "TGG" + "ACGT" * 5, name="c")
+    g = guido.Guide("A" * 10 + "C" * 10, 10, 3)
+    g.locus_seq, g.relative_cut_pos = "AAAACCCC", 4
+    with pytest.raises(TypeError):
+        g.simulate_end_joining()
+    with pytest.raises(ValueError):
+        guido.Locus(sequence="ACGTACGT", name="c").simulate_end_joining()
+
+
+def test_offtarget_records(cpu_fakes, monkeypatch):
+    for c in fakes.load_golden("offtargets_synth.json.gz"):
+        contigs = [tuple(x) for x in c["contigs"]]
+        image = fakes.FakeImage(contigs)
+        monkeypatch.setattr(off_targets, "get_image", lambda path, device=None, **kw: image)
+        for spec, golden, layers in ((c["locus"], c["result"], c["layers"]),
+                                     (c["external"], c["external"]["result"], c["external"]["layers"])):
+            genome = type("G", (), {"bowtie_index": "/virtual/index"})()
+            loc = guido.Locus(sequence=spec["seq"], name=spec["name"], start=spec["start"], genome=genome)
+            loc.find_guides(pam=c["pam"])
+            found = loc.find_off_targets(**c["kwargs"])
+            golden = fakes.int_keys(golden)
+            assert set(found) == set(golden)
+            for ix, recs in golden.items():
+                want = sorted((dict(r, mismatches=fakes.int_keys(r["mismatches"])) for r in recs),
+                              key=lambda r: (r["chromosome"], r["start"], r["strand"]))
+                got = sorted(found[ix], key=lambda r: (r["chromosome"], r["start"], r["strand"]))
+                assert got == want
+            for g, lay in zip(loc.guides, layers):
+                if "ot_cfd_score_mean" in lay and not math.isnan(lay["ot_cfd_score_mean"]):
+                    # mean/sum depend on bowtie's (unspecified) emission order only in the last ulp
+                    assert g.layers["ot_sum_score"] == lay["ot_sum_score"]
+                    assert g.layers["ot_cfd_score_max"] == lay["ot_cfd_score_max"]
+                    assert math.isclose(g.layers["ot_cfd_score_sum"], lay["ot_cfd_score_sum"], rel_tol=1e-12)
+                    assert math.isclose(g.layers["ot_cfd_score_mean"], lay["ot_cfd_score_mean"], rel_tol=1e-12)
+                else:
+                    same_layers(g.layers, lay)
+            if spec is c["locus"]:
+                assert [g.off_target_str for g in loc.guides] == c["off_target_str"]
+                assert [g.off_targets_string for g in loc.guides] == c["off_targets_string"]
+
+
+def test_offtarget_argument_errors(cpu_fakes, monkeypatch):
+    loc = guido.Locus(sequence="ACGT" * 30, name="c")
+    with pytest.raises(ValueError, match="No genome"):
+        loc.find_off_targets()
+    loc.genome = type("G", (), {"bowtie_index": None})()
+    with pytest.raises(ValueError, match="not built"):
+        loc.find_off_targets()
+
+
+def test_rev_comp_semantics():
+    assert guido.rev_comp("ACGTNRX") == "NNNACGT"
+    assert guido.rev_comp("acgt") == "NNNN"
+    assert guido.rev_comp("ACGU-", rna=True) == "-ACGT"
+    assert guido.rev_comp("N", rna=True) == "N"  # not in the RNA table -> 'N' by the fallback
+    from guido_b200.helpers import rev_comp_fast
+    for s in ("ACGTNRYKMacgtn-*", "", "G"):
+        assert rev_comp_fast(s) == guido.rev_comp(s)
+
+
+# ------------------------------------------------------------------ Genome.build / factories
+
+def _write_genome(tmp_path, gtf=True):
+    contigs = util.synthetic_contigs(31, [4000, 2500], n_runs=2, run_len=(5, 60))
+    fa = tmp_path / "toy.fa"
+    with open(fa, "w") as fh:
+        for name, s in contigs:
+            fh.write(f">{name} description text\n")
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+    ann = None
+    if gtf:
+        ann = tmp_path / "toy.gff3"
+        rows = [("chr1", "src", "gene", 1001, 2000, ".", "+", ".", "ID=GENE1;Name=g1"),
+                ("chr1", "src", "exon", 1001, 1200, ".", "+", ".", "ID=e1;Parent=GENE1;Name=E1;gene_id=GENE1"),
+                ("chr1", "src", "exon", 1500, 2000, ".", "+", ".", "ID=e2;Parent=GENE1;Name=E2;gene_id=GENE1"),
+                ("chr2", "src", "gene", 100, 900, ".", "-", ".", "ID=GENE2;Name=g2"),
+                ("chr1", "src", "gene", 10, 400, ".", "-", ".", "ID=GENE0;Name=g0")]
+        with open(ann, "w") as fh:
+            fh.write("##gff-version 3\n")
+            for r in rows:
+                fh.write("\t".join(str(x) for x in r) + "\n")
+    return contigs, fa, ann
+
+
+def test_genome_build_and_reload(tmp_path, capsys):
+    contigs, fa, ann = _write_genome(tmp_path)
+    g = guido.Genome("toy", genome_file_abspath=str(fa), annotation_file_abspath=str(ann))
+    with pytest.raises(AttributeError):
+        g.is_built  # upstream quirk: fai_file is only set by build()
+    g.build()
+    assert g.is_built and g.bowtie_index and os.path.exists(g.bowtie_index)
+    assert os.path.exists(str(fa) + ".fai") and os.path.exists(str(ann) + ".gz")
+    fai = [ln.split("\t") for ln in open(str(fa) + ".fai").read().splitlines()]
+    assert [(r[0], int(r[1]), int(r[3]), int(r[4])) for r in fai] == [("chr1", 4000, 60, 61), ("chr2", 2500, 60, 61)]
+    state = pickle.load(open(tmp_path / "toy.guido", "rb"))
+    assert {"genome_name", "_bowtie_ignore", "bowtie_index", "genome_file_abspath", "annotation_file_abspath",
+            "annotation_sorted_gz_file", "tbi_file", "fai_file"} <= set(state)
+    g2 = guido.load_genome_from_file(tmp_path / "toy.guido")
+    assert g2.__dict__ == g.__dict__
+    with pytest.raises(ValueError):
+        guido.load_genome_from_file(tmp_path / "missing.guido")
+    with pytest.raises(ValueError):
+        guido.Genome("x", genome_file_abspath=str(tmp_path / "nope.fa"))
+    # the image holds the same bases as the FASTA
+    img = _native.Image.load(g.bowtie_index)
+    assert [(c[0], c[1]) for c in img.contigs] == [(n, len(s)) for n, s in contigs]
+    assert img.fetch(0, 0, 4000) == contigs[0][1].upper() and img.fetch(1, 0, 2500) == contigs[1][1].upper()
+    # sequence fetch: 1-based inclusive, case preserved
+    assert g.sequence.get_seq("chr1", 11, 130).seq == contigs[0][1][10:130]
+
+
+def test_locus_factories(tmp_path, cpu_fakes):
+    contigs, fa, ann = _write_genome(tmp_path)
+    g = guido.Genome("toy", genome_file_abspath=str(fa), annotation_file_abspath=str(ann))
+    g.build()
+    loc = guido.locus_from_coordinates(g, "chr1", 1100, 1600)
+    assert (loc.chromosome, loc.start, loc.end) == ("chr1", 1100, 1600)
+    assert loc.sequence.seq == contigs[0][1][1099:1600]
+    assert set(loc.annotation["Feature"]) == {"gene", "exon"} and "Exon" in loc.annotation.columns
+    assert loc.annotation["Start"].min() >= 1100 and loc.annotation["End"].max() <= 1600
+    loc.find_guides(selected_features="exon")
+    assert loc.intervals == [[1100, 1200], [1499, 1600]]
+    loc2 = guido.locus_from_gene(g, "GENE1")
+    assert (loc2.chromosome, loc2.start, loc2.end) == ("chr1", 1001, 2000)
+    assert loc2.sequence.seq == contigs[0][1][1000:2000] and len(loc2.annotation) == 3
+    with pytest.raises(ValueError, match="not found"):
+        guido.locus_from_gene(g, "NOPE")
+    assert guido.locus_from_sequence("ACGT", "s").chromosome == "s"

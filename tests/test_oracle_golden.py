@@ -1,0 +1,123 @@
+"""The CPU oracle against the golden fixtures generated from the reference (tests/golden/), and
+against the reference's own stored outputs.  No GPU, no /root/reference needed."""
+import math
+
+import pytest
+
+from tests import fakes
+
+GUIDE_ATTRS = ["id", "guide_seq", "guide_long_seq", "guide_pam", "guide_chrom", "guide_start", "guide_end",
+               "guide_strand", "relative_cut_pos", "absolute_cut_pos", "locus_seq"]
+
+
+def _same_guides(mine, golden, attrs=GUIDE_ATTRS):
+    assert len(mine) == len(golden)
+    for a, b in zip(mine, golden):
+        for k in attrs:
+            if k in a:
+                assert a[k] == b[k], (k, a[k], b[k])
+
+
+def test_kat_loci(oracle):
+    kat = fakes.load_golden("kat.json")
+    for key in ("locus101", "locus126", "locus490", "agap005958"):
+        c = kat[key]
+        mine = oracle.find_guides_records(c["seq"], c["start"], c.get("end"), chromosome=c["name"])
+        _same_guides(mine, c["guides"])
+    got = [[g["id"], g["guide_seq"], g["guide_start"], g["guide_end"], g["guide_strand"]]
+           for g in oracle.find_guides_records(kat["locus126"]["seq"], 48714541, 48714666, chromosome="AgamP4_2R")]
+    assert got == kat["locus126"]["readme_expected"]  # README.md:69-73, incl. the tie order of gRNA-1/2
+
+
+def test_kat_mmej_stored_notebook_output(oracle):
+    kat = fakes.load_golden("kat.json")["agap005958"]
+    guides = oracle.find_guides_records(kat["seq"], kat["start"], kat["end"], chromosome=kat["name"])
+    assert len(guides) == 195
+    top, s, sum_score, oof = oracle.simulate_end_joining(guides[5]["locus_seq"], guides[5]["relative_cut_pos"])
+    assert top == kat["stored_mmej_guide5"]           # notebooks/examples.ipynb:237-298
+    assert top[3]["pattern_score"] == 230.79999999999998
+    for g, m in zip(guides, kat["mmej"]):
+        top, s, sum_score, oof = oracle.simulate_end_joining(g["locus_seq"], g["relative_cut_pos"])
+        assert top == m["patterns"] and s == m["mmej_str"]
+        assert sum_score == m["layers"]["mmej_sum_score"] and oof == m["layers"]["mmej_oof_score"]
+
+
+def test_kat_cfd_record(oracle):
+    from guido_b200.helpers import load_cfd_scoring_matrix
+    c = fakes.load_golden("kat.json")["cfd_record"]
+    mm, pam = load_cfd_scoring_matrix()
+    assert oracle.cfd_score(c["guide_seq"], c["guide_pam"], c["record"]["seq"], mm, pam) == c["record"]["cfd_score"]
+
+
+def test_synthetic_find_guides(oracle):
+    for c in fakes.load_golden("guides_synth.json.gz"):
+        mine = oracle.find_guides_records(c["seq"], c["start"], None, pam=c["pam"], chromosome="chrS",
+                                          min_flanking_length=c["min_flanking_length"], intervals=c["intervals"])
+        _same_guides(mine, c["guides"])
+        raw = oracle.guide_records(c["seq"][:c["interval_prefix"]], c["start"], c["pam"], chromosome="chrS")
+        _same_guides(raw, c["interval_guides"], [a for a in GUIDE_ATTRS if a != "id"])
+
+
+def test_synthetic_mmej(oracle):
+    for c in fakes.load_golden("mmej_synth.json.gz"):
+        assert oracle.mmej_patterns(c["cut"], c["seq"], c["length_weight"]) == c["patterns"], (c["seq"], c["cut"])
+
+
+def test_synthetic_offtargets(oracle):
+    from guido_b200.helpers import load_cfd_scoring_matrix
+    mm, pam_scores = load_cfd_scoring_matrix()
+    for c in fakes.load_golden("offtargets_synth.json.gz"):
+        contigs = [tuple(x) for x in c["contigs"]]
+        for spec, golden in ((c["locus"], c["result"]), (c["external"], c["external"]["result"])):
+            guides = oracle.find_guides_records(spec["seq"], spec["start"], None, pam=c["pam"], chromosome=spec["name"])
+            mine = oracle.off_target_records(guides, contigs, pam=c["pam"], **c["kwargs"])
+            golden = fakes.int_keys(golden)
+            assert set(mine) == set(golden)
+            for ix in mine:
+                want = sorted(golden[ix], key=lambda r: (r["chromosome"], r["start"], r["strand"]))
+                assert len(mine[ix]) == len(want)
+                for a, b in zip(mine[ix], want):
+                    b = dict(b, mismatches=fakes.int_keys(b["mismatches"]))
+                    cfd = b.pop("cfd_score")
+                    assert a == b
+                    assert oracle.cfd_score(guides[ix]["guide_seq"], guides[ix]["guide_pam"], a["seq"], mm, pam_scores) == cfd
+
+
+def test_bowtie_tsv_format_matches_stored_rows(oracle):
+    """Format of a '-' strand row with mismatches, as stored in the reference's test.ipynb:14081:
+    read TTATCATCCACTCTGACGGGTGG, shown reverse-complemented, descriptors on the forward strand."""
+    read = "TTATCATCCACTCTGACGGGTGG"
+    # build a reference window that differs from rc(read) at the stored offsets 15,17,18,19,20,22
+    shown = oracle.rev_comp(read)
+    assert shown == "CCACCCGTCAGAGTGGATGATAA"
+    stored = {15: ("G", "T"), 17: ("T", "C"), 18: ("T", "C"), 19: ("G", "C"), 20: ("C", "A"), 22: ("T", "C")}
+    window = list(shown)
+    for off, (ref, rd) in stored.items():
+        assert shown[22 - off] == rd
+        window[22 - off] = ref
+    genome = "ACGT" * 10 + "".join(window) + "TGCA" * 10
+    raw = oracle.bowtie_n([("2R", genome)], [read], 1, 13, 180)
+    rows = oracle.bowtie_tsv(raw, ["0"], [read]).strip().split("\n")
+    assert "0\t-\t2R\t40\tCCACCCGTCAGAGTGGATGATAA\t" + "I" * 23 + "\t0\t15:G>T,17:T>C,18:T>C,19:G>C,20:C>A,22:T>C" in rows
+
+
+def test_bowtie_rule_budget(oracle):
+    """-e 150 admits 5 mismatches incl. the read's N, not 6; -n counts N inside the seed."""
+    guide = "ACGTTGCATGCAAGCTTGCA"
+    read = oracle.rev_comp(guide + "NGG")
+    def genome(mm_positions):
+        g = list(guide)
+        for p in mm_positions:
+            g[p] = "ACGT"[("ACGT".index(g[p]) + 1) % 4]
+        return "TTTT" * 8 + "".join(g) + "AGG" + "TTTT" * 8
+    args = oracle.bowtie_args("NGG", 10, 2, 4)
+    assert args == (3, 13, 150)
+    assert len(oracle.bowtie_n([("c", genome([0, 1, 2, 3]))], [read], *args)) == 1      # 4 distal
+    assert len(oracle.bowtie_n([("c", genome([0, 1, 2, 3, 4]))], [read], *args)) == 0   # 5 distal > e
+    assert len(oracle.bowtie_n([("c", genome([18, 19]))], [read], *args)) == 1          # 2 in core
+    assert len(oracle.bowtie_n([("c", genome([17, 18, 19]))], [read], *args)) == 0      # 3 in core > n
+    assert len(oracle.bowtie_n([("c", genome([9, 18, 19]))], [read], *args)) == 1       # position 10 is distal
+    with pytest.raises(ValueError):
+        oracle.bowtie_args("NGG", 10, 3, 4)
+    with pytest.raises(ValueError):
+        oracle.bowtie_args("NGG", 10, 2, 1)
