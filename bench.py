@@ -240,7 +240,7 @@ def main():
 
         def e2e_step():
             st = N.Stats()
-            fw, rv = img.pam_scan_genome(PAM, N.SCAN_GUIDE, stats=st, cap_hint=cap)
+            fw, rv = img.pam_scan_genome(PAM, N.SCAN_GUIDE, stats=st, cap_hint=cap, pinned=True)
             return st, (len(fw) + len(rv))
     else:
         guides_u8 = sample_guides(img, args.guides, seed + 1)
@@ -267,7 +267,7 @@ def main():
 
         def e2e_step():
             st = N.Stats()
-            hits, _ = img.offtarget_search(protos_blob, pam=PAM, algo=algo, want_raw_flags=False, stats=st, **OT_KW)
+            hits, _ = img.offtarget_search(protos_blob, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
             if world > 1:
                 t = torch.from_numpy(hits.view(np.int32).reshape(-1, 4)).to(dev)
                 cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)

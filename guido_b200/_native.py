@@ -43,6 +43,8 @@ _SIGNATURES = {
     "guido_last_error": (ctypes.c_char_p, []),
     "guido_version": (ctypes.c_int, []),
     "guido_device_count": (ctypes.c_int, []),
+    "guido_host_alloc": (ctypes.c_int, [_i64, _P(_vp)]),
+    "guido_host_free": (ctypes.c_int, [_vp]),
     "guido_image_from_fasta": (ctypes.c_int, [_cp, _P(_vp)]),
     "guido_image_from_seqs": (ctypes.c_int, [_i32, _P(_cp), _P(_cp), _P(_i64), _P(_vp)]),
     "guido_image_synth": (ctypes.c_int, [_i32, _P(_cp), _P(_i64), ctypes.c_uint64, ctypes.c_double,
@@ -125,12 +127,44 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+class PinnedBuffer:
+    """Page-locked host memory exposed as numpy arrays (grown on demand, freed with the owner)."""
+
+    def __init__(self):
+        self._p = ctypes.c_void_p()
+        self._cap = 0
+
+    def array(self, n, dtype):
+        dtype = np.dtype(dtype)
+        need = max(int(n) * dtype.itemsize, 1)
+        if need > self._cap:
+            self.free()
+            cap = max(need * 5 // 4, 1 << 20)
+            check(lib().guido_host_alloc(cap, ctypes.byref(self._p)))
+            self._cap = cap
+        buf = (ctypes.c_char * need).from_address(self._p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self._p:
+            lib().guido_host_free(self._p)
+            self._p = ctypes.c_void_p()
+            self._cap = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Image:
     """Owner of one ``guido_image`` handle (host planes + optional HBM copy of one shard)."""
 
     def __init__(self, handle):
         self._h = ctypes.c_void_p(handle)
         self._contigs = None
+        self._pins = {}
 
     # ---- construction -----------------------------------------------------------------
     @classmethod
@@ -172,6 +206,8 @@ class Image:
         check(lib().guido_image_save(self._h, str(path).encode()))
 
     def close(self):
+        for pin in getattr(self, "_pins", {}).values():
+            pin.free()
         if self._h:
             lib().guido_image_free(self._h)
             self._h = ctypes.c_void_p()
@@ -233,13 +269,19 @@ class Image:
         return out
 
     # ---- PAM scan ---------------------------------------------------------------------
-    def pam_scan_genome(self, pam, mode=SCAN_GUIDE, stats=None, cap_hint=None):
+    def _pinned(self, name, n, dtype):
+        return self._pins.setdefault(name, PinnedBuffer()).array(n, dtype)
+
+    def pam_scan_genome(self, pam, mode=SCAN_GUIDE, stats=None, cap_hint=None, pinned=False):
         """Whole shard -> (fw, rv) uint32 arrays of global PAM-start positions (ascending)."""
         span = self.info.shard_hi - self.info.shard_lo
         cap = int(cap_hint) if cap_hint else max(1024, span // 8)
         st = stats if stats is not None else Stats()
         while True:
-            fw, rv = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+            if pinned:  # views of page-locked buffers owned by this image: valid until the next call
+                fw, rv = self._pinned("fw", cap, np.uint32), self._pinned("rv", cap, np.uint32)
+            else:
+                fw, rv = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
             nf, nr = ctypes.c_int64(), ctypes.c_int64()
             rc = lib().guido_pam_scan_genome(self._h, pam.encode(), mode, fw.ctypes.data, cap,
                                              ctypes.byref(nf), rv.ctypes.data, cap, ctypes.byref(nr),
@@ -272,7 +314,7 @@ class Image:
 
     # ---- off-target search ------------------------------------------------------------
     def offtarget_search(self, protos, pam="NGG", core_length=10, core_mismatches=2,
-                         total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None):
+                         total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False):
         """protos: list of 20-nt strings (or an (n,20) uint8 array of letters).
 
         Returns (hits structured array sorted by (guide, gpos, strand), raw_flags uint8[n] | None).
@@ -291,7 +333,7 @@ class Image:
         st = stats if stats is not None else Stats()
         cap = max(4096, 32 * n)
         while True:
-            hits = np.empty(cap, OT_HIT_DTYPE)
+            hits = self._pinned("hits", cap, OT_HIT_DTYPE) if pinned else np.empty(cap, OT_HIT_DTYPE)
             nh = ctypes.c_int64()
             rc = lib().guido_offtarget_search(self._h, blob, n, pam.encode(), core_length,
                                               core_mismatches, total_mismatches, algo, hits.ctypes.data,

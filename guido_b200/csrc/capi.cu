@@ -56,7 +56,7 @@ void device_release(guido_image *img) {
     if (ds->device >= 0) {
         cudaSetDevice(ds->device);
         if (ds->stream) cudaStreamSynchronize(ds->stream);
-        cudaFree(ds->d_planes); cudaFree(ds->d_run_start); cudaFree(ds->d_run_end); cudaFree(ds->d_run_kind);
+        cudaFree(ds->d_planes); cudaFree(ds->d_run_start); cudaFree(ds->d_run_end); cudaFree(ds->d_run_kind); cudaFree(ds->d_tile_first_run);
         cudaFree(ds->d_desc); cudaFree(ds->d_counts); cudaFree(ds->d_tile_counter);
         cudaFree(ds->d_out[0]); cudaFree(ds->d_out[1]); cudaFree(ds->d_guides); cudaFree(ds->d_flags);
         cudaFree(ds->d_index); cudaFree(ds->d_bucket);
@@ -71,7 +71,7 @@ void device_release(guido_image *img) {
 static PlanesView view_of(const DeviceState *ds) {
     PlanesView pv;
     pv.planes = ds->d_planes; pv.blk_lo = ds->blk_lo; pv.blk_n = ds->blk_n;
-    pv.run_start = ds->d_run_start; pv.run_end = ds->d_run_end; pv.run_kind = ds->d_run_kind;
+    pv.run_start = ds->d_run_start; pv.run_end = ds->d_run_end; pv.run_kind = ds->d_run_kind; pv.tile_first_run = ds->d_tile_first_run;
     pv.n_runs = ds->n_runs;
     return pv;
 }
@@ -83,12 +83,14 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
     img->dev = ds;
     int rc = device_init(ds, device);
     if (rc) { device_release(img); return rc; }
-    // contiguous shards with equal block counts; a shard owns the PAM starts inside it
+    // contiguous shards of equal size, aligned to scan tiles (1024 blocks = 65536 bases); a shard
+    // owns the PAM starts inside it and keeps a halo of 4 blocks (>= 20 + P bases) on either side
     int64_t per = (img->n_blocks + n_shards - 1) / n_shards;
+    per = (per + 1023) / 1024 * 1024;
     int64_t b0 = std::min<int64_t>(per * shard_ix, img->n_blocks), b1 = std::min<int64_t>(b0 + per, img->n_blocks);
     ds->shard_lo = b0 * 64; ds->shard_hi = b1 * 64;
-    ds->blk_lo = std::max<int64_t>(b0 - 1, 0);
-    int64_t blk_hi = std::min<int64_t>(b1 + 1, img->n_blocks);
+    ds->blk_lo = std::max<int64_t>((b0 & ~(int64_t)3) - 4, 0);   // multiple of 4: 256-bit loads stay aligned
+    int64_t blk_hi = std::min<int64_t>(b1 + 4, img->n_blocks);
     ds->blk_n = blk_hi - ds->blk_lo;
     GUIDO_CUDA(cudaMalloc(&ds->d_planes, (size_t)(ds->blk_n + 1) * sizeof(ulonglong2)));
     GUIDO_CUDA(cudaMemsetAsync(ds->d_planes + ds->blk_n, 0, sizeof(ulonglong2), ds->stream));
@@ -105,6 +107,19 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_start, rs.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_end, re.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_kind, rk.data(), (size_t)ds->n_runs, cudaMemcpyHostToDevice, ds->stream));
+    // first run whose end lies beyond (tile start - 32), one entry per 65536-base tile
+    const int64_t n_rt = img->padded_bases / 65536 + 2;
+    std::vector<uint32_t> first((size_t)n_rt);
+    size_t ri = 0;
+    for (int64_t t = 0; t < n_rt; t++) {
+        const int64_t from = std::max<int64_t>(t * 65536 - 32, 0);
+        while (ri < img->runs.size() && (int64_t)img->runs[ri].end <= from) ri++;
+        // bit 31: some run touches [tile start - 32, tile end + 32) -- the kernels' slow-path flag
+        const bool touched = ri < img->runs.size() && (int64_t)img->runs[ri].start < (t + 1) * 65536 + 32;
+        first[(size_t)t] = (uint32_t)ri | (touched ? 0x80000000u : 0u);
+    }
+    GUIDO_CUDA(cudaMalloc(&ds->d_tile_first_run, (size_t)n_rt * 4));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_tile_first_run, first.data(), (size_t)n_rt * 4, cudaMemcpyHostToDevice, ds->stream));
     GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
     return GUIDO_OK;
 }
@@ -174,6 +189,18 @@ int guido_device_count(void) {
         if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ok++;
     }
     return ok;
+}
+
+int guido_host_alloc(int64_t bytes, void **out) {
+    if (bytes < 0 || !out) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    *out = nullptr;
+    GUIDO_CUDA(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+    return GUIDO_OK;
+}
+
+int guido_host_free(void *p) {
+    if (p) GUIDO_CUDA(cudaFreeHost(p));
+    return GUIDO_OK;
 }
 
 int guido_image_upload(guido_image *img, int32_t device, int32_t shard_ix, int32_t n_shards) {
@@ -305,7 +332,7 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
     cudaStream_t st = (cudaStream_t)stream;
     GUIDO_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-    if (algo == GUIDO_OT_INDEX)
+    if (algo == GUIDO_OT_INDEX || (algo == GUIDO_OT_AUTO && ot_index_applicable(op, n_guides)))
         return launch_ot_index(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
                                (uint64_t)cap, (unsigned long long *)d_count, nullptr, st, nullptr);
     return launch_ot_scan(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
@@ -326,7 +353,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     std::vector<uint32_t> enc((size_t)(2 * n_guides));
     if ((rc = guido_encode_guides(protos, n_guides, enc.data()))) return rc;
     if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, std::max<int64_t>(8 * n_guides, 8)))) return rc;
-    const bool use_index = algo == GUIDO_OT_INDEX;
+    const bool use_index = algo == GUIDO_OT_INDEX || (algo == GUIDO_OT_AUTO && ot_index_applicable(op, n_guides));
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
     int launches = 0;
     GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
@@ -358,25 +385,25 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         dcap = (int64_t)found;  // exact size known now: one more pass
     }
     *n_hits = (int64_t)found;
-    std::vector<guido_ot_hit> tmp((size_t)found);
-    if (found) GUIDO_CUDA(cudaMemcpyAsync(tmp.data(), ds->d_out[0], (size_t)found * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
+    // canonical (guide, gpos, strand) order on the device, then one copy straight into the
+    // caller's buffer (fast when that buffer is pinned, see guido_host_alloc)
+    if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;
+    int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
+    if (ncopy) GUIDO_CUDA(cudaMemcpyAsync(hits, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
     GUIDO_CUDA(cudaEventRecord(ds->ev[3], st));
     GUIDO_CUDA(cudaStreamSynchronize(st));
-    std::sort(tmp.begin(), tmp.end(), [](const guido_ot_hit &a, const guido_ot_hit &b) {
-        if (a.guide != b.guide) return a.guide < b.guide;
-        if (a.gpos != b.gpos) return a.gpos < b.gpos;
-        return (a.hi >> 31) < (b.hi >> 31);
-    });
-    int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
-    if (ncopy) memcpy(hits, tmp.data(), (size_t)ncopy * sizeof(guido_ot_hit));
-    int64_t d2h = 16 + (int64_t)found * 16, h2d = 8 * n_guides;
+    int64_t d2h = 16 + ncopy * 16, h2d = 8 * n_guides;
+    if ((int64_t)found > cap) {
+        set_error("output capacity too small: need %lld hits", (long long)found);
+        return GUIDO_ERR_CAPACITY;
+    }
 
     if (raw_flags) {
         // key presence (off_targets.py:183-184): any raw bowtie alignment, PAM mismatches allowed
         // inside the seed budget.  A valid hit is a raw alignment, so only guides without one
         // need the relaxed all-window pass.
         memset(raw_flags, 0, (size_t)n_guides);
-        for (auto &h : tmp) raw_flags[h.guide] = 1;
+        for (int64_t i = 0; i < (int64_t)found; i++) raw_flags[hits[i].guide] = 1;
         std::vector<int64_t> todo;
         for (int64_t g = 0; g < n_guides; g++) if (!raw_flags[g]) todo.push_back(g);
         if (!todo.empty()) {

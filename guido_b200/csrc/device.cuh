@@ -19,11 +19,13 @@ namespace guido {
 struct DeviceState {
     int device = -1;
     int sm_count = 0;
+    int scan_grid[2] = {0, 0};  // resident-CTA grids of the PAM count / fill kernels (cached)
     int64_t blk_lo = 0;  // first resident block (global block index), includes the halo
     int64_t blk_n = 0;   // resident blocks (+1 spare at the end so `next` loads stay in bounds)
     ulonglong2 *d_planes = nullptr;
     uint32_t *d_run_start = nullptr, *d_run_end = nullptr;
     uint8_t *d_run_kind = nullptr;
+    uint32_t *d_tile_first_run = nullptr;  // per 65536-base tile: first run ending after tile start - 32
     int n_runs = 0;
     int64_t shard_lo = 0, shard_hi = 0;  // owned global positions (PAM starts), 64-aligned
     cudaStream_t stream = nullptr;
@@ -57,6 +59,7 @@ struct PlanesView {
     int64_t blk_n;
     const uint32_t *run_start, *run_end;
     const uint8_t *run_kind;
+    const uint32_t *tile_first_run;
     int n_runs;
 };
 
@@ -78,6 +81,10 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
                    unsigned long long *d_count, uint8_t *d_flags, unsigned long long *d_site_count,
                    cudaStream_t stream, int *n_launches);
+
+int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t n_guides, cudaStream_t stream,
+                     int *n_launches);
+bool ot_index_applicable(const OtParams &op, int64_t n_guides);
 
 int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
                     const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,

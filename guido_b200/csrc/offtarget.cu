@@ -1,29 +1,46 @@
 // offtarget.cu -- batched <=k-mismatch off-target search over the bit-plane genome image.
 //
 // Sits under run_bowtie (reference guido/off_targets.py:89-227): replaces the bowtie 1
-// `-n/-l/-e -a -y` subprocess.  Two kernels:
+// `-n/-l/-e -a -y` subprocess.  One kernel template, two ways to consume the PAM-valid windows:
 //
-//   ot_scan_kernel   brute force: every PAM-valid window (both strands) x every guide, by plane
-//                    XOR + OR + popc.  Integer-issue bound.  Also the raw-alignment flag pass
-//                    (all windows, PAM letters inside the compare) that decides key presence.
-//   ot_index_kernel  (offtarget_index.cu) guide-side seed index; windows look up their core.
+//   ot_kernel<false>  brute force: every PAM-valid window (both strands) x every guide, by plane
+//                     XOR + OR + popc.  Integer-issue bound.  Also the raw-alignment flag pass
+//                     (all windows, PAM letters inside the compare) that decides key presence.
+//   ot_kernel<true>   guide-side seed index: a window looks up the bucket of its core k-mer and
+//                     compares only the distal bases of the guides filed there.  Memory bound.
+//
+// Both share the front end: a CTA streams 16384-base tiles, extracts the PAM-valid windows of both
+// strands into a shared-memory ring (guide orientation, two bit planes per window) and hands full
+// rounds of windows to the consumer, so the consumer always works on dense batches.
 //
 // Plane trick: with guides and windows both stored as two 1-bit planes (hi, lo) in GUIDE
 // orientation, the per-position mismatch mask of all 20 positions is two LOP3s:
 //     m = (A_w ^ A_g) | (B_w ^ B_g)
 // and the mismatch count is one POPC -- no 2-bit fold, no shifts in the inner loop.
 #include <algorithm>
+#include <cstdlib>
+#include <functional>
+#include <vector>
 
 #include "scan_common.cuh"
 
 namespace guido {
 
-constexpr int kRing = 4096;        // site ring buffer entries per CTA (3 x u32 each = 48 KB)
 constexpr int kSitesPerThread = 8;
-constexpr int kRound = kThreads * kSitesPerThread;  // 2048 sites compared per round
+
+// guide-side seed index (built per search call by the idx_* kernels below), structure of arrays:
+// the search streams `keys` only and touches `guides` on a hit
+struct OtIndex {
+    const uint32_t *offsets;  // n_buckets + 1
+    const uint32_t *keys;     // distal_hi | distal_lo << dl | core_mm << 2*dl
+    const uint32_t *guides;   // guide index of the entry
+    int cl, dl;               // core / distal length (cl + dl = 20)
+    int wide;                 // average bucket is large: walk buckets warp-wide
+};
 
 struct OtScanArgs {
     PlanesView pv;
+    OtIndex ix;
     OtParams op;
     ScanRange r;
     int64_t first_block;
@@ -47,6 +64,7 @@ __device__ __forceinline__ uint32_t extract_bits(uint64_t w0, uint64_t w1, uint6
 }
 
 // compare one round of sites held in the ring [head, head+n) against every guide
+template <int RING>
 __device__ __forceinline__ void compare_round(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
                                               const uint32_t *sQ, uint32_t head, uint32_t n) {
     uint32_t A[kSitesPerThread], B[kSitesPerThread];
@@ -55,7 +73,7 @@ __device__ __forceinline__ void compare_round(const OtScanArgs &a, const uint32_
 #pragma unroll
     for (int k = 0; k < kSitesPerThread; k++) {
         uint32_t j = k * kThreads + threadIdx.x;
-        uint32_t idx = (head + j) & (kRing - 1);
+        uint32_t idx = (head + j) & (RING - 1);
         if (j < n) { A[k] = sA[idx] & cmp; B[k] = sB[idx] & cmp; valid |= 1u << k; }
         else { A[k] = 0xffffffffu; B[k] = 0xffffffffu; }
     }
@@ -81,7 +99,7 @@ __device__ __forceinline__ void compare_round(const OtScanArgs &a, const uint32_
                 } else {
                     unsigned long long slot = atomicAdd(a.count, 1ull);
                     if (slot < a.cap) {
-                        uint32_t idx = (head + k * kThreads + threadIdx.x) & (kRing - 1);
+                        uint32_t idx = (head + k * kThreads + threadIdx.x) & (RING - 1);
                         guido_ot_hit h;
                         h.guide = g; h.gpos = sQ[idx]; h.hi = sA[idx]; h.lo = sB[idx];
                         a.hits[slot] = h;
@@ -92,11 +110,158 @@ __device__ __forceinline__ void compare_round(const OtScanArgs &a, const uint32_
     }
 }
 
-__global__ void __launch_bounds__(kThreads) ot_scan_kernel(const OtScanArgs a) {
+// per-warp scratch of the index lookup
+struct LookupSmem {
+    uint32_t start[kThreads / 32][32];
+    uint32_t pref[kThreads / 32][33];
+    uint32_t dist[kThreads / 32][32];
+};
+
+// Look the sites of the ring [head, head+n) up in the guide-side seed index.  A warp takes 32 sites
+// at a time: every lane fetches one site's bucket range (32 independent loads), the ranges are
+// flattened by a warp prefix sum, and the lanes then walk the flattened key list 4 x 32 keys per
+// step (coalesced 4-byte loads inside a bucket, 4 independent loads per lane in flight), so lanes
+// stay busy and HBM latency stays covered whatever the bucket sizes are.
+template <int RING>
+__device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
+                                             const uint32_t *sQ, uint32_t head, uint32_t n, LookupSmem &ls) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cl = a.ix.cl, dl = a.ix.dl;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    const int tot_max = a.op.total_max;
+    const uint32_t *__restrict__ keys = a.ix.keys;
+    uint32_t *w_start = ls.start[warp], *w_pref = ls.pref[warp], *w_dist = ls.dist[warp];
+    for (uint32_t b = warp * 32; b < n; b += kThreads) {
+        const uint32_t j = b + lane;
+        const uint32_t idx = (head + j) & (RING - 1);
+        uint32_t start = 0, len = 0, dist = 0;
+        if (j < n) {
+            const uint32_t A = sA[idx], B = sB[idx];
+            const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+            start = __ldg(&a.ix.offsets[key]);
+            len = __ldg(&a.ix.offsets[key + 1]) - start;
+            dist = (A & dmask) | ((B & dmask) << dl);
+        }
+        uint32_t inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t total = __shfl_sync(kFull, inc, 31);
+        __syncwarp();
+        w_start[lane] = start;
+        w_pref[lane] = inc - len;
+        w_dist[lane] = dist;
+        if (lane == 31) w_pref[32] = total;
+        __syncwarp();
+        uint32_t cur = 0;
+        for (uint32_t t0 = lane; t0 < total; t0 += 32 * U) {
+            uint32_t pos[U], site[U], kv[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t t = t0 + 32 * u;
+                if (t < total) {
+                    while (t >= w_pref[cur + 1]) cur++;
+                    site[u] = cur;
+                    pos[u] = w_start[cur] + (t - w_pref[cur]);
+                } else {
+                    site[u] = 0xffffffffu;
+                    pos[u] = 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) kv[u] = (site[u] != 0xffffffffu) ? __ldg(&keys[pos[u]]) : 0u;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (site[u] == 0xffffffffu) continue;
+                const uint32_t x = kv[u] ^ w_dist[site[u]];
+                const uint32_t m = (x | (x >> dl)) & dmask;
+                if ((int)(__popc(m) + (x >> (2 * dl))) <= tot_max) {
+                    unsigned long long slot = atomicAdd(a.count, 1ull);
+                    if (slot < a.cap) {
+                        const uint32_t si = (head + b + site[u]) & (RING - 1);
+                        guido_ot_hit h;
+                        h.guide = __ldg(&a.ix.guides[pos[u]]); h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
+                        a.hits[slot] = h;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Same lookup for LARGE buckets (>= ~12 guides per bucket, e.g. 100k guides): the warp walks one
+// bucket at a time with all 32 lanes -- coalesced 128-byte key loads and no per-key search for
+// the owning site -- and keeps the loads of 8 buckets in flight together.
+template <int RING>
+__device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
+                                                  const uint32_t *sQ, uint32_t head, uint32_t n) {
+    constexpr int U = 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cl = a.ix.cl, dl = a.ix.dl;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    const int tot_max = a.op.total_max;
+    const uint32_t *__restrict__ keys = a.ix.keys;
+    for (uint32_t b = warp * 32; b < n; b += kThreads) {
+        const uint32_t j = b + lane;
+        uint32_t start = 0, len = 0, dist = 0;
+        if (j < n) {
+            const uint32_t idx = (head + j) & (RING - 1);
+            const uint32_t A = sA[idx], B = sB[idx];
+            const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+            start = __ldg(&a.ix.offsets[key]);
+            len = __ldg(&a.ix.offsets[key + 1]) - start;
+            dist = (A & dmask) | ((B & dmask) << dl);
+        }
+        for (int s0 = 0; s0 < 32; s0 += U) {
+            uint32_t st[U], ln[U], ds[U], maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                st[u] = __shfl_sync(kFull, start, s0 + u);
+                ln[u] = __shfl_sync(kFull, len, s0 + u);
+                ds[u] = __shfl_sync(kFull, dist, s0 + u);
+                maxlen = max(maxlen, ln[u]);
+            }
+            for (uint32_t off = lane; off < maxlen; off += 32) {
+                uint32_t kv[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) kv[u] = (off < ln[u]) ? __ldg(&keys[st[u] + off]) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t x = kv[u] ^ ds[u];
+                    const uint32_t m = (x | (x >> dl)) & dmask;
+                    if (off < ln[u] && (int)(__popc(m) + (x >> (2 * dl))) <= tot_max) {
+                        unsigned long long slot = atomicAdd(a.count, 1ull);
+                        if (slot < a.cap) {
+                            const uint32_t si = (head + b + s0 + u) & (RING - 1);
+                            guido_ot_hit h;
+                            h.guide = __ldg(&a.ix.guides[st[u] + off]); h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
+                            a.hits[slot] = h;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool kIndex>
+struct OtCfg {
+    // the brute-force consumer wants 8 sites per thread in registers (2048 per round); the index
+    // consumer only needs dense warps, so a smaller ring buys occupancy (more loads in flight)
+    static constexpr int kRing = kIndex ? 2048 : 4096;
+    static constexpr int kRound = kIndex ? 1024 : kThreads * kSitesPerThread;
+};
+
+template <bool kIndex>
+__global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
+    constexpr int RING = OtCfg<kIndex>::kRing, ROUND = OtCfg<kIndex>::kRound;
     extern __shared__ uint32_t s_dyn[];
-    uint32_t *sA = s_dyn, *sB = s_dyn + kRing, *sQ = s_dyn + 2 * kRing;
+    uint32_t *sA = s_dyn, *sB = s_dyn + RING, *sQ = s_dyn + 2 * RING;
+    __shared__ LookupSmem s_lookup;  // unused (and tiny) in the brute-force instantiation
     __shared__ uint32_t s_warp[kThreads / 32];
-    __shared__ int s_run[3];
     const int lane = threadIdx.x & 31;
     const int P = a.op.pam.len;
     const int W = kProto + P;
@@ -108,19 +273,10 @@ __global__ void __launch_bounds__(kThreads) ot_scan_kernel(const OtScanArgs a) {
     for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int64_t tile_block = a.first_block + (int64_t)tile * kThreads;
         const uint32_t t0 = (uint32_t)(tile_block * 64), t1 = t0 + kTileBases;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int r_lo = first_run_ending_after(a.pv, t0 >= 32 ? t0 - 32 : 0);
-            int r_hi = r_lo, skip = 0;
-            while (r_hi < a.pv.n_runs && a.pv.run_start[r_hi] < t1 + 32) {
-                if (a.pv.run_start[r_hi] <= t0 && a.pv.run_end[r_hi] >= t1) skip = 1;
-                r_hi++;
-            }
-            s_run[0] = r_lo; s_run[1] = r_hi; s_run[2] = skip;
-        }
-        __syncthreads();
-        if (s_run[2]) continue;
-        const int r_lo = s_run[0], r_hi = s_run[1];
+        int r_lo, r_hi;
+        bool skip;
+        tile_runs(a.pv, t0, t1, r_lo, r_hi, skip);
+        if (skip) continue;
         const int64_t block = tile_block + threadIdx.x;
         const ulonglong2 cur = load_block(a.pv, block);
         ulonglong2 nxt = shfl_down_u2(cur, 1), prv = shfl_up_u2(cur, 1);
@@ -137,13 +293,13 @@ __global__ void __launch_bounds__(kThreads) ot_scan_kernel(const OtScanArgs a) {
         if (r_hi > r_lo && (hf | hr))
             veto_hits(a.pv, r_lo, r_hi, raw ? kScanRawWindow : GUIDO_SCAN_STRICT, P, (uint32_t)(block * 64), hf, hr);
 
-        // append this tile's sites to the ring; run full compare rounds whenever 2048 are queued
+        // append this tile's sites to the ring; run full rounds whenever enough are queued
         while (true) {
             uint32_t total;
             const uint32_t mine = __popcll(hf) + __popcll(hr);
             uint32_t off = block_exclusive_scan(mine, s_warp, &total);
             if (total == 0) break;
-            const uint32_t space = kRing - qlen;
+            const uint32_t space = RING - qlen;
             const uint32_t base = (uint32_t)(block * 64);
             uint32_t appended = total < space ? total : space;
             // forward-strand sites first, then reverse, lowest bit first; stop at `space`
@@ -165,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) ot_scan_kernel(const OtScanArgs a) {
                         hi_bits |= 0x80000000u;
                         q = base + i;
                     }
-                    uint32_t idx = (head + qlen + off) & (kRing - 1);
+                    uint32_t idx = (head + qlen + off) & (RING - 1);
                     sA[idx] = hi_bits; sB[idx] = lo_bits; sQ[idx] = q;
                     off++;
                 }
@@ -174,18 +330,44 @@ __global__ void __launch_bounds__(kThreads) ot_scan_kernel(const OtScanArgs a) {
             qlen += appended;
             n_sites += (threadIdx.x == 0) ? appended : 0;
             __syncthreads();
-            while (qlen >= kRound) {
-                compare_round(a, sA, sB, sQ, head, kRound);
-                head = (head + kRound) & (kRing - 1);
-                qlen -= kRound;
+            while (qlen >= ROUND) {
+                if constexpr (kIndex) {
+                    if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, ROUND);
+                    else lookup_round<RING>(a, sA, sB, sQ, head, ROUND, s_lookup);
+                }
+                else compare_round<RING>(a, sA, sB, sQ, head, ROUND);
+                head = (head + ROUND) & (RING - 1);
+                qlen -= ROUND;
             }
             __syncthreads();
             if (appended == total) break;
         }
     }
     __syncthreads();
-    if (qlen) compare_round(a, sA, sB, sQ, head, qlen);
+    if (qlen) {
+        if constexpr (kIndex) {
+            if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, qlen);
+            else lookup_round<RING>(a, sA, sB, sQ, head, qlen, s_lookup);
+        }
+        else compare_round<RING>(a, sA, sB, sQ, head, qlen);
+    }
     if (threadIdx.x == 0 && a.site_count) atomicAdd(a.site_count, n_sites);
+}
+
+template <bool kIndex>
+static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream) {
+    a.first_block = a.r.lo / 64;
+    int64_t last_block = ((int64_t)a.r.hi - 1) / 64;
+    a.n_tiles = (uint32_t)((last_block - a.first_block + 1 + kThreads - 1) / kThreads);
+    const int smem = 3 * OtCfg<kIndex>::kRing * (int)sizeof(uint32_t);
+    GUIDO_CUDA(cudaFuncSetAttribute(ot_kernel<kIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_kernel<kIndex>, kThreads, smem));
+    int grid = ds->sm_count * std::max(per_sm, 1);
+    if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
+    ot_kernel<kIndex><<<grid, kThreads, smem, stream>>>(a);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
 }
 
 int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
@@ -195,20 +377,185 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.first_block = r.lo / 64;
-    int64_t last_block = ((int64_t)r.hi - 1) / 64;
-    a.n_tiles = (uint32_t)((last_block - a.first_block + 1 + kThreads - 1) / kThreads);
+    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
-    const int smem = 3 * kRing * (int)sizeof(uint32_t);
-    GUIDO_CUDA(cudaFuncSetAttribute(ot_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0;
-    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_scan_kernel, kThreads, smem));
-    int grid = ds->sm_count * std::max(per_sm, 1);
-    if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
-    ot_scan_kernel<<<grid, kThreads, smem, stream>>>(a);
-    GUIDO_CUDA(cudaGetLastError());
+    int rc = launch_ot_kernel<false>(ds, a, stream);
+    if (rc) return rc;
     if (n_launches) *n_launches += 1;
+    return GUIDO_OK;
+}
+
+// ------------------------------------------------------------------------- seed index build
+//
+// Key of a guide / window = its core_len PAM-proximal bases as (hi plane << cl) | lo plane.
+// Every guide is filed under ALL keys within <= core_mm substitutions of its own core (436 keys
+// for core 10 / 2 mismatches), so a window finds, under its own key, exactly the guides whose
+// core is within the budget -- the bowtie seed rule -- and only the distal bases are left to
+// compare.  A substitution XORs the 2-bit code with 1..3, so the variants are the (xh, xl) plane
+// masks with popc(xh | xl) <= core_mm; the host enumerates them once per call.
+
+struct IdxArgs {
+    const uint2 *guides;
+    uint32_t n_guides;
+    const uint32_t *variants;  // xh | xl << 16
+    uint32_t n_variants;
+    int cl, dl;
+    uint32_t *counts;          // n_buckets + 1 (pass 1), becomes offsets after the scan
+    uint32_t *fill;            // n_buckets
+    uint32_t *keys, *ids;      // n_entries each
+};
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
+    const unsigned long long total = (unsigned long long)a.n_guides * a.n_variants;
+    const uint32_t cmask = (1u << a.cl) - 1, dmask = (1u << a.dl) - 1;
+    for (unsigned long long t = blockIdx.x * 256ull + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * 256ull) {
+        const uint32_t g = (uint32_t)(t / a.n_variants), v = (uint32_t)(t % a.n_variants);
+        const uint2 G = __ldg(&a.guides[g]);
+        const uint32_t var = __ldg(&a.variants[v]);
+        const uint32_t xh = var & 0xffff, xl = var >> 16;
+        const uint32_t key = ((((G.x >> a.dl) & cmask) ^ xh) << a.cl) | (((G.y >> a.dl) & cmask) ^ xl);
+        if constexpr (!kFill) {
+            atomicAdd(&a.counts[key], 1u);
+        } else {
+            const uint32_t pos = a.counts[key] + atomicAdd(&a.fill[key], 1u);
+            a.keys[pos] = (G.x & dmask) | ((G.y & dmask) << a.dl) | ((uint32_t)__popc(xh | xl) << (2 * a.dl));
+            a.ids[pos] = g;
+        }
+    }
+}
+
+// in-place exclusive scan of n u32 values: 4096 per block, then the block sums, then the fix-up
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint32_t n, uint32_t *block_sums) {
+    __shared__ uint32_t s_w[32];
+    const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = (base + i < n) ? data[base + i] : 0; sum += v[i]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(kFull, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_w[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(kFull, wi, d); if (lane >= d) wi += t; }
+        s_w[lane] = wi - w;
+        if (lane == 31) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_w[warp] + inc - sum;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { if (base + i < n) data[base + i] = run; run += v[i]; }
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *block_sums, uint32_t n_blocks) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(kFull, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_w[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(kFull, wi, d); if (lane >= d) wi += t; }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + s_w[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_w[31] + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) scan_fixup_kernel(uint32_t *data, uint32_t n, const uint32_t *block_sums) {
+    const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
+    const uint32_t add = block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (base + i < n) data[base + i] += add;
+}
+
+static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
+    // all (xh, xl) with popc(xh | xl) <= cm over cl positions; per chosen position 3 substitutions
+    out->clear();
+    std::function<void(int, uint32_t, uint32_t, int)> rec = [&](int from, uint32_t xh, uint32_t xl, int left) {
+        out->push_back(xh | (xl << 16));
+        if (!left) return;
+        for (int p = from; p < cl; p++)
+            for (int d = 1; d <= 3; d++)
+                rec(p + 1, xh | ((uint32_t)(d >> 1) << p), xl | ((uint32_t)(d & 1) << p), left - 1);
+    };
+    rec(0, 0, 0, cm);
+}
+
+bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
+    if (op.raw_mode || op.core_len < 6 || op.core_len > 12 || op.core_max > 3) return false;
+    std::vector<uint32_t> v;
+    enumerate_variants(op.core_len, op.core_max, &v);
+    return (double)v.size() * (double)n_guides < 1.5e9;  // entries are addressed with 32 bits (12 GB)
+}
+
+int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                    unsigned long long *d_count, unsigned long long *d_site_count,
+                    cudaStream_t stream, int *n_launches) {
+    if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
+    if (!ot_index_applicable(op, n_guides)) {
+        set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
+        return GUIDO_ERR_ARG;
+    }
+    const int cl = op.core_len, dl = kProto - cl;
+    std::vector<uint32_t> variants;
+    enumerate_variants(cl, op.core_max, &variants);
+    const uint32_t n_buckets = 1u << (2 * cl);
+    const uint64_t n_entries = (uint64_t)variants.size() * (uint64_t)n_guides;
+    const uint32_t n_scan = n_buckets + 1, n_scan_blocks = (n_scan + 4095) / 4096;
+    // d_bucket: [counts/offsets n_buckets+1][fill n_buckets][block sums][variants]
+    const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16;
+    int rc;
+    if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
+    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_entries * 8))) return rc;
+    uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
+             *d_var = sums + n_scan_blocks;
+    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_entries;
+    GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
+    // variants are tiny; a pageable async copy is staged by the driver before it returns
+    GUIDO_CUDA(cudaMemcpyAsync(d_var, variants.data(), variants.size() * 4, cudaMemcpyHostToDevice, stream));
+    IdxArgs ia;
+    ia.guides = d_guides; ia.n_guides = (uint32_t)n_guides; ia.variants = d_var; ia.n_variants = (uint32_t)variants.size();
+    ia.cl = cl; ia.dl = dl; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
+    const int bgrid = (int)std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)ds->sm_count * 32);
+    idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
+    GUIDO_CUDA(cudaGetLastError());
+
+    OtScanArgs a;
+    a.pv = pv; a.op = op; a.r = r;
+    // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
+    const char *force = getenv("GUIDO_OT_WIDE");
+    const int wide = force ? atoi(force) : (n_entries / n_buckets >= 12);
+    a.ix = OtIndex{counts, keys, ids, cl, dl, wide};
+    a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
+    a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
+    rc = launch_ot_kernel<true>(ds, a, stream);
+    if (rc) return rc;
+    if (n_launches) *n_launches += 6;
     return GUIDO_OK;
 }
 

@@ -1,163 +1,389 @@
 // pam_scan.cu -- whole-genome / region PAM scan, both strands, ordered compaction.
 //
 // Sits under Locus._find_guides_in_interval (reference guido/locus.py:178-183): the two
-// overlapping `re.finditer` passes become one streaming pass over the bit-plane image.
+// overlapping `re.finditer` passes become two streaming passes over the bit-plane image.
 //
-// One CTA = one tile of 256 blocks (16384 bases); a thread owns one 64-base block:
-//   1. 128-bit coalesced load of {lo,hi}; the next block's words come from lane+1 by shuffle
-//      (lane 31 re-loads, an L1 hit) -- that is the PAM-length halo;
-//   2. per-strand 64-bit hit masks by bit-parallel set membership, AND-ed across PAM offsets;
-//   3. run veto only in the rare tiles that touch a non-ACGT run / contig pad;
-//   4. CTA prefix sum of popcounts, then a single-pass chained scan across tiles (decoupled
-//      look-back on 64-bit {flag,count} descriptors; tiles are handed out by an atomic ticket so
-//      a waiting tile's predecessors are always resident) => ascending output, one genome read;
-//   5. hits staged in shared memory and written as coalesced 4-byte stores.
+// Two launches, no inter-CTA waiting anywhere:
+//   pam_count_kernel  per tile (1024 blocks = 65536 bases): hit masks -> popcounts -> tile counts
+//   pam_fill_kernel   per tile: hit masks again (the planes come from L2 when the shard fits,
+//                     else from HBM); the tile's output offset is the running sum of the tile
+//                     counts (each CTA adds the counts of the tiles it strides over); CTA prefix
+//                     sum; hits staged in shared memory; coalesced 4-byte stores
+// A single-pass chained scan (decoupled look-back) was built first and rejected: with every
+// resident CTA on a tile of the same wave, the look-back polls hundreds of descriptors per tile
+// and the polling traffic alone saturated L2 (profiles/r1_pam_scan.md).
 //
-// HBM traffic per launch (algorithmic): 0.25 B/base read + 4 B per hit written.
+// A thread owns 4 consecutive blocks (256 bases), handled as eight 32-bit words per plane:
+//   * two 256-bit loads (LDG.E.256) fetch its 64 bytes of {lo,hi} words; the next block (the
+//     PAM-length halo) comes from lane+1 by shuffle, lane 31 loads it itself;
+//   * set membership per PAM position is 4 LOP3 per word, branch-free: every base set is a
+//     boolean function of (hi, lo), evaluated in algebraic normal form
+//         f = c0 ^ (c1 & lo) ^ (c2 & hi) ^ (c3 & hi & lo)
+//     with all-ones / all-zeros coefficients prepared on the host; PAM offsets are funnel shifts;
+//   * the run veto (non-ACGT runs, contig pads) happens only in the rare tiles that touch a run,
+//     as bit masks: invalid-base masks per word, dilated by the window length with shift-OR
+//     doubling -- no per-hit loop, no per-hit global load.
+//
+// HBM traffic per scan (algorithmic): 0.25 B/base read + 4 B per hit written.
 #include <algorithm>
 
 #include "scan_common.cuh"
 
 namespace guido {
 
-constexpr int kStage = 2048;  // staged hits per strand and tile (NGG: ~1024 expected)
-constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
+constexpr int kBpt = 4;                        // blocks per thread
+constexpr int kWpt = 2 * kBpt;                 // 32-bit words per thread and plane
+constexpr int kScanTileBlocks = kThreads * kBpt;
+constexpr int kScanTileBases = kScanTileBlocks * 64;
+constexpr int kStage = 5120;  // staged hits per strand and tile (NGG: 4096 expected, sigma 62)
+
+static_assert(kScanTileBases == (1 << kTileRunShift), "tile_first_run granularity must match the scan tile");
+
+// per strand and PAM position: ANF coefficients of the base set, or skip (set = all four bases)
+struct PamCoef {
+    uint32_t c[2][kMaxPam][4];
+    uint8_t skip[2][kMaxPam];
+    uint8_t same[2][kMaxPam];  // same set as the previous non-skipped position: reuse its masks
+    int len;
+};
 
 struct PamScanArgs {
     PlanesView pv;
-    PamSpec pam;
+    PamCoef pc;
     ScanRange r;
     int mode;
-    int64_t first_block;  // global block index of tile 0's first block
+    uint32_t first_tile;  // absolute tile index (tile t covers blocks [1024 t, 1024 t + 1024))
     uint32_t n_tiles;
     uint32_t *out_fw, *out_rv;
     unsigned long long cap_fw, cap_rv;
-    unsigned long long *counts;  // [0] n_fw, [1] n_rv
-    unsigned long long *desc;    // 2 * n_tiles
-    unsigned int *ticket;
+    unsigned long long *counts;   // [0] n_fw, [1] n_rv
+    unsigned long long *tiles;    // n_tiles: per-tile counts, fw | rv << 32
+    int vec_ok;                   // both output arrays are 16-byte aligned: copy out as uint4
 };
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
-    return *reinterpret_cast<const volatile unsigned long long *>(p);
-}
+// planes of the thread's 4 blocks + the following block, as 32-bit words (10 per plane)
+struct ThreadWords {
+    uint32_t lo[kWpt + 2], hi[kWpt + 2];
+};
 
-// chained-scan look-back for one strand, run by one full warp; returns the exclusive prefix
-__device__ __forceinline__ unsigned long long lookback(unsigned long long *desc, uint32_t tile,
-                                                       int strand, unsigned long long agg) {
-    int lane = threadIdx.x & 31;
-    unsigned long long *mine = desc + 2ull * tile + strand;
-    if (tile == 0) {
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(mine) = kFlagPrefix | agg;
-        return 0;
-    }
-    if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(mine) = kFlagAgg | agg;
-    unsigned long long excl = 0;
-    int64_t look = (int64_t)tile - 1;
-    while (true) {
-        int64_t idx = look - lane;
-        unsigned long long d = kFlagPrefix;  // tiles before the first contribute a zero prefix
-        if (idx >= 0) {
-            const unsigned long long *p = desc + 2ull * (uint64_t)idx + strand;
-            do { d = ld_volatile_u64(p); } while ((d >> 62) == 0);
-        }
-        unsigned pm = __ballot_sync(kFull, (d >> 62) == 2);
-        int first = pm ? (__ffs(pm) - 1) : 32;
-        unsigned long long v = (lane <= first) ? (d & kValMask) : 0ull;
+// raw registers of one thread's tile slice: requested early (software pipelining), expanded late
+struct ThreadRaw {
+    unsigned long long q[2 * kBpt];  // lo0, hi0, lo1, hi1, ...
+    ulonglong2 halo;                 // lane 31 only: the block after the warp's last
+};
+
+__device__ __forceinline__ void issue_thread_loads(const PlanesView &pv, int64_t block0, int lane, ThreadRaw &raw) {
+    const int64_t i = block0 - pv.blk_lo;
+    if (i >= 0 && i + kBpt <= pv.blk_n) {
+        const ulonglong2 *p = pv.planes + i;  // 32-byte aligned: blk_lo and block0 are multiples of 4
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(raw.q[0]), "=l"(raw.q[1]), "=l"(raw.q[2]), "=l"(raw.q[3]) : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(raw.q[4]), "=l"(raw.q[5]), "=l"(raw.q[6]), "=l"(raw.q[7]) : "l"(p + 2));
+    } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        excl += v;
-        if (pm) break;
-        look -= 32;
+        for (int k = 0; k < kBpt; k++) { ulonglong2 b = load_block(pv, block0 + k); raw.q[2 * k] = b.x; raw.q[2 * k + 1] = b.y; }
     }
-    if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(mine) = kFlagPrefix | (excl + agg);
-    return excl;
+    raw.halo = make_ulonglong2(0ull, 0ull);
+    if (lane == 31) raw.halo = load_block(pv, block0 + kBpt);
 }
 
-__global__ void __launch_bounds__(kThreads) pam_scan_kernel(const PamScanArgs a) {
-    __shared__ uint32_t s_warp[kThreads / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ int s_run[3];                     // run range [lo,hi) touching this tile, skip flag
-    __shared__ unsigned long long s_excl[2];
-    __shared__ uint32_t s_stage[2][kStage];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int P = a.pam.len;
+__device__ __forceinline__ void expand_thread_words(const ThreadRaw &raw, int lane, ThreadWords &t) {
+    const unsigned long long *q = raw.q;
+    ulonglong2 halo = raw.halo;
+    const ulonglong2 first = make_ulonglong2(q[0], q[1]);
+    const ulonglong2 nb = shfl_down_u2(first, 1);
+    if (lane != 31) halo = nb;
+#pragma unroll
+    for (int k = 0; k < kBpt; k++) {
+        t.lo[2 * k] = (uint32_t)q[2 * k]; t.lo[2 * k + 1] = (uint32_t)(q[2 * k] >> 32);
+        t.hi[2 * k] = (uint32_t)q[2 * k + 1]; t.hi[2 * k + 1] = (uint32_t)(q[2 * k + 1] >> 32);
+    }
+    t.lo[kWpt] = (uint32_t)halo.x; t.lo[kWpt + 1] = (uint32_t)(halo.x >> 32);
+    t.hi[kWpt] = (uint32_t)halo.y; t.hi[kWpt + 1] = (uint32_t)(halo.y >> 32);
+}
 
-    while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+// hit words of one strand: bit i of h[w] <=> the PAM matches at base (thread base + 32 w + i)
+__device__ __forceinline__ void strand_hit_words(const ThreadWords &t, const PamCoef &pc, int strand, uint32_t h[kWpt]) {
+#pragma unroll
+    for (int w = 0; w < kWpt; w++) h[w] = 0xffffffffu;
+    uint32_t m[kWpt + 1];
+    for (int i = 0; i < pc.len; i++) {
+        if (pc.skip[strand][i]) continue;  // N: every base; non-ACGT bases are removed by the run veto
+        if (!pc.same[strand][i]) {         // e.g. the second G of NGG reuses the first G's masks
+            const uint32_t c0 = pc.c[strand][i][0], c1 = pc.c[strand][i][1], c2 = pc.c[strand][i][2], c3 = pc.c[strand][i][3];
+#pragma unroll
+            for (int w = 0; w < kWpt + 1; w++)
+                m[w] = c0 ^ (c1 & t.lo[w]) ^ (c2 & t.hi[w]) ^ (c3 & t.hi[w] & t.lo[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < kWpt; w++) h[w] &= __funnelshift_r(m[w], m[w + 1], i);  // i < 32
+    }
+}
+
+// words [a, a+L) OR-ed together for every start bit: z bit p = OR_{d<L} v bit (p+d), L <= 32
+__device__ __forceinline__ uint32_t dilate(uint32_t w0, uint32_t w1, int L) {
+    unsigned long long v = ((unsigned long long)w1 << 32) | w0;
+    int k = 1;
+    while (2 * k <= L) { v |= v >> k; k *= 2; }
+    if (L > k) v |= v >> (L - k);
+    return (uint32_t)v;
+}
+
+// Veto words for the thread's 8 hit words (rare path: tile touches >= 1 run).  A forward hit at p
+// owns window [p-20, p+P), a reverse hit [p, p+P+20) (guides.py:53-67); what is checked depends
+// on the scan mode (see GUIDO_SCAN_* in the header).
+__device__ __forceinline__ void veto_words(const PlanesView &pv, int r_lo, int r_hi, int mode, int P, uint32_t base,
+                                           uint32_t hf[kWpt], uint32_t hr[kWpt]) {
+    // most threads of a tile that touches a run are nowhere near it: skip them (and whole warps)
+    bool near = false;
+    for (int r = r_lo; r < r_hi; r++)
+        near |= __ldg(&pv.run_start[r]) < base + 32 * (kWpt + 2) && __ldg(&pv.run_end[r]) + 32 > base;
+    if (!near) return;
+    // invalid-base words -1 .. 9 around the thread's 256 bases (index w + 1)
+    uint32_t any[kWpt + 3], k0[kWpt + 3];
+#pragma unroll
+    for (int w = 0; w < kWpt + 3; w++) any[w] = k0[w] = 0;
+    for (int r = r_lo; r < r_hi; r++) {
+        const int64_t s = (int64_t)__ldg(&pv.run_start[r]) - ((int64_t)base - 32);
+        const int64_t e = (int64_t)__ldg(&pv.run_end[r]) - ((int64_t)base - 32);
+        const bool kind0 = __ldg(&pv.run_kind[r]) == 0;
+#pragma unroll
+        for (int w = 0; w < kWpt + 3; w++) {
+            const int64_t a = s - 32 * w, b = e - 32 * w;
+            if (b <= 0 || a >= 32) continue;
+            const uint32_t hi_m = b >= 32 ? 0xffffffffu : ((1u << (int)b) - 1);
+            const uint32_t lo_m = a <= 0 ? 0u : ((1u << (int)a) - 1);
+            const uint32_t m = hi_m & ~lo_m;
+            any[w] |= m;
+            if (kind0) k0[w] |= m;
+        }
+    }
+    const int W = P + kProto;
+#pragma unroll
+    for (int w = 0; w < kWpt; w++) {
+        // word w of the thread sits at index w + 1
+        const uint32_t pam_bad = dilate(any[w + 1], any[w + 2], P);
+        uint32_t fbad = pam_bad, rbad = pam_bad;
+        if (mode == GUIDO_SCAN_GUIDE || mode == GUIDO_SCAN_STRICT) {
+            const bool g = (mode == GUIDO_SCAN_GUIDE);  // '+' guides drop literal N / pads only
+            const uint32_t s0 = g ? k0[w] : any[w], s1 = g ? k0[w + 1] : any[w + 1], s2 = g ? k0[w + 2] : any[w + 2];
+            // window starts 20 bases before the PAM: z(p - 20)
+            const uint32_t z0 = dilate(s0, s1, W), z1 = dilate(s1, s2, W);
+            fbad |= __funnelshift_l(z0, z1, kProto);
+            rbad = dilate(any[w + 1], any[w + 2], W);
+        } else if (mode == kScanRawWindow) {
+            fbad = rbad = dilate(any[w + 1], any[w + 2], W);
+        }
+        hf[w] &= ~fbad;
+        hr[w] &= ~rbad;
+    }
+}
+
+// restrict hit words to PAM starts p with r.lo <= p < r.hi and p + P <= r.limit (boundary tiles)
+__device__ __forceinline__ uint32_t range_word(int64_t base, const ScanRange &r, int P) {
+    int64_t hi = (int64_t)r.hi;
+    const int64_t lim = (int64_t)r.limit - P + 1;
+    if (lim < hi) hi = lim;
+    int64_t a = (int64_t)r.lo - base, b = hi - base;
+    if (a < 0) a = 0;
+    if (b > 32) b = 32;
+    if (b <= a) return 0;
+    const uint32_t hm = b >= 32 ? 0xffffffffu : ((1u << (int)b) - 1);
+    const uint32_t lm = a <= 0 ? 0u : ((1u << (int)a) - 1);
+    return hm & ~lm;
+}
+
+// both strands' hit words of one thread for tile `tile` (all zero for tiles inside one run)
+__device__ __forceinline__ int64_t tile_block0(const PamScanArgs &a, uint32_t tile) {
+    return (int64_t)(a.first_tile + tile) * kScanTileBlocks + threadIdx.x * kBpt;
+}
+
+// `raw` holds the thread's planes of this tile, requested one tile earlier (issue_thread_loads)
+__device__ __forceinline__ void tile_hit_words(const PamScanArgs &a, uint32_t tile, const ThreadRaw &raw,
+                                               uint32_t hf[kWpt], uint32_t hr[kWpt]) {
+    const int lane = threadIdx.x & 31;
+    const int P = a.pc.len;
+    const uint32_t t0 = (a.first_tile + tile) * (uint32_t)kScanTileBases;
+    int r_lo, r_hi;
+    bool skip;
+    tile_runs(a.pv, t0, t0 + kScanTileBases, r_lo, r_hi, skip);
+    const int64_t block0 = tile_block0(a, tile);
+    ThreadWords t;
+    expand_thread_words(raw, lane, t);
+#pragma unroll
+    for (int w = 0; w < kWpt; w++) hf[w] = hr[w] = 0;
+    if (skip) return;
+    strand_hit_words(t, a.pc, 0, hf);
+    strand_hit_words(t, a.pc, 1, hr);
+    const uint32_t base = (uint32_t)(block0 * 64);
+    // only the first / last tile of a range can be cut by it
+    const int64_t lim = min((long long)a.r.hi, (long long)a.r.limit - P + 1);
+    if ((int64_t)t0 < (int64_t)a.r.lo || (int64_t)t0 + kScanTileBases > lim) {
+#pragma unroll
+        for (int w = 0; w < kWpt; w++) {
+            const uint32_t rm = range_word((int64_t)base + 32 * w, a.r, P);
+            hf[w] &= rm; hr[w] &= rm;
+        }
+    }
+    if (r_hi > r_lo) veto_words(a.pv, r_lo, r_hi, a.mode, P, base, hf, hr);
+}
+
+__device__ __forceinline__ unsigned long long popc_words(const uint32_t hf[kWpt], const uint32_t hr[kWpt]) {
+    uint32_t cf = 0, cr = 0;
+#pragma unroll
+    for (int w = 0; w < kWpt; w++) { cf += __popc(hf[w]); cr += __popc(hr[w]); }
+    return (unsigned long long)cf | ((unsigned long long)cr << 32);
+}
+
+// sum of a packed counter over the CTA (every thread gets it); s_warp: kThreads/32 words
+__device__ __forceinline__ unsigned long long cta_sum(unsigned long long v, unsigned long long *s_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) t += s_warp[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 3) pam_count_kernel(const PamScanArgs a) {
+    __shared__ unsigned long long s_warp[kThreads / 32];
+    const int lane = threadIdx.x & 31;
+    ThreadRaw raw;
+    if (blockIdx.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, blockIdx.x), lane, raw);
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        // request the next tile's planes before touching this tile's: one tile of loads is always in flight
+        ThreadRaw nxt = raw;
+        if (tile + gridDim.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, tile + gridDim.x), lane, nxt);
+        uint32_t hf[kWpt], hr[kWpt];
+        tile_hit_words(a, tile, raw, hf, hr);
+        const unsigned long long t = cta_sum(popc_words(hf, hr), s_warp);
+        if (threadIdx.x == 0) a.tiles[tile] = t;
+        raw = nxt;
+    }
+}
+
+// set bits of a word -> positions base+bit appended to dst[off...]
+__device__ __forceinline__ uint32_t emit_word(uint32_t m, uint32_t base, uint32_t *dst, uint32_t off) {
+    while (m) { dst[off++] = base + (__ffs(m) - 1); m &= m - 1; }
+    return off;
+}
+
+// staged hits [a0, a0+n) of s -> g[a0 .. a0+n); s and g agree modulo 16 bytes, so whole uint4s
+// move in the middle and at most 3 scalars at either end
+__device__ __forceinline__ void copy_out(const uint32_t *s, uint32_t a0, uint32_t n, uint32_t *g, int vec_ok) {
+    const uint32_t end = a0 + n;
+    const uint32_t q0 = (a0 + 3) >> 2, q1 = end >> 2;
+    if (vec_ok && q1 > q0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+        uint4 *g4 = reinterpret_cast<uint4 *>(g);
+        for (uint32_t q = q0 + threadIdx.x; q < q1; q += kThreads) g4[q] = s4[q];
+        const uint32_t h = a0 + threadIdx.x, t = 4 * q1 + threadIdx.x;
+        if (h < 4 * q0) g[h] = s[h];
+        if (t < end) g[t] = s[t];
+    } else {
+        for (uint32_t i = a0 + threadIdx.x; i < end; i += kThreads) g[i] = s[i];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs a) {
+    __shared__ unsigned long long s_warp[kThreads / 32], s_part[kThreads / 32];
+    __shared__ __align__(16) uint32_t s_stage[2][kStage + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // running output offsets of the current tile = counts of all tiles before it
+    unsigned long long ef = 0, er = 0;
+    uint32_t summed = 0;  // tiles [0, summed) are in (ef, er)
+    ThreadRaw raw;
+    if (blockIdx.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, blockIdx.x), lane, raw);
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        ThreadRaw nxt = raw;  // next tile's planes fly while this tile is scanned, staged and stored
+        if (tile + gridDim.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, tile + gridDim.x), lane, nxt);
+        // advance (ef, er) over the tiles [summed, tile): at most gridDim.x counts (<= 2^16 each, so
+        // the packed 32-bit halves cannot overflow), L2 resident; reduced alongside the CTA scan
+        unsigned long long part = 0;
+        for (uint32_t u = summed + threadIdx.x; u < tile; u += kThreads) part += __ldg(&a.tiles[u]);
+        summed = tile;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        uint32_t hf[kWpt], hr[kWpt];
+        tile_hit_words(a, tile, raw, hf, hr);
+        raw = nxt;
+        const unsigned long long mine = popc_words(hf, hr);
+        // CTA exclusive scan of the packed (fw, rv) counts
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) { s_warp[warp] = inc; s_part[warp] = part; }
         __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= a.n_tiles) break;
-        const int64_t tile_block = a.first_block + (int64_t)tile * kThreads;
-        const uint32_t t0 = (uint32_t)(tile_block * 64), t1 = t0 + kTileBases;
-        if (threadIdx.x == 0) {
-            int r_lo = first_run_ending_after(a.pv, t0 >= 32 ? t0 - 32 : 0);
-            int r_hi = r_lo;
-            int skip = 0;
-            while (r_hi < a.pv.n_runs && a.pv.run_start[r_hi] < t1 + 32) {
-                if (a.pv.run_start[r_hi] <= t0 && a.pv.run_end[r_hi] >= t1) skip = 1;
-                r_hi++;
-            }
-            s_run[0] = r_lo; s_run[1] = r_hi; s_run[2] = skip;
+        unsigned long long warp_prefix = 0, total = 0, adv = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) {
+            const unsigned long long x = s_warp[w];
+            if (w < warp) warp_prefix += x;
+            total += x;
+            adv += s_part[w];
         }
-        __syncthreads();
-        const int r_lo = s_run[0], r_hi = s_run[1];
-        uint64_t hf = 0, hr = 0;
-        const int64_t block = tile_block + threadIdx.x;
-        if (!s_run[2]) {
-            const ulonglong2 cur = load_block(a.pv, block);
-            ulonglong2 nxt = shfl_down_u2(cur, 1);
-            if (lane == 31) nxt = load_block(a.pv, block + 1);
-            const uint64_t rm = range_mask(block, a.r, P);
-            hf = pam_hit_mask(cur, nxt, a.pam.fw, P) & rm;
-            hr = pam_hit_mask(cur, nxt, a.pam.rv, P) & rm;
-            if (r_hi > r_lo && (hf | hr)) veto_hits(a.pv, r_lo, r_hi, a.mode, P, (uint32_t)(block * 64), hf, hr);
-        }
-        const uint32_t cf = __popcll(hf), cr = __popcll(hr);
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(cf | (cr << 16), s_warp, &total);
-        const uint32_t agg_f = total & 0xffff, agg_r = total >> 16;
-        if (warp == 0) {
-            unsigned long long e = lookback(a.desc, tile, 0, agg_f);
-            if (lane == 0) s_excl[0] = e;
-        } else if (warp == 1) {
-            unsigned long long e = lookback(a.desc, tile, 1, agg_r);
-            if (lane == 0) s_excl[1] = e;
-        }
-        // stage (or, for unusually dense tiles, write straight from registers)
-        const uint32_t base = (uint32_t)(block * 64) - a.r.out_base;
+        ef += adv & 0xffffffffull;
+        er += adv >> 32;
+        const unsigned long long excl = warp_prefix + inc - mine;
+        const uint32_t agg_f = (uint32_t)total, agg_r = (uint32_t)(total >> 32);
+        const int64_t block0 = (int64_t)(a.first_tile + tile) * kScanTileBlocks + threadIdx.x * kBpt;
+        const uint32_t base = (uint32_t)(block0 * 64) - a.r.out_base;
+        // staged at index (ef & 3) + local rank, so shared and global addresses share their 16-byte
+        // phase and the copy-out below can move uint4s
+        const uint32_t pf = (uint32_t)ef & 3u, pr = (uint32_t)er & 3u;
+        uint32_t of = (uint32_t)excl + pf, orv = (uint32_t)(excl >> 32) + pr;
+        // capacity: a tile is written completely or not at all (the counts stay exact either way)
+        const bool fits_f = ef + agg_f <= a.cap_fw, fits_r = er + agg_r <= a.cap_rv;
         const bool stage_f = agg_f <= kStage, stage_r = agg_r <= kStage;
-        uint32_t of = excl & 0xffff, orv = excl >> 16;
         if (stage_f) {
-            uint64_t m = hf;
-            while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; s_stage[0][of++] = base + i; }
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, s_stage[0], of);
+        } else if (fits_f) {  // unusually dense tile: straight from registers to HBM
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, a.out_fw + ef - pf, of);
         }
         if (stage_r) {
-            uint64_t m = hr;
-            while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; s_stage[1][orv++] = base + i; }
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, s_stage[1], orv);
+        } else if (fits_r) {
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, a.out_rv + er - pr, orv);
         }
         __syncthreads();
-        const unsigned long long ef = s_excl[0], er = s_excl[1];
-        if (stage_f) {
-            for (uint32_t j = threadIdx.x; j < agg_f; j += kThreads)
-                if (ef + j < a.cap_fw) a.out_fw[ef + j] = s_stage[0][j];
-        } else {
-            uint64_t m = hf;
-            unsigned long long o = ef + of;
-            while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; if (o < a.cap_fw) a.out_fw[o] = base + i; o++; }
-        }
-        if (stage_r) {
-            for (uint32_t j = threadIdx.x; j < agg_r; j += kThreads)
-                if (er + j < a.cap_rv) a.out_rv[er + j] = s_stage[1][j];
-        } else {
-            uint64_t m = hr;
-            unsigned long long o = er + orv;
-            while (m) { int i = __ffsll((long long)m) - 1; m &= m - 1; if (o < a.cap_rv) a.out_rv[o] = base + i; o++; }
-        }
+        if (stage_f && fits_f) copy_out(s_stage[0], pf, agg_f, a.out_fw + ef - pf, a.vec_ok);
+        if (stage_r && fits_r) copy_out(s_stage[1], pr, agg_r, a.out_rv + er - pr, a.vec_ok);
         if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
             a.counts[0] = ef + agg_f;
             a.counts[1] = er + agg_r;
         }
-        __syncthreads();  // s_stage / s_tile are rewritten by the next iteration
+        __syncthreads();  // s_stage / s_warp are rewritten by the next iteration
+    }
+}
+
+static void make_coef(const PamSpec &pam, PamCoef *pc) {
+    pc->len = pam.len;
+    for (int strand = 0; strand < 2; strand++) {
+        int prev = -1;
+        for (int i = 0; i < pam.len; i++) {
+            const int s = strand ? pam.rv[i] : pam.fw[i];
+            pc->same[strand][i] = (s != 15 && s == prev);
+            if (s != 15) prev = s;
+            // truth table over (hi, lo): A=(0,0) bit0, C=(0,1) bit1, G=(1,0) bit2, T=(1,1) bit3
+            const int f00 = s & 1, f01 = (s >> 1) & 1, f10 = (s >> 2) & 1, f11 = (s >> 3) & 1;
+            const int c0 = f00, c1 = f00 ^ f01, c2 = f00 ^ f10, c3 = f00 ^ f01 ^ f10 ^ f11;
+            pc->c[strand][i][0] = c0 ? 0xffffffffu : 0u;
+            pc->c[strand][i][1] = c1 ? 0xffffffffu : 0u;
+            pc->c[strand][i][2] = c2 ? 0xffffffffu : 0u;
+            pc->c[strand][i][3] = c3 ? 0xffffffffu : 0u;
+            pc->skip[strand][i] = (s == 15);
+        }
     }
 }
 
@@ -170,30 +396,33 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         return GUIDO_OK;
     }
     PamScanArgs a;
-    a.pv = pv; a.pam = pam; a.r = r; a.mode = mode;
-    a.first_block = r.lo / 64;
-    int64_t last_block = ((int64_t)r.hi - 1) / 64;
-    a.n_tiles = (uint32_t)((last_block - a.first_block + 1 + kThreads - 1) / kThreads);
+    a.pv = pv; a.r = r; a.mode = mode;
+    make_coef(pam, &a.pc);
+    a.first_tile = (uint32_t)((r.lo / 64) / kScanTileBlocks);
+    const uint32_t last_tile = (uint32_t)((((int64_t)r.hi - 1) / 64) / kScanTileBlocks);
+    a.n_tiles = last_tile - a.first_tile + 1;
     a.out_fw = d_fw; a.out_rv = d_rv; a.cap_fw = cap_fw; a.cap_rv = cap_rv;
     a.counts = d_counts;
-    int64_t need = 2 * (int64_t)a.n_tiles;
+    a.vec_ok = ((reinterpret_cast<uintptr_t>(d_fw) | reinterpret_cast<uintptr_t>(d_rv)) & 15) == 0;
+    int64_t need = (int64_t)a.n_tiles;
     if (need > ds->desc_cap) {
         if (ds->d_desc) cudaFree(ds->d_desc);
         ds->d_desc = nullptr; ds->desc_cap = 0;
         GUIDO_CUDA(cudaMalloc(&ds->d_desc, (size_t)need * sizeof(unsigned long long)));
         ds->desc_cap = need;
     }
-    a.desc = ds->d_desc;
-    a.ticket = ds->d_tile_counter;
-    GUIDO_CUDA(cudaMemsetAsync(ds->d_desc, 0, (size_t)need * sizeof(unsigned long long), stream));
-    GUIDO_CUDA(cudaMemsetAsync(ds->d_tile_counter, 0, sizeof(unsigned int), stream));
-    int per_sm = 0;
-    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_scan_kernel, kThreads, 0));
-    int grid = ds->sm_count * std::max(per_sm, 1);
-    if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
-    pam_scan_kernel<<<grid, kThreads, 0, stream>>>(a);
+    a.tiles = ds->d_desc;
+    if (ds->scan_grid[0] == 0) {
+        int per_sm = 0;
+        GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_count_kernel, kThreads, 0));
+        ds->scan_grid[0] = ds->sm_count * std::max(per_sm, 1);
+        GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_fill_kernel, kThreads, 0));
+        ds->scan_grid[1] = ds->sm_count * std::max(per_sm, 1);
+    }
+    pam_count_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[0]), kThreads, 0, stream>>>(a);
+    pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, 0, stream>>>(a);
     GUIDO_CUDA(cudaGetLastError());
-    if (n_launches) *n_launches += 1;
+    if (n_launches) *n_launches += 2;
     return GUIDO_OK;
 }
 

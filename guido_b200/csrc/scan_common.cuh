@@ -11,6 +11,7 @@ namespace guido {
 constexpr int kThreads = 256;               // threads per CTA in the scan kernels
 constexpr int kTileBases = kThreads * 64;   // 16384 bases per tile
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTileRunShift = 16;          // tile_first_run has one entry per 65536 bases
 constexpr int kScanRawWindow = 3;         // internal: both orientations own window [p, p+P+20)
 
 // positions whose base belongs to set s (bit0 A, bit1 C, bit2 G, bit3 T); s is warp-uniform
@@ -68,6 +69,30 @@ __device__ __forceinline__ int first_run_ending_after(const PlanesView &pv, uint
         if (pv.run_end[mid] > pos) hi = mid; else lo = mid + 1;
     }
     return lo;
+}
+
+// Run range [r_lo, r_hi) touching positions [t0 - 32, t1 + 32), and whether one run covers the
+// whole [t0, t1).  pv.tile_first_run[t0 >> 16] (built at upload) gives the starting point, so the
+// hot path does one table load instead of a binary search; every thread computes it (uniform,
+// cached loads) and no shared-memory broadcast / barrier is needed.
+__device__ __forceinline__ void tile_runs(const PlanesView &pv, uint32_t t0, uint32_t t1, int &r_lo, int &r_hi,
+                                          bool &skip) {
+    const uint32_t entry = __ldg(&pv.tile_first_run[t0 >> kTileRunShift]);
+    if (!(entry >> 31)) {  // no run anywhere near this 65536-base tile: the common case
+        r_lo = r_hi = 0;
+        skip = false;
+        return;
+    }
+    int r = (int)(entry & 0x7fffffffu);
+    const uint32_t from = t0 >= 32 ? t0 - 32 : 0;
+    while (r < pv.n_runs && __ldg(&pv.run_end[r]) <= from) r++;
+    r_lo = r;
+    skip = false;
+    while (r < pv.n_runs && __ldg(&pv.run_start[r]) < t1 + 32) {
+        if (__ldg(&pv.run_start[r]) <= t0 && __ldg(&pv.run_end[r]) >= t1) skip = true;
+        r++;
+    }
+    r_hi = r;
 }
 
 __device__ __forceinline__ bool span_touches_run(const PlanesView &pv, int r_lo, int r_hi, uint32_t a,

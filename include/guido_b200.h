@@ -88,6 +88,12 @@ int guido_version(void);
 /* number of usable sm_100 devices (0 when there is none) */
 int guido_device_count(void);
 
+/* page-locked host memory for the caller's input/output buffers: device<->host copies into
+ * such buffers run at full PCIe rate (any host pointer is accepted everywhere, pageable is just
+ * slower).  Pinning is process-wide, so no device needs to be selected. */
+int guido_host_alloc(int64_t bytes, void **out);
+int guido_host_free(void *p);
+
 /* ---- genome image: replaces `bowtie-build` in Genome.build (guido/genome.py:156-171) --------- */
 /* FASTA -> two bit planes (1 bit/base each, interleaved per 64 bases) + sorted list of non-ACGT
  * runs + contig table.  Sequence names are the header up to the first whitespace.            */

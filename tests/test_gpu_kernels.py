@@ -130,12 +130,13 @@ def _protos_from_genome(rng, contigs, n, mutate=3):
     ("NRG", dict(core_mismatches=1)),
     ("TGG", dict(core_mismatches=3, total_mismatches=4)),
 ])
-def test_offtarget_scan_matches_oracle(native, oracle, pam, kw):
+@pytest.mark.parametrize("algo", ["scan", "index"])
+def test_offtarget_scan_matches_oracle(native, oracle, pam, kw, algo):
     contigs = util.synthetic_contigs(21, [60000, 25000, 300], n_runs=4, iupac=5)
     rng = np.random.default_rng(3)
     protos = _protos_from_genome(rng, contigs, 60)
     img = native.Image.from_seqs(contigs).upload()
-    hits, flags = img.offtarget_search(protos, pam=pam, algo=native.OT_SCAN, **kw)
+    hits, flags = img.offtarget_search(protos, pam=pam, algo={"scan": native.OT_SCAN, "index": native.OT_INDEX}[algo], **kw)
     valid, keys = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
     assert util.gpu_hit_set(img, hits) == valid
     assert len(hits) == len(valid)
@@ -173,3 +174,37 @@ def test_offtarget_sharded_union(native):
     merged = np.concatenate(parts)
     merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
     assert np.array_equal(merged, whole)
+
+
+@pytest.mark.parametrize("core_length,core_mismatches", [(6, 2), (8, 0), (11, 1), (12, 2), (10, 2)])
+def test_offtarget_index_equals_scan(native, core_length, core_mismatches):
+    """the seed-index kernel returns byte-identical sorted hit lists to the brute-force kernel"""
+    contigs = util.synthetic_contigs(24, [120000, 40000], n_runs=3)
+    rng = np.random.default_rng(6)
+    protos = _protos_from_genome(rng, contigs, 300, mutate=4) + ["ACGT" * 5, "G" * 20]
+    protos += protos[:5]  # duplicated guides must each get their own hits
+    img = native.Image.from_seqs(contigs).upload()
+    kw = dict(core_length=core_length, core_mismatches=core_mismatches, total_mismatches=4, want_raw_flags=False)
+    a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
+    b, _ = img.offtarget_search(protos, algo=native.OT_INDEX, **kw)
+    assert len(a) > 0 and np.array_equal(a, b)
+
+
+def test_offtarget_index_rejects_unsupported_core(native):
+    img = native.Image.from_seqs(util.synthetic_contigs(25, [5000], n_runs=0)).upload()
+    with pytest.raises(ValueError, match="seed index"):
+        img.offtarget_search(["ACGT" * 5], core_length=20, algo=native.OT_INDEX)
+    hits, _ = img.offtarget_search(["ACGT" * 5], core_length=20, algo=native.OT_AUTO)  # falls back to the scan kernel
+
+
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_offtarget_index_lookup_variants(native, monkeypatch, wide):
+    """both bucket-walking strategies of the seed-index kernel give the brute-force answer"""
+    monkeypatch.setenv("GUIDO_OT_WIDE", wide)
+    contigs = util.synthetic_contigs(26, [150000], n_runs=3)
+    rng = np.random.default_rng(7)
+    protos = _protos_from_genome(rng, contigs, 500, mutate=4)
+    img = native.Image.from_seqs(contigs).upload()
+    a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    b, _ = img.offtarget_search(protos, algo=native.OT_INDEX, want_raw_flags=False)
+    assert len(a) > 0 and np.array_equal(a, b)
