@@ -35,6 +35,7 @@ struct OtIndex {
     const uint32_t *keys;     // distal_hi | distal_lo << dl | core_mm << 2*dl
     const uint32_t *guides;   // guide index of the entry
     int cl, dl;               // core / distal length (cl + dl = 20)
+    int field;                // bits per plane field of a key: dl + core_mm pseudo-positions
     int wide;                 // average bucket is large: walk buckets warp-wide
 };
 
@@ -122,9 +123,52 @@ struct LookupSmem {
 // flattened by a warp prefix sum, and the lanes then walk the flattened key list 4 x 32 keys per
 // step (coalesced 4-byte loads inside a bucket, 4 independent loads per lane in flight), so lanes
 // stay busy and HBM latency stays covered whatever the bucket sizes are.
+// Hits of the index lookups are parked in shared memory and moved to the global list with ONE
+// atomic per flush: a single global cursor serialises at L2 (~1 ns per atomic), which would cost
+// ~10 ms for the 1.1e7 hits of the 100k-guide workload.
+constexpr int kHitBuf = 384;
+struct HitBuf {
+    uint32_t n;
+    unsigned long long base;
+    guido_ot_hit rec[kHitBuf];
+};
+
+__device__ __forceinline__ void push_hit(const OtScanArgs &a, HitBuf &hb, const guido_ot_hit &h) {
+    const uint32_t i = atomicAdd(&hb.n, 1u);
+    if (i < kHitBuf) {
+        hb.rec[i] = h;
+    } else {  // parked list is full until the next flush: straight to the global list
+        unsigned long long slot = atomicAdd(a.count, 1ull);
+        if (slot < a.cap) a.hits[slot] = h;
+    }
+}
+
+// whole CTA, after a barrier that ends the pushing phase
+__device__ __forceinline__ void flush_hits(const OtScanArgs &a, HitBuf &hb, bool force) {
+    const uint32_t n = min(hb.n, (uint32_t)kHitBuf);
+    if (n == 0 || (!force && n < kHitBuf / 2)) return;
+    if (threadIdx.x == 0) hb.base = atomicAdd(a.count, (unsigned long long)n);
+    __syncthreads();
+    const unsigned long long base = hb.base;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads)
+        if (base + i < a.cap) a.hits[base + i] = hb.rec[i];
+    __syncthreads();
+    if (threadIdx.x == 0) hb.n = 0;
+    __syncthreads();
+}
+
+// bucket of a core key: offsets[] holds EVEN starts (64-bit key loads stay aligned) with the
+// "true count is odd" flag in bit 0
+__device__ __forceinline__ void bucket_range(const OtIndex &ix, uint32_t key, uint32_t &start, uint32_t &len) {
+    const uint32_t v = __ldg(&ix.offsets[key]), w = __ldg(&ix.offsets[key + 1]);
+    start = v & ~1u;
+    len = (w & ~1u) - start - (v & 1u);
+}
+
 template <int RING>
 __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
-                                             const uint32_t *sQ, uint32_t head, uint32_t n, LookupSmem &ls) {
+                                             const uint32_t *sQ, uint32_t head, uint32_t n, LookupSmem &ls,
+                                             HitBuf &hb) {
     constexpr int U = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cl = a.ix.cl, dl = a.ix.dl;
@@ -132,6 +176,8 @@ __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t
     const int tot_max = a.op.total_max;
     const uint32_t *__restrict__ keys = a.ix.keys;
     uint32_t *w_start = ls.start[warp], *w_pref = ls.pref[warp], *w_dist = ls.dist[warp];
+    const int F = a.ix.field;
+    const uint32_t fmask = (1u << F) - 1;
     for (uint32_t b = warp * 32; b < n; b += kThreads) {
         const uint32_t j = b + lane;
         const uint32_t idx = (head + j) & (RING - 1);
@@ -139,9 +185,8 @@ __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t
         if (j < n) {
             const uint32_t A = sA[idx], B = sB[idx];
             const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
-            start = __ldg(&a.ix.offsets[key]);
-            len = __ldg(&a.ix.offsets[key + 1]) - start;
-            dist = (A & dmask) | ((B & dmask) << dl);
+            bucket_range(a.ix, key, start, len);
+            dist = (A & dmask) | ((B & dmask) << F);
         }
         uint32_t inc = len;
 #pragma unroll
@@ -177,15 +222,12 @@ __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t
             for (int u = 0; u < U; u++) {
                 if (site[u] == 0xffffffffu) continue;
                 const uint32_t x = kv[u] ^ w_dist[site[u]];
-                const uint32_t m = (x | (x >> dl)) & dmask;
-                if ((int)(__popc(m) + (x >> (2 * dl))) <= tot_max) {
-                    unsigned long long slot = atomicAdd(a.count, 1ull);
-                    if (slot < a.cap) {
-                        const uint32_t si = (head + b + site[u]) & (RING - 1);
-                        guido_ot_hit h;
-                        h.guide = __ldg(&a.ix.guides[pos[u]]); h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
-                        a.hits[slot] = h;
-                    }
+                const uint32_t m = (x | (x >> F)) & fmask;
+                if ((int)__popc(m) <= tot_max) {
+                    const uint32_t si = (head + b + site[u]) & (RING - 1);
+                    guido_ot_hit h;
+                    h.guide = __ldg(&a.ix.guides[pos[u]]); h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
+                    push_hit(a, hb, h);
                 }
             }
         }
@@ -197,11 +239,11 @@ __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t
 // the owning site -- and keeps the loads of 8 buckets in flight together.
 template <int RING>
 __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
-                                                  const uint32_t *sQ, uint32_t head, uint32_t n) {
-    constexpr int U = 8;
+                                                  const uint32_t *sQ, uint32_t head, uint32_t n, HitBuf &hb) {
+    constexpr int U = 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cl = a.ix.cl, dl = a.ix.dl;
-    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    const int cl = a.ix.cl, dl = a.ix.dl, F = a.ix.field;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1, fmask = (1u << F) - 1;
     const int tot_max = a.op.total_max;
     const uint32_t *__restrict__ keys = a.ix.keys;
     for (uint32_t b = warp * 32; b < n; b += kThreads) {
@@ -211,9 +253,8 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
             const uint32_t idx = (head + j) & (RING - 1);
             const uint32_t A = sA[idx], B = sB[idx];
             const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
-            start = __ldg(&a.ix.offsets[key]);
-            len = __ldg(&a.ix.offsets[key + 1]) - start;
-            dist = (A & dmask) | ((B & dmask) << dl);
+            bucket_range(a.ix, key, start, len);
+            dist = (A & dmask) | ((B & dmask) << F);
         }
         for (int s0 = 0; s0 < 32; s0 += U) {
             uint32_t st[U], ln[U], ds[U], maxlen = 0;
@@ -224,22 +265,23 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
                 ds[u] = __shfl_sync(kFull, dist, s0 + u);
                 maxlen = max(maxlen, ln[u]);
             }
-            for (uint32_t off = lane; off < maxlen; off += 32) {
-                uint32_t kv[U];
+            // a lane takes keys off, off+1 of each bucket: one aligned 8-byte load, 64 keys per warp step
+            for (uint32_t off = 2 * lane; off < maxlen; off += 64) {
+                uint2 kv[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) kv[u] = (off < ln[u]) ? __ldg(&keys[st[u] + off]) : 0u;
+                for (int u = 0; u < U; u++)
+                    kv[u] = (off < ln[u]) ? __ldg(reinterpret_cast<const uint2 *>(keys + st[u] + off)) : make_uint2(0u, 0u);
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint32_t x = kv[u] ^ ds[u];
-                    const uint32_t m = (x | (x >> dl)) & dmask;
-                    if (off < ln[u] && (int)(__popc(m) + (x >> (2 * dl))) <= tot_max) {
-                        unsigned long long slot = atomicAdd(a.count, 1ull);
-                        if (slot < a.cap) {
-                            const uint32_t si = (head + b + s0 + u) & (RING - 1);
-                            guido_ot_hit h;
-                            h.guide = __ldg(&a.ix.guides[st[u] + off]); h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
-                            a.hits[slot] = h;
-                        }
+                    const uint32_t x0 = kv[u].x ^ ds[u], x1 = kv[u].y ^ ds[u];
+                    const bool h0 = off < ln[u] && (int)__popc((x0 | (x0 >> F)) & fmask) <= tot_max;
+                    const bool h1 = off + 1 < ln[u] && (int)__popc((x1 | (x1 >> F)) & fmask) <= tot_max;
+                    if (h0 | h1) {
+                        const uint32_t si = (head + b + s0 + u) & (RING - 1);
+                        guido_ot_hit h;
+                        h.gpos = sQ[si]; h.hi = sA[si]; h.lo = sB[si];
+                        if (h0) { h.guide = __ldg(&a.ix.guides[st[u] + off]); push_hit(a, hb, h); }
+                        if (h1) { h.guide = __ldg(&a.ix.guides[st[u] + off + 1]); push_hit(a, hb, h); }
                     }
                 }
             }
@@ -260,9 +302,12 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
     constexpr int RING = OtCfg<kIndex>::kRing, ROUND = OtCfg<kIndex>::kRound;
     extern __shared__ uint32_t s_dyn[];
     uint32_t *sA = s_dyn, *sB = s_dyn + RING, *sQ = s_dyn + 2 * RING;
-    __shared__ LookupSmem s_lookup;  // unused (and tiny) in the brute-force instantiation
+    __shared__ LookupSmem s_lookup;  // the index consumer's scratch (dead in the brute-force instantiation)
+    __shared__ HitBuf s_hits;
     __shared__ uint32_t s_warp[kThreads / 32];
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_hits.n = 0;
+    __syncthreads();
     const int P = a.op.pam.len;
     const int W = kProto + P;
     const uint32_t wmask = (1u << W) - 1;
@@ -332,10 +377,13 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
             __syncthreads();
             while (qlen >= ROUND) {
                 if constexpr (kIndex) {
-                    if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, ROUND);
-                    else lookup_round<RING>(a, sA, sB, sQ, head, ROUND, s_lookup);
+                    if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, ROUND, s_hits);
+                    else lookup_round<RING>(a, sA, sB, sQ, head, ROUND, s_lookup, s_hits);
+                    __syncthreads();
+                    flush_hits(a, s_hits, false);
+                } else {
+                    compare_round<RING>(a, sA, sB, sQ, head, ROUND);
                 }
-                else compare_round<RING>(a, sA, sB, sQ, head, ROUND);
                 head = (head + ROUND) & (RING - 1);
                 qlen -= ROUND;
             }
@@ -344,12 +392,15 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
         }
     }
     __syncthreads();
-    if (qlen) {
-        if constexpr (kIndex) {
-            if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, qlen);
-            else lookup_round<RING>(a, sA, sB, sQ, head, qlen, s_lookup);
+    if constexpr (kIndex) {
+        if (qlen) {
+            if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, qlen, s_hits);
+            else lookup_round<RING>(a, sA, sB, sQ, head, qlen, s_lookup, s_hits);
         }
-        else compare_round<RING>(a, sA, sB, sQ, head, qlen);
+        __syncthreads();
+        flush_hits(a, s_hits, true);
+    } else {
+        if (qlen) compare_round<RING>(a, sA, sB, sQ, head, qlen);
     }
     if (threadIdx.x == 0 && a.site_count) atomicAdd(a.site_count, n_sites);
 }
@@ -377,7 +428,7 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0};
+    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
     int rc = launch_ot_kernel<false>(ds, a, stream);
@@ -400,7 +451,7 @@ struct IdxArgs {
     uint32_t n_guides;
     const uint32_t *variants;  // xh | xl << 16
     uint32_t n_variants;
-    int cl, dl;
+    int cl, dl, field;
     uint32_t *counts;          // n_buckets + 1 (pass 1), becomes offsets after the scan
     uint32_t *fill;            // n_buckets
     uint32_t *keys, *ids;      // n_entries each
@@ -419,20 +470,33 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
         if constexpr (!kFill) {
             atomicAdd(&a.counts[key], 1u);
         } else {
-            const uint32_t pos = a.counts[key] + atomicAdd(&a.fill[key], 1u);
-            a.keys[pos] = (G.x & dmask) | ((G.y & dmask) << a.dl) | ((uint32_t)__popc(xh | xl) << (2 * a.dl));
+            // offsets are even with the odd-count flag in bit 0; the fill cursor keeps that flag in bit 31
+            const uint32_t pos = (a.counts[key] & ~1u) + (atomicAdd(&a.fill[key], 1u) & 0x7fffffffu);
+            // key = distal planes in two fields of `field` bits; the core mismatches of this variant
+            // are appended to the hi field as that many 1-bits, which the window's zeros turn into
+            // mismatches -- so popc of the folded XOR is the TOTAL mismatch count, no extra add
+            const uint32_t cmm = (uint32_t)__popc(xh | xl);
+            a.keys[pos] = (G.x & dmask) | (((1u << cmm) - 1u) << a.dl) | ((G.y & dmask) << a.field);
             a.ids[pos] = g;
         }
     }
 }
 
 // in-place exclusive scan of n u32 values: 4096 per block, then the block sums, then the fix-up
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint32_t n, uint32_t *block_sums) {
+// With pad_even every value is rounded up to even before it is scanned (bucket starts stay 8-byte
+// aligned for the 64-bit key loads) and "the true count was odd" is kept in bit 0 of the result.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint32_t n, uint32_t *block_sums,
+                                                            int pad_even) {
     __shared__ uint32_t s_w[32];
     const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
-    uint32_t v[4], sum = 0;
+    uint32_t v[4], odd[4], sum = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { v[i] = (base + i < n) ? data[base + i] : 0; sum += v[i]; }
+    for (int i = 0; i < 4; i++) {
+        const uint32_t c = (base + i < n) ? data[base + i] : 0;
+        odd[i] = pad_even ? (c & 1u) : 0u;
+        v[i] = c + odd[i];
+        sum += v[i];
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = sum;
 #pragma unroll
@@ -449,7 +513,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint3
     __syncthreads();
     uint32_t run = s_w[warp] + inc - sum;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { if (base + i < n) data[base + i] = run; run += v[i]; }
+    for (int i = 0; i < 4; i++) { if (base + i < n) data[base + i] = run | odd[i]; run += v[i]; }
 }
 
 __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *block_sums, uint32_t n_blocks) {
@@ -503,6 +567,7 @@ static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
 
 bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
     if (op.raw_mode || op.core_len < 6 || op.core_len > 12 || op.core_max > 3) return false;
+    if (kProto - op.core_len + op.core_max > 16) return false;  // two key fields must fit 32 bits
     std::vector<uint32_t> v;
     enumerate_variants(op.core_len, op.core_max, &v);
     return (double)v.size() * (double)n_guides < 1.5e9;  // entries are addressed with 32 bits (12 GB)
@@ -527,19 +592,22 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
-    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_entries * 8))) return rc;
+    // every bucket may be padded by one slot to an even length
+    const uint64_t n_slots = (n_entries + n_buckets + 3) & ~(uint64_t)3;
+    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_slots * 8))) return rc;
     uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
              *d_var = sums + n_scan_blocks;
-    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_entries;
+    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots;
+    const int field = dl + op.core_max;  // <= 16, checked by ot_index_applicable
     GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
     // variants are tiny; a pageable async copy is staged by the driver before it returns
     GUIDO_CUDA(cudaMemcpyAsync(d_var, variants.data(), variants.size() * 4, cudaMemcpyHostToDevice, stream));
     IdxArgs ia;
     ia.guides = d_guides; ia.n_guides = (uint32_t)n_guides; ia.variants = d_var; ia.n_variants = (uint32_t)variants.size();
-    ia.cl = cl; ia.dl = dl; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
+    ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     const int bgrid = (int)std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)ds->sm_count * 32);
     idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
-    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 1);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
     idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
@@ -550,7 +618,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     const int wide = force ? atoi(force) : (n_entries / n_buckets >= 12);
-    a.ix = OtIndex{counts, keys, ids, cl, dl, wide};
+    a.ix = OtIndex{counts, keys, ids, cl, dl, field, wide};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
     rc = launch_ot_kernel<true>(ds, a, stream);
