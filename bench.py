@@ -5,15 +5,19 @@
                     [--workload offtarget|pam] [--genome human|agam|<Mb>] [--guides G] [--algo auto|scan|index]
 
 One "step" = one pass of the hot path over one batch:
-  offtarget  every PAM-valid window of the synthetic genome x all guides, <=4 mismatches
-             (BASELINE.json configs[3] at --genome human --guides 100000, configs[2] at agam/10000)
-  pam        whole-genome NGG scan, both strands (configs[1])
-Multi-GPU: one process per GPU (torchrun), genome sharded in contiguous chunks with a one-block halo,
-guides replicated, per-rank hit lists merged with an NCCL all-gather inside the step.
+  offtarget  (default) 100 000 SpCas9 guides, <=4 mismatches (core 10 / 2), against a synthetic
+             3.1 Gb genome -- BASELINE.json configs[3]; `--genome agam --guides 10000` is configs[2].
+             A step builds the guide-side seed index and scans every PAM-valid window of the genome.
+  pam        whole-genome NGG scan, both strands, synthetic 273 Mb genome -- configs[1].
+             The default run also measures this one and reports it under "pam_scan".
+Multi-GPU: one process per GPU (torchrun); the genome is sharded in contiguous, tile-aligned
+chunks with a 256-base halo, the guides are replicated, and the per-rank hit lists are merged with
+an NCCL all-gather inside the step.  Total work is fixed as N grows ("strong").
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with inputs resident in HBM;
-`e2e` goes through the host-buffer C-ABI call (guides H2D, hits D2H, host sort inside the region).
-`--impl reference` times the CPU oracle port (bowtie is not in this image) on the host cores.
+`e2e` goes through the host-buffer C-ABI call (guides H2D, hits sorted on the device, D2H into
+pinned host memory inside the region).  `--impl reference` times the CPU oracle port (bowtie is
+not in this image) on the host cores, on a bounded sample scaled to the whole workload.
 """
 import argparse
 import json
@@ -28,6 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "off-target guides/sec (<=4 mm, 3.1 Gb genome); PAM-scan genome GB/s vs HBM peak"
 AGAM_LENS = [49_400_000, 61_500_000, 42_000_000, 53_200_000, 24_400_000, 42_400_000, 240_000, 15_000]
 _HUMAN_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09,
              133.28, 114.36, 107.04, 101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82, 156.04, 57.23]
@@ -38,12 +43,12 @@ OT_KW = dict(core_length=10, core_mismatches=2, total_mismatches=4)
 
 def genome_lens(spec):
     if spec == "human":
-        return HUMAN_LENS, 1004, 0.01, "synthetic GRCh38-sized 3.1 Gb, 24 contigs, 1% N"
+        return HUMAN_LENS, 1004, 0.01, "synthetic GRCh38-sized 3.1 Gb genome, 24 contigs, 1% N"
     if spec == "agam":
-        return AGAM_LENS, 1002, 0.005, "synthetic AgamP4-sized 273 Mb, 8 contigs, 0.5% N"
+        return AGAM_LENS, 1002, 0.005, "synthetic AgamP4-sized 273 Mb genome, 8 contigs, 0.5% N"
     mb = float(spec)
     n = max(1, min(8, int(mb // 5) or 1))
-    return [int(mb * 1e6 / n)] * n, 1010, 0.005, f"synthetic {mb:g} Mb, {n} contigs, 0.5% N"
+    return [int(mb * 1e6 / n)] * n, 1010, 0.005, f"synthetic {mb:g} Mb genome, {n} contigs, 0.5% N"
 
 
 def sample_guides(img, n, seed):
@@ -52,8 +57,7 @@ def sample_guides(img, n, seed):
     contigs = img.contigs
     lens = np.array([c[1] for c in contigs], dtype=np.int64)
     offs = np.array([c[2] for c in contigs], dtype=np.int64)
-    out = []
-    have = 0
+    out, have = [], 0
     while have < n:
         m = max(4096, (n - have) * 20)
         ci = rng.choice(len(contigs), size=m, p=lens / lens.sum())
@@ -66,7 +70,7 @@ def sample_guides(img, n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the bench runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -75,10 +79,9 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
@@ -86,12 +89,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def summary(self, t0, t1):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        inside = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05]
+        rows = inside or [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -102,51 +104,50 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "in_timed_region": bool(inside), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
 
 
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured copy bandwidth (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------ CPU arm
 
 def cpu_offtarget_sample(img, guides_u8, n_windows_full, budget_s=12.0):
-    """Time the oracle port (all host cores) on a bounded sample: a slice of contig 1 x a subset of
-    the guides; scale to whole-genome guides/sec by the pair rate."""
+    """The oracle port (all host cores) on a bounded sample: a slice of contig 1 x a subset of the
+    guides; the pair rate is scaled to whole-genome guides/sec."""
     from oracle import oracle as O
     O.lib()
     cores = O.threads()
     name, clen, _ = img.contigs[0]
     reads = [O.rev_comp(bytes(g).decode() + PAM) for g in guides_u8[:256]]
     seed_mms, seed_len, e = O.bowtie_args(PAM, **OT_KW)
-    slice_len = 200_000
-    n_reads = 64
-    pairs_per_s = None
-    spent = 0.0
+    slice_len, n_reads, spent = 200_000, min(64, len(reads)), 0.0
     while True:
         seq = img.fetch(0, 0, min(slice_len, clen))
         t0 = time.perf_counter()
         O.bowtie_n_count([(name, seq)], reads[:n_reads], seed_mms, seed_len, e)
         dt = time.perf_counter() - t0
         spent += dt
-        pairs = 2.0 * len(seq) * n_reads  # every window, both strands (bowtie's search space)
-        pairs_per_s = pairs / dt
+        pairs_per_s = 2.0 * len(seq) * n_reads / dt  # every window, both strands (bowtie's search space)
         if dt > budget_s / 3 or spent > budget_s or slice_len >= clen:
             break
         scale = min(8.0, max(2.0, (budget_s / 2) / max(dt, 1e-3)))
-        if n_reads < 256:
-            n_reads = min(256, int(n_reads * scale))
+        if n_reads < len(reads):
+            n_reads = min(len(reads), int(n_reads * scale))
         else:
             slice_len = int(slice_len * scale)
-    # whole job = all windows of the genome (both strands) x all guides; guides/s = pair rate / windows
-    value = pairs_per_s / n_windows_full
-    return {"value": value, "unit": "guides/s", "cores": cores, "kind": "port",
-            "sample": f"oracle C port of bowtie -n rule, {len(seq)} bp of contig 1 x {n_reads} guides, "
-                      f"{dt:.2f} s, {pairs_per_s:.3e} window-guide pairs/s scaled to the whole genome",
+    return {"value": pairs_per_s / n_windows_full, "unit": "guides/s", "cores": cores, "kind": "port",
+            "sample": f"oracle C port of the bowtie -n rule (brute force, all {cores} host threads): "
+                      f"{len(seq)} bp of contig 1 x {n_reads} guides in {dt:.2f} s = {pairs_per_s:.3e} "
+                      "window-guide pairs/s, scaled to every window of the whole genome",
             "pairs_per_s": pairs_per_s}
 
 
@@ -159,16 +160,173 @@ def cpu_pam_sample(img, budget_s=10.0):
     t0 = time.perf_counter()
     reps = 0
     while time.perf_counter() - t0 < budget_s / 2:
-        O.pam_scan(seq, PAM)
+        fw, rv = O.pam_scan(seq, PAM)
         reps += 1
     dt = time.perf_counter() - t0
     bases_per_s = n * reps / dt
-    return {"value": bases_per_s * 0.25 / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-            "sample": f"oracle C scan of {n} bp x {reps} reps, {dt:.2f} s, {bases_per_s / 1e6:.1f} Mb/s "
-                      "(0.25 B/base equivalent)", "bases_per_s": bases_per_s}
+    bytes_per_base = 0.25 + 4.0 * (len(fw) + len(rv)) / n
+    return {"value": bases_per_s * bytes_per_base / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"oracle C scan (1 thread, as the reference runs): {n} bp x {reps} reps in {dt:.2f} s = "
+                      f"{bases_per_s / 1e6:.1f} Mb/s, expressed in the same algorithmic bytes/base",
+            "bases_per_s": bases_per_s}
 
 
-# ------------------------------------------------------------------------------ main
+# ------------------------------------------------------------------------------ GPU arm
+
+class Runner:
+    def __init__(self, args, N, torch, dist, rank, world, local_rank):
+        self.a, self.N, self.torch, self.dist = args, N, torch, dist
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", local_rank)
+        self.stream = torch.cuda.current_stream()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB of L2
+        self.sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allsum(self, x, op=None):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed(self, step, steps, warmup):
+        """W warm-up steps, then K steps timed by CUDA events on the launching stream (L2 flushed
+        between steps, outside the events), bracketed by barrier + synchronize; max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.time()
+        launches = 0
+        for s, e in ev:
+            self.flush.zero_()
+            s.record(self.stream)
+            launches += step()
+            e.record(self.stream)
+        self.barrier()
+        t1 = time.time()
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        ms_step = self.allsum(ms, self.dist.ReduceOp.MAX if self.world > 1 else None) / steps
+        clocks = self.sampler.summary(t0, t1) if self.sampler else None
+        return ms_step, launches, clocks
+
+    def wall(self, fn, reps):
+        fn()
+        self.barrier()
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(reps):
+            out = fn()
+        self.barrier()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        return self.allsum(ms, self.dist.ReduceOp.MAX if self.world > 1 else None), out
+
+
+def run_pam(R, img, steps, warmup):
+    """whole-shard NGG scan; returns a dict with value / roofline / e2e pieces"""
+    N, torch, dist = R.N, R.torch, R.dist
+    info = img.info
+    span = info.shard_hi - info.shard_lo
+    cap = span // 8 + (1 << 20)
+    d_fw = torch.empty(cap, dtype=torch.int32, device=R.dev)
+    d_rv = torch.empty(cap, dtype=torch.int32, device=R.dev)
+    d_counts = torch.zeros(2, dtype=torch.int64, device=R.dev)
+
+    def step():
+        img.pam_scan_genome_dev(PAM, N.SCAN_GUIDE, d_fw.data_ptr(), cap, d_rv.data_ptr(), cap,
+                                d_counts.data_ptr(), R.stream.cuda_stream)
+        if R.world > 1:  # merge: the per-rank lists are already globally ordered by shard; gather counts
+            allc = torch.empty(2 * R.world, dtype=torch.int64, device=R.dev)
+            dist.all_gather_into_tensor(allc, d_counts)
+        return 2
+
+    ms_step, launches, clocks = R.timed(step, steps, warmup)
+    kt = img.kernel_times(steps)
+    kernel_ms = R.allsum(float(np.mean(kt)), dist.ReduceOp.MAX if R.world > 1 else None)
+    hits_rank = float(d_counts.sum().item())
+    G = info.total_bases
+    hits = R.allsum(hits_rank)
+    alg_bytes_rank = 0.25 * span + 4.0 * hits_rank
+    alg_bytes = R.allsum(alg_bytes_rank)
+
+    def e2e():
+        st = N.Stats()
+        fw, rv = img.pam_scan_genome(PAM, N.SCAN_GUIDE, stats=st, cap_hint=cap, pinned=True)
+        return st
+
+    e2e_ms, st = R.wall(e2e, 3)
+    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": int(hits), "bases": int(G),
+            "gbs": alg_bytes / (ms_step * 1e-3) / 1e9, "kernel_ms": kernel_ms,
+            "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
+            "e2e_ms": e2e_ms, "e2e_gbs": alg_bytes / (e2e_ms * 1e-3) / 1e9,
+            "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
+
+
+def run_offtarget(R, img, guides_u8, algo, steps, warmup):
+    N, torch, dist = R.N, R.torch, R.dist
+    n_guides = len(guides_u8)
+    enc = N.encode_guides([bytes(g).decode() for g in guides_u8])
+    d_guides = torch.from_numpy(enc.view(np.int32).copy()).to(R.dev)
+    cap = max(1 << 20, 256 * n_guides // R.world + (1 << 18))
+    d_hits = torch.empty((cap, 4), dtype=torch.int32, device=R.dev)
+    d_count = torch.zeros(1, dtype=torch.int64, device=R.dev)
+    use_index = algo != N.OT_SCAN
+
+    def step():
+        img.offtarget_search_dev(d_guides.data_ptr(), n_guides, PAM, OT_KW["core_length"],
+                                 OT_KW["core_mismatches"], OT_KW["total_mismatches"], algo,
+                                 d_hits.data_ptr(), cap, d_count.data_ptr(), R.stream.cuda_stream)
+        if R.world > 1:  # merge the per-GPU hit lists: counts, then the (padded) records
+            allc = torch.empty(R.world, dtype=torch.int64, device=R.dev)
+            dist.all_gather_into_tensor(allc, d_count)
+            m = int(allc.max().item())
+            if m > cap:
+                raise RuntimeError(f"hit buffer too small: {m} > {cap}")
+            merged = torch.empty((R.world * max(m, 1), 4), dtype=torch.int32, device=R.dev)
+            dist.all_gather_into_tensor(merged, d_hits[:max(m, 1)].contiguous())
+        return 6 if use_index else 1
+
+    ms_step, launches, clocks = R.timed(step, steps, warmup)
+    kt = img.kernel_times(steps)
+    kernel_ms = R.allsum(float(np.mean(kt)), dist.ReduceOp.MAX if R.world > 1 else None)
+    hits = int(R.allsum(float(d_count.item())))
+
+    def e2e():
+        st = N.Stats()
+        h, _ = img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
+        if R.world > 1:
+            t = torch.from_numpy(h.view(np.int32).reshape(-1, 4)).to(R.dev, non_blocking=True)
+            cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=R.dev)
+            allc = torch.empty(R.world, dtype=torch.int64, device=R.dev)
+            dist.all_gather_into_tensor(allc, cnt)
+            m = max(int(allc.max().item()), 1)
+            pad = torch.zeros((m, 4), dtype=torch.int32, device=R.dev)
+            pad[:t.shape[0]] = t
+            merged = torch.empty((R.world * m, 4), dtype=torch.int32, device=R.dev)
+            dist.all_gather_into_tensor(merged, pad)
+            if R.rank == 0:
+                merged.cpu()
+        return st
+
+    e2e_ms, st = R.wall(e2e, 3)
+    info = img.info
+    span = info.shard_hi - info.shard_lo
+    # algorithmic bytes of the search kernel on this rank: genome planes once, one 8-byte bucket
+    # lookup per window, 4 bytes per index key compared, 16 bytes per hit written
+    sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
+    hits_rank = float(d_count.item())
+    alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
+    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits,
+            "kernel_ms": kernel_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
+            "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
+            "pairs_scan": float(st.n_pairs) if not use_index else None,
+            "e2e_ms": e2e_ms, "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -181,8 +339,8 @@ def main():
     ap.add_argument("--guides", type=int, default=None)
     ap.add_argument("--algo", default="auto", choices=["auto", "scan", "index"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pam", action="store_true", help="skip the secondary PAM-scan measurement")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,194 +354,93 @@ def main():
     from guido_b200 import _native as N
 
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        run_reference(args, N, lens, seed, n_frac, gdesc)
+        if rank == 0:
+            run_reference(args, N, lens, seed, n_frac, gdesc)
         return 0
 
+    args.warmup = max(args.warmup, 3)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     algo = {"auto": N.OT_AUTO, "scan": N.OT_SCAN, "index": N.OT_INDEX}[args.algo]
+    R = Runner(args, N, torch, dist, rank, world, local_rank)
+    peak, peak_src = measured_peak_gbs()
 
     img = N.Image.synth(lens, seed=seed, n_frac=n_frac)
     img.upload(device=local_rank, shard_ix=rank, n_shards=world)
-    info = img.info
-    G = info.total_bases
-    shard_span = info.shard_hi - info.shard_lo
-    stream = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    G = img.info.total_bases
+    out = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic"}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    result = {}
     if args.workload == "pam":
-        cap = shard_span // 8 + (1 << 20)
-        d_fw = torch.empty(cap, dtype=torch.int32, device=dev)
-        d_rv = torch.empty(cap, dtype=torch.int32, device=dev)
-        d_counts = torch.zeros(2, dtype=torch.int64, device=dev)
-
-        def step():
-            img.pam_scan_genome_dev(PAM, N.SCAN_GUIDE, d_fw.data_ptr(), cap, d_rv.data_ptr(), cap,
-                                    d_counts.data_ptr(), stream.cuda_stream)
-            if world > 1:
-                # merge: all-gather of the per-rank counts, then of the (padded) position lists
-                allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allc, d_counts)
-            return 1
-
-        def e2e_step():
-            st = N.Stats()
-            fw, rv = img.pam_scan_genome(PAM, N.SCAN_GUIDE, stats=st, cap_hint=cap, pinned=True)
-            return st, (len(fw) + len(rv))
+        r = run_pam(R, img, args.steps, args.warmup)
+        out.update({
+            "value": r["gbs"], "unit": "GB/s", "ms_per_step": r["ms_per_step"], "dtype": "u32 bit-plane words",
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "config": {"workload": f"whole-genome NGG PAM scan, both strands, {gdesc} (BASELINE configs[1])",
+                       "pam": PAM, "scan_mode": "guide windows (N-free, inside one contig)",
+                       "l2": "flushed between steps (256 MB memset outside the events)",
+                       "parallelism": f"genome sharded x{world}", "hits": r["hits"]},
+            "bases_per_s": r["bases"] / (r["ms_per_step"] * 1e-3),
+            "e2e": {"value": r["e2e_gbs"], "unit": "GB/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                         "frac": r["kernel_gbs_per_gpu"] / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "pam_count_kernel + pam_fill_kernel", "kernel_ms": r["kernel_ms"],
+                         "algorithmic_bytes": "0.25 B/base read + 4 B/hit written, per GPU"},
+        })
+        if not args.no_cpu_baseline and world == 1 and rank == 0:
+            out["cpu_baseline"] = cpu_pam_sample(img)
     else:
         guides_u8 = sample_guides(img, args.guides, seed + 1)
-        enc = N.encode_guides([bytes(g).decode() for g in guides_u8])
-        d_guides = torch.from_numpy(enc.view(np.int32).copy()).to(dev)
-        cap = max(1 << 20, 256 * args.guides // world + (1 << 18))
-        d_hits = torch.empty((cap, 4), dtype=torch.int32, device=dev)
-        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        protos_blob = np.ascontiguousarray(guides_u8)
-
-        def step():
-            img.offtarget_search_dev(d_guides.data_ptr(), args.guides, PAM, OT_KW["core_length"],
-                                     OT_KW["core_mismatches"], OT_KW["total_mismatches"], algo,
-                                     d_hits.data_ptr(), cap, d_count.data_ptr(), stream.cuda_stream)
-            if world > 1:
-                allc = torch.empty(world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allc, d_count)
-                m = int(allc.max().item())
-                if m > cap:
-                    raise RuntimeError(f"hit buffer too small: {m} > {cap}")
-                merged = torch.empty((world * max(m, 1), 4), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(merged, d_hits[:max(m, 1)].contiguous())
-            return 1
-
-        def e2e_step():
-            st = N.Stats()
-            hits, _ = img.offtarget_search(protos_blob, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
-            if world > 1:
-                t = torch.from_numpy(hits.view(np.int32).reshape(-1, 4)).to(dev)
-                cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
-                allc = torch.empty(world, dtype=torch.int64, device=dev)
-                dist.all_gather_into_tensor(allc, cnt)
-                m = max(int(allc.max().item()), 1)
-                pad = torch.zeros((m, 4), dtype=torch.int32, device=dev)
-                pad[:t.shape[0]] = t
-                merged = torch.empty((world * m, 4), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(merged, pad)
-                if rank == 0:
-                    merged.cpu()
-            return st, len(hits)
-
-    # ---- warm-up, then K timed steps (CUDA events per step on the launching stream; L2 flushed
-    # between steps outside the events), bracketed by barrier + synchronize
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
-    t_wall0 = time.time()
-    for s, e in ev:
-        flush.zero_()
-        s.record(stream)
-        launches += step()
-        e.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    ms_total = sum(s.elapsed_time(e) for s, e in ev)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-
-    # correctness guard inside the bench: counts of the last step
-    if args.workload == "pam":
-        cnt = d_counts.clone()
-        if world > 1:
-            dist.all_reduce(cnt)
-        n_fw, n_rv = int(cnt[0].item()), int(cnt[1].item())
-        units = {"n_fw": n_fw, "n_rv": n_rv}
-        alg_bytes_rank = 0.25 * shard_span + 4.0 * float(d_counts.sum().item())
-        alg_bytes = torch.tensor([alg_bytes_rank], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(alg_bytes)
-        gbs = float(alg_bytes.item()) / (ms_step * 1e-3) / 1e9
-    else:
-        cnt = d_count.clone()
-        if world > 1:
-            dist.all_reduce(cnt)
-        units = {"n_hits": int(cnt.item())}
-
-    # ---- e2e (host buffers through the C-ABI), same number of steps
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    st_last = None
-    for _ in range(max(2, min(args.steps, 3))):
-        st_last, n_out = e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(2, min(args.steps, 3))
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-
+        r = run_offtarget(R, img, guides_u8, algo, args.steps, args.warmup)
+        gps = args.guides / (r["ms_per_step"] * 1e-3)
+        use_index = algo != N.OT_SCAN
+        out.update({
+            "value": gps, "unit": "guides/s", "ms_per_step": r["ms_per_step"],
+            "dtype": "u32 bit planes (XOR/OR + popc)", "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "config": {"workload": f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
+                                   + (" (BASELINE configs[3] on N GPUs)" if args.genome == "human" else " (BASELINE configs[2])"),
+                       "pam": PAM, "algo": "seed index + window scan" if use_index else "brute-force window x guide scan",
+                       "l2": "flushed between steps; the shard's planes + index keys exceed L2",
+                       "parallelism": f"genome sharded x{world}, guides replicated, NCCL all-gather of hit lists",
+                       "hits": r["hits"], "windows": r["sites"], "index_keys_compared": r["visited"]},
+            "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                         "frac": r["kernel_gbs_per_gpu"] / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "ot_kernel<index>" if use_index else "ot_kernel<scan>", "kernel_ms": r["kernel_ms"],
+                         "algorithmic_bytes": ("per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
+                                               "key compared + 16 B per hit" if use_index else
+                                               "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
+                                               "integer-issue bound, see int_pipe)")},
+        })
+        if not use_index and r["pairs_scan"]:
+            out["int_pipe"] = {"pairs_per_s_per_gpu": r["pairs_scan"] / (r["kernel_ms"] * 1e-3), "ops_per_pair": 4,
+                               "note": "2 LOP3 + POPC + ISETP per (window, guide) pair"}
+        if not args.no_pam and world == 1:
+            # second half of the metric in the same run: NGG scan of the 273 Mb genome (configs[1])
+            img.close()
+            lens2, seed2, nf2, gdesc2 = genome_lens("agam")
+            img2 = N.Image.synth(lens2, seed=seed2, n_frac=nf2).upload(device=local_rank)
+            p = run_pam(R, img2, 10, 3)
+            out["pam_scan"] = {"value": p["gbs"], "unit": "GB/s", "ms_per_step": p["ms_per_step"],
+                               "workload": f"whole-genome NGG PAM scan, both strands, {gdesc2} (BASELINE configs[1])",
+                               "hits": p["hits"], "bases_per_s": p["bases"] / (p["ms_per_step"] * 1e-3),
+                               "roofline": {"bound": "hbm", "achieved": p["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                                            "frac": p["kernel_gbs_per_gpu"] / peak, "kernel": "pam_count_kernel + pam_fill_kernel",
+                                            "kernel_ms": p["kernel_ms"]},
+                               "e2e": {"value": p["e2e_gbs"], "unit": "GB/s", "ms_per_step": p["e2e_ms"],
+                                       "d2h_bytes_per_step": p["d2h"]}}
+            img = img2
+        if not args.no_cpu_baseline and world == 1 and rank == 0:
+            img3 = N.Image.synth(lens, seed=seed, n_frac=n_frac) if not args.no_pam else img
+            out["cpu_baseline"] = cpu_offtarget_sample(img3, guides_u8, 2.0 * G)
+    if R.sampler:
+        R.sampler.stop()
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        out = {
-            "metric": "off-target guides/sec (<=4 mm, 3.1 Gb genome); PAM-scan genome GB/s vs HBM peak",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
-            "gpu_launches": launches, "clocks": clocks,
-        }
-        if args.workload == "pam":
-            out.update({
-                "value": gbs, "unit": "GB/s", "dtype": "u64 bit planes",
-                "config": {"workload": f"whole-genome NGG PAM scan, both strands, {gdesc} (BASELINE configs[1])",
-                           "pam": PAM, "scan_mode": "guide windows (N-free, in-contig)", "l2": "flushed between steps (256 MB memset)",
-                           "parallelism": f"genome sharded x{world}", **units},
-                "bases_per_s": G / (ms_step * 1e-3),
-                "e2e": {"value": (0.25 * G + 4.0 * (units["n_fw"] + units["n_rv"])) / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
-                        "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(st_last.bytes_h2d), "d2h_bytes_per_step": int(st_last.bytes_d2h)},
-                "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peak, "unit": "GB/s", "frac": gbs / world / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "pam_scan_kernel",
-                             "algorithmic_bytes": "0.25 B/base read + 4 B/hit written"},
-            })
-            if not args.no_cpu_baseline and world == 1:
-                out["cpu_baseline"] = cpu_pam_sample(img)
-        else:
-            n_windows = 2.0 * G
-            gps = args.guides / (ms_step * 1e-3)
-            passes = 1
-            out.update({
-                "value": gps, "unit": "guides/s", "dtype": "u32 bit planes (XOR/OR + popc)",
-                "config": {"workload": f"{args.guides} SpCas9 guides, <=4 mm (core 10/2) vs {gdesc}"
-                                       + (" (BASELINE configs[3])" if args.genome == "human" else " (BASELINE configs[2])"),
-                           "pam": PAM, "algo": args.algo, "l2": "flushed between steps; genome planes exceed L2 at 3.1 Gb",
-                           "parallelism": f"genome sharded x{world}, guides replicated, NCCL all-gather of hits", **units},
-                "e2e": {"value": args.guides / (e2e_ms * 1e-3), "unit": "guides/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(st_last.bytes_h2d), "d2h_bytes_per_step": int(st_last.bytes_d2h)},
-                "roofline": {"bound": "hbm", "achieved": 0.25 * G * passes / world / (ms_step * 1e-3) / 1e9, "peak": peak,
-                             "unit": "GB/s", "frac": 0.25 * G * passes / world / (ms_step * 1e-3) / 1e9 / peak, "traffic": None,
-                             "peak_source": peak_src, "kernel": "ot_scan_kernel" if args.algo == "scan" else "ot kernel",
-                             "algorithmic_bytes": "0.25 B/base genome read per pass (the compare is integer-issue bound, see int_pipe)"},
-                "sites_per_step": int(st_last.n_sites) if st_last else None,
-            })
-            if st_last and st_last.n_pairs:
-                pairs_s = st_last.n_pairs * world / (ms_step * 1e-3)
-                out["int_pipe"] = {"pairs_per_s": pairs_s, "ops_per_pair": 4,
-                                   "note": "2 LOP3 + POPC + ISETP per (window, guide) pair; see profiles/ for ncu pipe utilisation"}
-            if not args.no_cpu_baseline and world == 1:
-                out["cpu_baseline"] = cpu_offtarget_sample(img, guides_u8, n_windows)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -395,15 +452,13 @@ def run_reference(args, N, lens, seed, n_frac, gdesc):
     oracle's C restatement of its -n rule (all host cores) stands in, on a bounded sample."""
     img = N.Image.synth(lens, seed=seed, n_frac=n_frac)
     G = img.info.total_bases
-    vals = []
+    vals, cb = [], None
     t_all = time.perf_counter()
-    steps = max(1, args.steps)
-    cb = None
-    for i in range(args.warmup + steps):
+    guides_u8 = sample_guides(img, min(args.guides, 512), seed + 1) if args.workload == "offtarget" else None
+    for i in range(args.warmup + max(1, args.steps)):
         if args.workload == "pam":
             cb = cpu_pam_sample(img, budget_s=6.0)
         else:
-            guides_u8 = sample_guides(img, min(args.guides, 512), seed + 1)
             cb = cpu_offtarget_sample(img, guides_u8, 2.0 * G, budget_s=8.0)
         if i >= args.warmup:
             vals.append(cb["value"])
@@ -411,19 +466,20 @@ def run_reference(args, N, lens, seed, n_frac, gdesc):
             break
     v = float(np.mean(vals)) if vals else cb["value"]
     cb["value"] = v
-    unit = cb["unit"]
-    ms = (args.guides / v * 1e3) if args.workload == "offtarget" else (0.25 * G / (v * 1e9) * 1e3)
+    if args.workload == "offtarget":
+        ms = args.guides / v * 1e3
+        workload = f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
+    else:
+        ms = G / cb["bases_per_s"] * 1e3
+        workload = f"whole-genome NGG PAM scan, both strands, {gdesc}"
     print(json.dumps({
-        "impl": "reference",
-        "metric": "off-target guides/sec (<=4 mm, 3.1 Gb genome); PAM-scan genome GB/s vs HBM peak",
-        "value": v, "unit": unit, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64 (2-bit XOR + popcount)", "data": "synthetic",
-        "config": {"workload": (f"{args.guides} SpCas9 guides, <=4 mm (core 10/2) vs {gdesc}" if args.workload == "offtarget"
-                                else f"whole-genome NGG PAM scan, both strands, {gdesc}"),
+        "impl": "reference", "metric": METRIC, "value": v, "unit": cb["unit"], "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 (2-bit XOR + popcount)", "data": "synthetic",
+        "config": {"workload": workload,
                    "note": "bounded sample scaled to the whole workload; ms_per_step is the projected full-job time"},
         "cpu_baseline": cb,
-        "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": v, "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "guido_device_count": (ctypes.c_int, []),
     "guido_host_alloc": (ctypes.c_int, [_i64, _P(_vp)]),
     "guido_host_free": (ctypes.c_int, [_vp]),
+    "guido_kernel_times": (ctypes.c_int, [_vp, _vp, _i32, _P(_i32)]),
     "guido_image_from_fasta": (ctypes.c_int, [_cp, _P(_vp)]),
     "guido_image_from_seqs": (ctypes.c_int, [_i32, _P(_cp), _P(_cp), _P(_i64), _P(_vp)]),
     "guido_image_synth": (ctypes.c_int, [_i32, _P(_cp), _P(_i64), ctypes.c_uint64, ctypes.c_double,
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "guido_image_load": (ctypes.c_int, [_cp, _P(_vp)]),
     "guido_image_free": (ctypes.c_int, [_vp]),
     "guido_image_upload": (ctypes.c_int, [_vp, _i32, _i32, _i32]),
+    "guido_shard_bounds": (ctypes.c_int, [_i64, _i32, _i32, _P(_i64), _P(_i64)]),
     "guido_image_get_info": (ctypes.c_int, [_vp, _P(ImageInfo)]),
     "guido_image_contig": (ctypes.c_int, [_vp, _i64, _cp, _i64, _P(_i64), _P(_i64)]),
     "guido_image_fetch": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp]),
@@ -121,6 +123,13 @@ def default_device():
         if os.environ.get(key, "") != "":
             return int(os.environ[key])
     return 0
+
+
+def shard_bounds(padded_bases, shard_ix, n_shards):
+    """(lo, hi): global PAM-start range owned by shard_ix of n_shards (the library's partition rule)."""
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().guido_shard_bounds(int(padded_bases), shard_ix, n_shards, ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
 
 
 def _ptr(a):
@@ -260,6 +269,13 @@ class Image:
         buf = np.empty(n, dtype=np.uint8)
         check(lib().guido_image_fetch(self._h, contig_ix, start0, n, buf.ctypes.data))
         return buf.tobytes().decode()
+
+    def kernel_times(self, max_n=64):
+        """ms of the dominant kernel of the last calls (oldest first); synchronise first."""
+        out = np.zeros(max_n, np.float64)
+        n = ctypes.c_int32()
+        check(lib().guido_kernel_times(self._h, out.ctypes.data, max_n, ctypes.byref(n)))
+        return out[:n.value]
 
     def fetch_windows(self, gpos, width):
         """(n, width) uint8 array of letters for windows starting at global positions gpos."""

@@ -45,9 +45,19 @@ int device_init(DeviceState *ds, int device) {
     ds->sm_count = prop.multiProcessorCount;
     GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     for (auto &e : ds->ev) GUIDO_CUDA(cudaEventCreate(&e));
+    for (auto &p : ds->kev) { GUIDO_CUDA(cudaEventCreate(&p[0])); GUIDO_CUDA(cudaEventCreate(&p[1])); }
     GUIDO_CUDA(cudaMalloc(&ds->d_counts, 8 * sizeof(unsigned long long)));
     GUIDO_CUDA(cudaMalloc(&ds->d_tile_counter, 4 * sizeof(unsigned int)));
     return GUIDO_OK;
+}
+
+void kev_begin(DeviceState *ds, cudaStream_t stream) {
+    cudaEventRecord(ds->kev[ds->kev_count % DeviceState::kKev][0], stream);
+}
+
+void kev_end(DeviceState *ds, cudaStream_t stream) {
+    cudaEventRecord(ds->kev[ds->kev_count % DeviceState::kKev][1], stream);
+    ds->kev_count++;
 }
 
 void device_release(guido_image *img) {
@@ -62,6 +72,7 @@ void device_release(guido_image *img) {
         cudaFree(ds->d_index); cudaFree(ds->d_bucket);
         if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
         for (auto &e : ds->ev) if (e) cudaEventDestroy(e);
+        for (auto &p : ds->kev) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         if (ds->stream) cudaStreamDestroy(ds->stream);
     }
     delete ds;
@@ -85,10 +96,8 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
     if (rc) { device_release(img); return rc; }
     // contiguous shards of equal size, aligned to scan tiles (1024 blocks = 65536 bases); a shard
     // owns the PAM starts inside it and keeps a halo of 4 blocks (>= 20 + P bases) on either side
-    int64_t per = (img->n_blocks + n_shards - 1) / n_shards;
-    per = (per + 1023) / 1024 * 1024;
-    int64_t b0 = std::min<int64_t>(per * shard_ix, img->n_blocks), b1 = std::min<int64_t>(b0 + per, img->n_blocks);
-    ds->shard_lo = b0 * 64; ds->shard_hi = b1 * 64;
+    guido_shard_bounds(img->padded_bases, shard_ix, n_shards, &ds->shard_lo, &ds->shard_hi);
+    const int64_t b0 = ds->shard_lo / 64, b1 = ds->shard_hi / 64;
     ds->blk_lo = std::max<int64_t>((b0 & ~(int64_t)3) - 4, 0);   // multiple of 4: 256-bit loads stay aligned
     int64_t blk_hi = std::min<int64_t>(b1 + 4, img->n_blocks);
     ds->blk_n = blk_hi - ds->blk_lo;
@@ -191,6 +200,17 @@ int guido_device_count(void) {
     return ok;
 }
 
+int guido_shard_bounds(int64_t padded_bases, int32_t shard_ix, int32_t n_shards, int64_t *lo, int64_t *hi) {
+    if (n_shards < 1 || shard_ix < 0 || shard_ix >= n_shards || !lo || !hi) { set_error("bad shard arguments"); return GUIDO_ERR_ARG; }
+    const int64_t n_blocks = (padded_bases + 63) / 64;
+    int64_t per = (n_blocks + n_shards - 1) / n_shards;
+    per = (per + 1023) / 1024 * 1024;
+    const int64_t b0 = std::min<int64_t>(per * shard_ix, n_blocks), b1 = std::min<int64_t>(b0 + per, n_blocks);
+    *lo = b0 * 64;
+    *hi = b1 * 64;
+    return GUIDO_OK;
+}
+
 int guido_host_alloc(int64_t bytes, void **out) {
     if (bytes < 0 || !out) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     *out = nullptr;
@@ -200,6 +220,21 @@ int guido_host_alloc(int64_t bytes, void **out) {
 
 int guido_host_free(void *p) {
     if (p) GUIDO_CUDA(cudaFreeHost(p));
+    return GUIDO_OK;
+}
+
+int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t *n) {
+    if (!img || !img->dev || !out_ms || !n) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    long long have = std::min<long long>(ds->kev_count, DeviceState::kKev);
+    long long take = std::min<long long>(have, max_n);
+    for (long long i = 0; i < take; i++) {
+        long long k = ds->kev_count - take + i;
+        float ms = 0;
+        GUIDO_CUDA(cudaEventElapsedTime(&ms, ds->kev[k % DeviceState::kKev][0], ds->kev[k % DeviceState::kKev][1]));
+        out_ms[i] = ms;
+    }
+    *n = (int32_t)take;
     return GUIDO_OK;
 }
 
@@ -359,7 +394,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, enc.data(), (size_t)(8 * n_guides), cudaMemcpyHostToDevice, st));
     int64_t dcap = std::max<int64_t>(std::max<int64_t>(cap, 64 * n_guides), 1 << 16);
-    unsigned long long found = 0, sites = 0;
+    unsigned long long found = 0, sites = 0, visited = 0;
     float kernel_ms = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = ensure_bytes(&ds->d_out[0], &ds->out_cap[0], dcap * (int64_t)sizeof(guido_ot_hit)))) return rc;
@@ -374,13 +409,13 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
                                 ds->d_counts + 1, st, &launches);
         if (rc) return rc;
         GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
-        unsigned long long c2[2];
+        unsigned long long c2[3];
         GUIDO_CUDA(cudaMemcpyAsync(c2, ds->d_counts, sizeof c2, cudaMemcpyDeviceToHost, st));
         GUIDO_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
         kernel_ms += ms;
-        found = c2[0]; sites = c2[1];
+        found = c2[0]; sites = c2[1]; visited = c2[2];
         if ((int64_t)found <= dcap) break;
         dcap = (int64_t)found;  // exact size known now: one more pass
     }
@@ -442,7 +477,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         cudaEventElapsedTime(&t, ds->ev[0], ds->ev[3]);
         stats->kernel_ms = kernel_ms; stats->total_ms = t; stats->n_launches = launches;
         stats->n_sites = (int64_t)sites;
-        stats->n_pairs = use_index ? 0 : (int64_t)sites * n_guides;
+        stats->n_pairs = use_index ? (int64_t)visited : (int64_t)sites * n_guides;
         stats->bytes_h2d = h2d; stats->bytes_d2h = d2h;
     }
     if ((int64_t)found > cap) {

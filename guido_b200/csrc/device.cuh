@@ -30,6 +30,10 @@ struct DeviceState {
     int64_t shard_lo = 0, shard_hi = 0;  // owned global positions (PAM starts), 64-aligned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ring of event pairs around the dominant kernel of the last calls (guido_kernel_times)
+    static constexpr int kKev = 64;
+    cudaEvent_t kev[kKev][2] = {};
+    long long kev_count = 0;
     // scratch (grown on demand, reused between calls)
     unsigned long long *d_desc = nullptr;  int64_t desc_cap = 0;     // look-back descriptors
     unsigned long long *d_counts = nullptr;                          // 8 x u64 counters
@@ -43,6 +47,8 @@ struct DeviceState {
 };
 
 int device_init(DeviceState *ds, int device);
+void kev_begin(DeviceState *ds, cudaStream_t stream);
+void kev_end(DeviceState *ds, cudaStream_t stream);
 int ensure_bytes(void **p, int64_t *cap, int64_t need);
 int ensure_pinned(DeviceState *ds, int64_t need);
 

@@ -130,6 +130,7 @@ constexpr int kHitBuf = 384;
 struct HitBuf {
     uint32_t n;
     unsigned long long base;
+    unsigned long long visited;  // index entries compared by this CTA (statistics)
     guido_ot_hit rec[kHitBuf];
 };
 
@@ -195,6 +196,7 @@ __device__ __forceinline__ void lookup_round(const OtScanArgs &a, const uint32_t
             if (lane >= d) inc += t;
         }
         const uint32_t total = __shfl_sync(kFull, inc, 31);
+        if (lane == 0) atomicAdd(&hb.visited, (unsigned long long)total);
         __syncwarp();
         w_start[lane] = start;
         w_pref[lane] = inc - len;
@@ -256,6 +258,10 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
             bucket_range(a.ix, key, start, len);
             dist = (A & dmask) | ((B & dmask) << F);
         }
+        {
+            const uint32_t warp_total = __reduce_add_sync(kFull, len);
+            if (lane == 0) atomicAdd(&hb.visited, (unsigned long long)warp_total);
+        }
         for (int s0 = 0; s0 < 32; s0 += U) {
             uint32_t st[U], ln[U], ds[U], maxlen = 0;
 #pragma unroll
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
     __shared__ HitBuf s_hits;
     __shared__ uint32_t s_warp[kThreads / 32];
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_hits.n = 0;
+    if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
     __syncthreads();
     const int P = a.op.pam.len;
     const int W = kProto + P;
@@ -402,7 +408,10 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
     } else {
         if (qlen) compare_round<RING>(a, sA, sB, sQ, head, qlen);
     }
-    if (threadIdx.x == 0 && a.site_count) atomicAdd(a.site_count, n_sites);
+    if (threadIdx.x == 0 && a.site_count) {  // [0] windows examined, [1] index entries compared
+        atomicAdd(a.site_count, n_sites);
+        if constexpr (kIndex) atomicAdd(a.site_count + 1, s_hits.visited);
+    }
 }
 
 template <bool kIndex>
@@ -416,7 +425,9 @@ static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream)
     GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_kernel<kIndex>, kThreads, smem));
     int grid = ds->sm_count * std::max(per_sm, 1);
     if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
+    kev_begin(ds, stream);
     ot_kernel<kIndex><<<grid, kThreads, smem, stream>>>(a);
+    kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
     return GUIDO_OK;
 }

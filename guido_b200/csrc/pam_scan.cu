@@ -419,8 +419,10 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_fill_kernel, kThreads, 0));
         ds->scan_grid[1] = ds->sm_count * std::max(per_sm, 1);
     }
+    kev_begin(ds, stream);
     pam_count_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[0]), kThreads, 0, stream>>>(a);
     pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, 0, stream>>>(a);
+    kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
     if (n_launches) *n_launches += 2;
     return GUIDO_OK;

@@ -94,6 +94,11 @@ int guido_device_count(void);
 int guido_host_alloc(int64_t bytes, void **out);
 int guido_host_free(void *p);
 
+/* device time (ms, CUDA events on the launching stream) of the DOMINANT kernel of the last calls on
+ * this handle -- PAM count+fill, or the off-target search kernel -- oldest first, up to 64 kept.
+ * The caller must have synchronised the streams it launched on. */
+int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t *n);
+
 /* ---- genome image: replaces `bowtie-build` in Genome.build (guido/genome.py:156-171) --------- */
 /* FASTA -> two bit planes (1 bit/base each, interleaved per 64 bases) + sorted list of non-ACGT
  * runs + contig table.  Sequence names are the header up to the first whitespace.            */
@@ -110,6 +115,9 @@ int guido_image_free(guido_image *img);
 /* copy shard `shard_ix` of `n_shards` (contiguous, equal block counts, +1 block halo each side)
  * to HBM of `device`; afterwards scans/searches on this handle cover that shard only. */
 int guido_image_upload(guido_image *img, int32_t device, int32_t shard_ix, int32_t n_shards);
+/* the partition rule itself: global range [lo, hi) of PAM starts owned by shard_ix of n_shards
+ * (equal, 65536-base aligned chunks of the padded coordinate; trailing shards may be empty) */
+int guido_shard_bounds(int64_t padded_bases, int32_t shard_ix, int32_t n_shards, int64_t *lo, int64_t *hi);
 int guido_image_get_info(const guido_image *img, guido_image_info *info);
 int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t name_cap,
                        int64_t *len, int64_t *global_offset);
