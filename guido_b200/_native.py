@@ -347,7 +347,7 @@ class Image:
             blob = "".join(protos).encode()
         flags = np.zeros(n, np.uint8) if want_raw_flags else None
         st = stats if stats is not None else Stats()
-        cap = max(4096, 32 * n)
+        cap = max(4096, 32 * n, getattr(self, "_ot_hint", 0))
         while True:
             hits = self._pinned("hits", cap, OT_HIT_DTYPE) if pinned else np.empty(cap, OT_HIT_DTYPE)
             nh = ctypes.c_int64()
@@ -358,6 +358,7 @@ class Image:
                 cap = nh.value
                 continue
             check(rc)
+            self._ot_hint = nh.value + nh.value // 16 + 16  # right-size the next call's buffer
             return hits[:nh.value], flags
 
     def offtarget_search_dev(self, d_guides, n_guides, pam, core_length, core_mismatches,

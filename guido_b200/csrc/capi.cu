@@ -393,7 +393,8 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     int launches = 0;
     GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, enc.data(), (size_t)(8 * n_guides), cudaMemcpyHostToDevice, st));
-    int64_t dcap = std::max<int64_t>(std::max<int64_t>(cap, 64 * n_guides), 1 << 16);
+    // device-side capacity: the caller's, a per-guide guess, or what the previous search needed
+    int64_t dcap = std::max<int64_t>(std::max<int64_t>(cap, 64 * n_guides), std::max<int64_t>(1 << 16, ds->hits_hint + ds->hits_hint / 16));
     unsigned long long found = 0, sites = 0, visited = 0;
     float kernel_ms = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -420,6 +421,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         dcap = (int64_t)found;  // exact size known now: one more pass
     }
     *n_hits = (int64_t)found;
+    ds->hits_hint = (int64_t)found;
     // canonical (guide, gpos, strand) order on the device, then one copy straight into the
     // caller's buffer (fast when that buffer is pinned, see guido_host_alloc)
     if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;

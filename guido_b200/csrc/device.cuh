@@ -44,6 +44,7 @@ struct DeviceState {
     void *d_index = nullptr;               int64_t index_cap = 0;        // OT seed index entries
     void *d_bucket = nullptr;              int64_t bucket_cap = 0;       // OT seed index offsets
     void *h_pinned = nullptr;              int64_t pinned_cap = 0;
+    int64_t hits_hint = 0;  // hit count of the previous off-target search (sizes the next buffer)
 };
 
 int device_init(DeviceState *ds, int device);
