@@ -216,7 +216,8 @@ class Runner:
         return ms_step, launches, clocks
 
     def wall(self, fn, reps):
-        fn()
+        for _ in range(3):  # warm-up: the first calls size the device / pinned result buffers
+            fn()
         self.barrier()
         t0 = time.perf_counter()
         out = None
