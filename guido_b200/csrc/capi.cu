@@ -45,14 +45,15 @@ int device_init(DeviceState *ds, int device) {
     ds->sm_count = prop.multiProcessorCount;
     GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     for (auto &e : ds->ev) GUIDO_CUDA(cudaEventCreate(&e));
-    for (auto &p : ds->kev) { GUIDO_CUDA(cudaEventCreate(&p[0])); GUIDO_CUDA(cudaEventCreate(&p[1])); }
     GUIDO_CUDA(cudaMalloc(&ds->d_counts, 8 * sizeof(unsigned long long)));
     GUIDO_CUDA(cudaMalloc(&ds->d_tile_counter, 4 * sizeof(unsigned int)));
     return GUIDO_OK;
 }
 
 void kev_begin(DeviceState *ds, cudaStream_t stream) {
-    cudaEventRecord(ds->kev[ds->kev_count % DeviceState::kKev][0], stream);
+    cudaEvent_t *p = ds->kev[ds->kev_count % DeviceState::kKev];
+    if (!p[0]) { cudaEventCreate(&p[0]); cudaEventCreate(&p[1]); }  // created on first use
+    cudaEventRecord(p[0], stream);
 }
 
 void kev_end(DeviceState *ds, cudaStream_t stream) {
