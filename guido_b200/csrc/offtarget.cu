@@ -271,8 +271,9 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
                 ds[u] = __shfl_sync(kFull, dist, s0 + u);
                 maxlen = max(maxlen, ln[u]);
             }
-            // a lane takes keys off, off+1 of each bucket: one aligned 8-byte load, 64 keys per warp step
-            for (uint32_t off = 2 * lane; off < maxlen; off += 64) {
+            // a lane takes keys off, off+1 of each bucket: one aligned 8-byte load, 64 keys per warp
+            // step.  The first step is straight-line code (a bucket rarely holds more than 64 keys).
+            auto step = [&](const uint32_t off) {
                 uint2 kv[U];
 #pragma unroll
                 for (int u = 0; u < U; u++)
@@ -290,7 +291,9 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
                         if (h1) { h.guide = __ldg(&a.ix.guides[st[u] + off + 1]); push_hit(a, hb, h); }
                     }
                 }
-            }
+            };
+            step(2 * lane);
+            for (uint32_t off = 2 * lane + 64; off < maxlen; off += 64) step(off);
         }
     }
 }

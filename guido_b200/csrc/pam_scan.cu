@@ -267,9 +267,20 @@ __global__ void __launch_bounds__(kThreads, 3) pam_count_kernel(const PamScanArg
 }
 
 // set bits of a word -> positions base+bit appended to dst[off...]
+// A 32-base word holds Poisson(2) NGG hits: the first four are extracted by predicated
+// straight-line code (no loop, no divergence penalty), the rare rest by a loop.
 __device__ __forceinline__ uint32_t emit_word(uint32_t m, uint32_t base, uint32_t *dst, uint32_t off) {
-    while (m) { dst[off++] = base + (__ffs(m) - 1); m &= m - 1; }
-    return off;
+    uint32_t *p = dst + off;
+    const uint32_t next = off + __popc(m);
+    const uint32_t b1 = base - 1;  // __ffs is 1-based
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (m) p[k] = b1 + __ffs(m);
+        m &= m - 1;  // 0 stays 0
+    }
+    uint32_t n = 4;
+    while (m) { p[n++] = b1 + __ffs(m); m &= m - 1; }
+    return next;
 }
 
 // staged hits [a0, a0+n) of s -> g[a0 .. a0+n); s and g agree modulo 16 bytes, so whole uint4s
