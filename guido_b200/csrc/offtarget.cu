@@ -158,12 +158,12 @@ __device__ __forceinline__ void flush_hits(const OtScanArgs &a, HitBuf &hb, bool
     __syncthreads();
 }
 
-// bucket of a core key: offsets[] holds EVEN starts (64-bit key loads stay aligned) with the
-// "true count is odd" flag in bit 0
+// bucket of a core key: offsets[] holds starts that are multiples of 8 (the vector key loads stay
+// aligned) with the amount of padding (0..7) in the low 3 bits
 __device__ __forceinline__ void bucket_range(const OtIndex &ix, uint32_t key, uint32_t &start, uint32_t &len) {
     const uint32_t v = __ldg(&ix.offsets[key]), w = __ldg(&ix.offsets[key + 1]);
-    start = v & ~1u;
-    len = (w & ~1u) - start - (v & 1u);
+    start = v & ~7u;
+    len = (w & ~7u) - start - (v & 7u);
 }
 
 template <int RING>
@@ -298,6 +298,58 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
     }
 }
 
+// Default lookup: ONE THREAD PER WINDOW.  A lane walks its own bucket with 256-bit loads (8 keys,
+// one full 32-byte sector per load; buckets start on 32-byte boundaries), so a warp instruction
+// advances 32 windows at once and the per-window overhead of the warp-per-window variants
+// (shuffles, per-key validity, loop control) disappears: ~5 issue slots per key compared.  The
+// padding keys at a bucket's end are not filtered in the hot loop -- only in the rare hit path.
+template <int RING>
+__device__ __forceinline__ void lookup_round_thread(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
+                                                    const uint32_t *sQ, uint32_t head, uint32_t n, HitBuf &hb) {
+    const int cl = a.ix.cl, dl = a.ix.dl, F = a.ix.field;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1, fmask = (1u << F) - 1;
+    const int tot_max = a.op.total_max;
+    unsigned long long visited = 0;
+    for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
+        const uint32_t idx = (head + j) & (RING - 1);
+        const uint32_t A = sA[idx], B = sB[idx];
+        const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+        uint32_t start, len;
+        bucket_range(a.ix, key, start, len);
+        const uint32_t dist = (A & dmask) | ((B & dmask) << F);
+        visited += len;
+        const uint32_t *p = a.ix.keys + start;
+        for (uint32_t off = 0; off < len; off += 8) {
+            uint32_t kv[8];
+            unsigned long long q0, q1, q2, q3;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p + off));
+            kv[0] = (uint32_t)q0; kv[1] = (uint32_t)(q0 >> 32); kv[2] = (uint32_t)q1; kv[3] = (uint32_t)(q1 >> 32);
+            kv[4] = (uint32_t)q2; kv[5] = (uint32_t)(q2 >> 32); kv[6] = (uint32_t)q3; kv[7] = (uint32_t)(q3 >> 32);
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t x = kv[k] ^ dist;
+                any |= (int)__popc((x | (x >> F)) & fmask) <= tot_max;
+            }
+            if (any) {  // rare (6e-4 per key): redo with the validity check and park the hits
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t x = kv[k] ^ dist;
+                    if (off + k < len && (int)__popc((x | (x >> F)) & fmask) <= tot_max) {
+                        guido_ot_hit h;
+                        h.guide = __ldg(&a.ix.guides[start + off + k]); h.gpos = sQ[idx]; h.hi = A; h.lo = B;
+                        push_hit(a, hb, h);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&hb.visited, visited);
+}
+
 template <bool kIndex>
 struct OtCfg {
     // the brute-force consumer wants 8 sites per thread in registers (2048 per round); the index
@@ -386,7 +438,8 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
             __syncthreads();
             while (qlen >= ROUND) {
                 if constexpr (kIndex) {
-                    if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, ROUND, s_hits);
+                    if (a.ix.wide == 2) lookup_round_thread<RING>(a, sA, sB, sQ, head, ROUND, s_hits);
+                    else if (a.ix.wide == 1) lookup_round_wide<RING>(a, sA, sB, sQ, head, ROUND, s_hits);
                     else lookup_round<RING>(a, sA, sB, sQ, head, ROUND, s_lookup, s_hits);
                     __syncthreads();
                     flush_hits(a, s_hits, false);
@@ -403,7 +456,8 @@ __global__ void __launch_bounds__(kThreads) ot_kernel(const OtScanArgs a) {
     __syncthreads();
     if constexpr (kIndex) {
         if (qlen) {
-            if (a.ix.wide) lookup_round_wide<RING>(a, sA, sB, sQ, head, qlen, s_hits);
+            if (a.ix.wide == 2) lookup_round_thread<RING>(a, sA, sB, sQ, head, qlen, s_hits);
+            else if (a.ix.wide == 1) lookup_round_wide<RING>(a, sA, sB, sQ, head, qlen, s_hits);
             else lookup_round<RING>(a, sA, sB, sQ, head, qlen, s_lookup, s_hits);
         }
         __syncthreads();
@@ -484,8 +538,8 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
         if constexpr (!kFill) {
             atomicAdd(&a.counts[key], 1u);
         } else {
-            // offsets are even with the odd-count flag in bit 0; the fill cursor keeps that flag in bit 31
-            const uint32_t pos = (a.counts[key] & ~1u) + (atomicAdd(&a.fill[key], 1u) & 0x7fffffffu);
+            // offsets are multiples of 8 with the padding in the low 3 bits
+            const uint32_t pos = (a.counts[key] & ~7u) + atomicAdd(&a.fill[key], 1u);
             // key = distal planes in two fields of `field` bits; the core mismatches of this variant
             // are appended to the hi field as that many 1-bits, which the window's zeros turn into
             // mismatches -- so popc of the folded XOR is the TOTAL mismatch count, no extra add
@@ -497,17 +551,18 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
 }
 
 // in-place exclusive scan of n u32 values: 4096 per block, then the block sums, then the fix-up
-// With pad_even every value is rounded up to even before it is scanned (bucket starts stay 8-byte
-// aligned for the 64-bit key loads) and "the true count was odd" is kept in bit 0 of the result.
+// With pad8 every value is rounded up to a multiple of 8 before it is scanned (bucket starts stay
+// 32-byte aligned for the 256-bit key loads) and the padding (0..7) is kept in the low 3 bits of the
+// result: start = v & ~7, true length = next start - start - (v & 7).
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint32_t n, uint32_t *block_sums,
-                                                            int pad_even) {
+                                                            int pad8) {
     __shared__ uint32_t s_w[32];
     const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
     uint32_t v[4], odd[4], sum = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t c = (base + i < n) ? data[base + i] : 0;
-        odd[i] = pad_even ? (c & 1u) : 0u;
+        odd[i] = pad8 ? ((8u - (c & 7u)) & 7u) : 0u;
         v[i] = c + odd[i];
         sum += v[i];
     }
@@ -606,8 +661,8 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
-    // every bucket may be padded by one slot to an even length
-    const uint64_t n_slots = (n_entries + n_buckets + 3) & ~(uint64_t)3;
+    // every bucket is padded to a multiple of 8 slots
+    const uint64_t n_slots = (n_entries + 7ull * n_buckets + 7) & ~(uint64_t)7;
     if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_slots * 8))) return rc;
     uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
              *d_var = sums + n_scan_blocks;
@@ -631,7 +686,8 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     a.pv = pv; a.op = op; a.r = r;
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
-    const int wide = force ? atoi(force) : (n_entries / n_buckets >= 12);
+    // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
+    const int wide = force ? atoi(force) : 2;
     a.ix = OtIndex{counts, keys, ids, cl, dl, field, wide};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;

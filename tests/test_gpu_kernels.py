@@ -197,7 +197,7 @@ def test_offtarget_index_rejects_unsupported_core(native):
     hits, _ = img.offtarget_search(["ACGT" * 5], core_length=20, algo=native.OT_AUTO)  # falls back to the scan kernel
 
 
-@pytest.mark.parametrize("wide", ["0", "1"])
+@pytest.mark.parametrize("wide", ["0", "1", "2"])
 def test_offtarget_index_lookup_variants(native, monkeypatch, wide):
     """both bucket-walking strategies of the seed-index kernel give the brute-force answer"""
     monkeypatch.setenv("GUIDO_OT_WIDE", wide)
