@@ -298,52 +298,89 @@ __device__ __forceinline__ void lookup_round_wide(const OtScanArgs &a, const uin
     }
 }
 
+// one window's walk through its bucket: current 8 keys in registers, the next 8 in flight
+struct BucketWalk {
+    const uint32_t *p;   // bucket start (32-byte aligned)
+    uint32_t len, off;   // true length, keys consumed so far
+    uint32_t dist, idx;  // the window's distal planes in key layout; its ring slot
+    unsigned long long n0, n1, n2, n3;
+};
+
+__device__ __forceinline__ void walk_load(BucketWalk &w, uint32_t off) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w.n0), "=l"(w.n1), "=l"(w.n2), "=l"(w.n3) : "l"(w.p + off));
+}
+
+template <int RING>
+__device__ __forceinline__ void walk_init(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB, uint32_t head,
+                                          uint32_t j, uint32_t n, BucketWalk &w, unsigned long long &visited) {
+    const int cl = a.ix.cl, dl = a.ix.dl, F = a.ix.field;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    w.len = 0; w.off = 0; w.p = a.ix.keys; w.dist = 0; w.idx = 0;
+    w.n0 = w.n1 = w.n2 = w.n3 = 0;
+    if (j >= n) return;
+    w.idx = (head + j) & (RING - 1);
+    const uint32_t A = sA[w.idx], B = sB[w.idx];
+    const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+    uint32_t start;
+    bucket_range(a.ix, key, start, w.len);
+    w.dist = (A & dmask) | ((B & dmask) << F);
+    w.p = a.ix.keys + start;
+    visited += w.len;
+    if (w.len) walk_load(w, 0);
+    // pull the rest of the bucket towards L2 right away (no registers tied up): the later sectors
+    // of the walk then cost an L2 hit instead of a DRAM round trip
+    for (uint32_t o = 32; o < w.len; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(w.p + o));
+}
+
+// compare the 8 keys in registers (the next 8 are requested first); hits are parked
+__device__ __forceinline__ void walk_step(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
+                                          const uint32_t *sQ, BucketWalk &w, HitBuf &hb) {
+    const int F = a.ix.field;
+    const uint32_t fmask = (1u << F) - 1;
+    const int tot_max = a.op.total_max;
+    uint32_t kv[8];
+    kv[0] = (uint32_t)w.n0; kv[1] = (uint32_t)(w.n0 >> 32); kv[2] = (uint32_t)w.n1; kv[3] = (uint32_t)(w.n1 >> 32);
+    kv[4] = (uint32_t)w.n2; kv[5] = (uint32_t)(w.n2 >> 32); kv[6] = (uint32_t)w.n3; kv[7] = (uint32_t)(w.n3 >> 32);
+    const uint32_t off = w.off;
+    if (off + 8 < w.len) walk_load(w, off + 8);
+    w.off = off + 8;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t x = kv[k] ^ w.dist;
+        any |= (int)__popc((x | (x >> F)) & fmask) <= tot_max;
+    }
+    if (any) {  // rare (6e-4 per key): redo with the validity check and park the hits
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t x = kv[k] ^ w.dist;
+            if (off + k < w.len && (int)__popc((x | (x >> F)) & fmask) <= tot_max) {
+                guido_ot_hit h;
+                h.guide = __ldg(&a.ix.guides[(w.p - a.ix.keys) + off + k]);
+                h.gpos = sQ[w.idx]; h.hi = sA[w.idx]; h.lo = sB[w.idx];
+                push_hit(a, hb, h);
+            }
+        }
+    }
+}
+
 // Default lookup: ONE THREAD PER WINDOW.  A lane walks its own bucket with 256-bit loads (8 keys,
 // one full 32-byte sector per load; buckets start on 32-byte boundaries), so a warp instruction
 // advances 32 windows at once and the per-window overhead of the warp-per-window variants
 // (shuffles, per-key validity, loop control) disappears: ~5 issue slots per key compared.  The
-// padding keys at a bucket's end are not filtered in the hot loop -- only in the rare hit path.
+// kernel is latency-bound on the key loads (profiles/r1_offtarget.md), so the next sector of the
+// bucket is requested before the current one is compared.  (Walking two windows per thread at once
+// was measured slower: 21.6 vs 19.6 ms, register spills and extra divergence.)  The padding keys
+// at a bucket's end are not filtered in the hot loop -- only in the rare hit path.
 template <int RING>
 __device__ __forceinline__ void lookup_round_thread(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
                                                     const uint32_t *sQ, uint32_t head, uint32_t n, HitBuf &hb) {
-    const int cl = a.ix.cl, dl = a.ix.dl, F = a.ix.field;
-    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1, fmask = (1u << F) - 1;
-    const int tot_max = a.op.total_max;
     unsigned long long visited = 0;
     for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
-        const uint32_t idx = (head + j) & (RING - 1);
-        const uint32_t A = sA[idx], B = sB[idx];
-        const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
-        uint32_t start, len;
-        bucket_range(a.ix, key, start, len);
-        const uint32_t dist = (A & dmask) | ((B & dmask) << F);
-        visited += len;
-        const uint32_t *p = a.ix.keys + start;
-        for (uint32_t off = 0; off < len; off += 8) {
-            uint32_t kv[8];
-            unsigned long long q0, q1, q2, q3;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                         : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p + off));
-            kv[0] = (uint32_t)q0; kv[1] = (uint32_t)(q0 >> 32); kv[2] = (uint32_t)q1; kv[3] = (uint32_t)(q1 >> 32);
-            kv[4] = (uint32_t)q2; kv[5] = (uint32_t)(q2 >> 32); kv[6] = (uint32_t)q3; kv[7] = (uint32_t)(q3 >> 32);
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t x = kv[k] ^ dist;
-                any |= (int)__popc((x | (x >> F)) & fmask) <= tot_max;
-            }
-            if (any) {  // rare (6e-4 per key): redo with the validity check and park the hits
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t x = kv[k] ^ dist;
-                    if (off + k < len && (int)__popc((x | (x >> F)) & fmask) <= tot_max) {
-                        guido_ot_hit h;
-                        h.guide = __ldg(&a.ix.guides[start + off + k]); h.gpos = sQ[idx]; h.hi = A; h.lo = B;
-                        push_hit(a, hb, h);
-                    }
-                }
-            }
-        }
+        BucketWalk w;
+        walk_init<RING>(a, sA, sB, head, j, n, w, visited);
+        while (w.off < w.len) walk_step(a, sA, sB, sQ, w, hb);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
