@@ -310,9 +310,14 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
             pad[:t.shape[0]] = t
             merged = torch.empty((R.world * m, 4), dtype=torch.int32, device=R.dev)
             dist.all_gather_into_tensor(merged, pad)
-            if R.rank == 0:
-                merged.cpu()
+            if R.rank == 0:  # the merged list lands in pinned host memory on rank 0
+                if e2e.host is None or e2e.host.shape[0] < merged.shape[0]:
+                    e2e.host = torch.empty((merged.shape[0] * 5 // 4, 4), dtype=torch.int32, pin_memory=True)
+                e2e.host[:merged.shape[0]].copy_(merged, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         return st
+
+    e2e.host = None
 
     e2e_ms, st = R.wall(e2e, 3)
     info = img.info
