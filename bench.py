@@ -111,6 +111,15 @@ class ClockSampler:
             self.proc.terminate()
 
 
+def ncu_traffic(kernel, workload_ok):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json);
+    only reported when this run is the workload the capture was taken on"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not workload_ok or not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel, {}).get("bytes")
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -329,7 +338,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
     return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits,
             "kernel_ms": kernel_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
-            "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
+            "alg_bytes_rank": alg_bytes_rank, "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
             "pairs_scan": float(st.n_pairs) if not use_index else None,
             "e2e_ms": e2e_ms, "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
 
@@ -393,7 +402,9 @@ def main():
             "e2e": {"value": r["e2e_gbs"], "unit": "GB/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
-                         "frac": r["kernel_gbs_per_gpu"] / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": r["kernel_gbs_per_gpu"] / peak,
+                         "traffic": ncu_traffic("pam_count_kernel + pam_fill_kernel", args.genome == "agam" and world == 1),
+                         "peak_source": peak_src,
                          "kernel": "pam_count_kernel + pam_fill_kernel", "kernel_ms": r["kernel_ms"],
                          "algorithmic_bytes": "0.25 B/base read + 4 B/hit written, per GPU"},
         })
@@ -416,7 +427,9 @@ def main():
             "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
-                         "frac": r["kernel_gbs_per_gpu"] / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": r["kernel_gbs_per_gpu"] / peak,
+                         "traffic": ncu_traffic("ot_kernel<index>", use_index and args.genome == "human" and args.guides == 100_000 and world == 1),
+                         "algorithmic_bytes_per_launch": r["alg_bytes_rank"], "peak_source": peak_src,
                          "kernel": "ot_kernel<index>" if use_index else "ot_kernel<scan>", "kernel_ms": r["kernel_ms"],
                          "algorithmic_bytes": ("per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
                                                "key compared + 16 B per hit" if use_index else

@@ -132,7 +132,7 @@ class Guide:
         if "N" in self.locus_seq:
             self._skip_end_joining()
             return
-        patterns = _mmej.generate_mmej_patterns(self.relative_cut_pos, self.locus_seq, length_weight)
+        patterns = _mmej.top_patterns_batch([self.relative_cut_pos], [self.locus_seq], length_weight, n_patterns)[0]
         self._finish_end_joining(patterns, n_patterns)
 
     # ------------------------------------------------------------------ off-targets

@@ -176,8 +176,10 @@ class Locus:
         if len(self.guides) == 0:
             raise ValueError("No gRNAs saved yet.")
         todo = [g for g in self.guides if "N" not in g.locus_seq]
-        results = _mmej.generate_mmej_patterns_batch([g.relative_cut_pos for g in todo],
-                                                     [g.locus_seq for g in todo], length_weight)
+        # only the n_patterns winners are materialised as dicts (their scores decide, and those
+        # are evaluated for every kept candidate, bit-identically, in numpy)
+        results = _mmej.top_patterns_batch([g.relative_cut_pos for g in todo],
+                                           [g.locus_seq for g in todo], length_weight, n_patterns)
         by_guide = {id(g): r for g, r in zip(todo, results)}
         for g in self.guides:  # in order, so an upstream-style TypeError leaves later guides untouched
             if id(g) in by_guide:

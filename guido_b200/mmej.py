@@ -68,6 +68,40 @@ def generate_mmej_patterns_batch(rel_cut_positions, sequences, length_weight, de
     return out
 
 
+def top_patterns_batch(rel_cut_positions, sequences, length_weight, n_patterns, device=None, stats=None):
+    """The ``n_patterns`` best-scoring patterns per cut site, in the order
+    ``sorted(patterns, key=lambda x: -x["pattern_score"])[:n]`` gives (stable), or None.
+
+    Same dicts as :func:`generate_mmej_patterns_batch` would give, but only the winners are built:
+    the scores of ALL kept candidates are evaluated vectorised -- ``100 * lf[del_len] * (len + GC)``
+    in float64 with ``lf`` tabulated by the reference's own expression, i.e. the same two IEEE
+    multiplications in the same order, hence bit-identical -- and the stable top-n is taken on them.
+    (A 150-bp window keeps ~240 patterns; guido keeps 5.)
+    """
+    sequences = list(sequences)
+    cuts = [int(c) for c in rel_cut_positions]
+    if not sequences:
+        return []
+    tuples, offsets, n_cand = _native.mmej_batch(sequences, cuts, device=device, stats=stats)
+    lf = np.array([round(1 / math.exp(d / length_weight), 3) for d in range(512)], dtype=np.float64)
+    out = []
+    for g, (seq, cut) in enumerate(zip(sequences, cuts)):
+        if n_cand[g] == 0:
+            out.append(None)
+            continue
+        t = tuples[offsets[g]:offsets[g + 1]]
+        ls, le, rs = _unpack(t)
+        left_seq, right_seq = seq[:cut], seq[cut:]
+        b = np.frombuffer(left_seq.encode(), dtype=np.uint8)
+        cum = np.concatenate(([0], np.cumsum((b == 71) | (b == 67))))
+        gc = cum[le] - cum[ls]
+        del_len = (len(left_seq) - ls) + rs
+        score = (100 * lf[del_len]) * (((le - ls) - gc) + (gc * 2))
+        best = np.argsort(-score, kind="stable")[:n_patterns]
+        out.append([_pattern_dict(left_seq, right_seq, ls[i], le[i], rs[i], length_weight) for i in best])
+    return out
+
+
 def generate_mmej_patterns(rel_cut_position, sequence, length_weight):
     """All MMEJ patterns around ``rel_cut_position`` of ``sequence`` (list of dicts or None)."""
     return generate_mmej_patterns_batch([rel_cut_position], [sequence], length_weight)[0]

@@ -1,0 +1,60 @@
+"""Columnar tables (guido_b200/tables.py) against the per-locus API: same guides, same records."""
+import numpy as np
+import pytest
+
+import guido_b200 as guido
+from guido_b200 import _native, off_targets, tables
+from tests import util
+from tests.test_host_logic import GUIDE_ATTRS
+
+pytestmark = pytest.mark.gpu
+
+
+def test_guide_table_equals_find_guides_per_contig():
+    contigs = util.synthetic_contigs(61, [30000, 12000, 50, 8000], n_runs=3, run_len=(5, 300), lower_frac=0.2)
+    img = _native.Image.from_seqs(contigs).upload()
+    t = tables.GuideTable(img, "NGG")
+    k = 0
+    for ci, (name, seq) in enumerate(contigs):
+        loc = guido.Locus(sequence=seq, name=name)
+        want = loc.find_guides()
+        n = int((t.contig == ci).sum())
+        assert n == len(want)
+        for j, w in enumerate(want):
+            g = t[k + j]
+            for a in GUIDE_ATTRS:
+                assert getattr(g, a) == getattr(w, a), (name, j, a, getattr(g, a), getattr(w, a))
+        protos = t.protospacers(np.arange(k, k + n))
+        assert [p.tobytes().decode() for p in protos] == [w.guide_seq[:20] for w in want]
+        k += n
+    assert k == len(t)
+    assert len(tables.GuideTable(img, "TTTV")) == 0  # upstream: only 3-nt PAMs give guides
+    with pytest.raises(KeyError):
+        tables.GuideTable(img, "NGX")
+
+
+def test_offtarget_table_equals_run_bowtie(tmp_path):
+    contigs = util.synthetic_contigs(62, [60000, 40000], n_runs=2)
+    s0 = contigs[0][1].upper()
+    contigs[1] = (contigs[1][0], contigs[1][1][:5000] + s0[1000:1800] + contigs[1][1][5800:])
+    path = tmp_path / "g.g2b"
+    _native.Image.from_seqs(contigs).save(path)
+    genome = guido.Genome("g", bowtie_index_abspath=str(path))
+    loc = guido.Locus(sequence=contigs[0][1][990:1810], name="chr1", start=991, genome=genome)
+    guides = loc.find_guides()
+    found = loc.find_off_targets()
+    img = off_targets.get_image(str(path))
+    t = tables.offtarget_table(img, [g.guide_seq[:20] for g in guides], guide_chrom=[g.guide_chrom for g in guides],
+                               guide_start=[g.guide_start for g in guides])
+    assert set(np.nonzero(t.has_key)[0].tolist()) == set(found)
+    sums = t.ot_sum_score()
+    counts = t.counts_matrix()
+    key = lambda r: (r["chromosome"], r["start"], r["strand"])
+    total = 0
+    for ix, recs in found.items():
+        want = sorted(({k: v for k, v in r.items() if k != "cfd_score"} for r in recs), key=key)
+        assert sorted(t.records(ix), key=key) == want
+        assert sums[ix] == guides[ix].layers["ot_sum_score"]
+        assert "|".join(str(c) for c in counts[ix]) == guides[ix].off_target_str
+        total += len(recs)
+    assert total == len(t) and total > 50
