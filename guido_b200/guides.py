@@ -90,6 +90,18 @@ class Guide:
         g._fill(geo, chromosome, strand)
         return g
 
+    @classmethod
+    def _from_fields(cls, locus_seq, guide_seq, long_seq, pam_len, chromosome, guide_start, guide_end,
+                     strand, rel_cut, abs_cut):
+        """Same record as ``_fill`` from already-sliced strings (the bulk path of Locus.find_guides)."""
+        g = cls.__new__(cls)
+        g.__dict__.update(
+            locus_seq=locus_seq, guide_seq=guide_seq, guide_long_seq=long_seq,
+            guide_pam=guide_seq[-pam_len:], guide_chrom=chromosome, guide_start=guide_start,
+            guide_end=guide_end, guide_strand=strand, relative_cut_pos=rel_cut, absolute_cut_pos=abs_cut,
+            rank_score=0.0, rank=0, id="", mmej_patterns=[], off_targets=[], off_target_str="", _layers={})
+        return g
+
     def __repr__(self):
         return (f"{self.id if self.id else 'gRNA'}({self.guide_seq}|{self.guide_chrom}:"
                 f"{self.guide_start}-{self.guide_end}|{self.guide_strand}|)")

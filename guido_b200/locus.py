@@ -90,17 +90,42 @@ class Locus:
         """Build Guide records for PAM starts (relative to ``fwd_seq``), forward strand first.
         ``keep`` optionally pre-filters (strand, position) pairs that find_guides would drop anyway."""
         P = len(pam)
+        n = len(fwd_seq)
         rc_seq = rev_comp_fast(fwd_seq) if len(pams_rv) else None
         chrom = self.chromosome
         out = []
+        make = Guide._from_fields
         for strand, positions, rc in (("+", pams_fw, None), ("-", pams_rv, rc_seq)):
+            minus = strand == "-"
             for p in positions:
                 if keep is not None and not keep(strand, p):
                     continue
-                geo = guide_geometry(fwd_seq, p, P, strand, start=start, rc_sequence=rc)
-                if "N" in geo["guide_seq"]:
+                if p < 24:
+                    # slices that can wrap around (guides.py:69-76 quirk): the general routine
+                    geo = guide_geometry(fwd_seq, p, P, strand, start=start, rc_sequence=rc)
+                    if "N" not in geo["guide_seq"]:
+                        out.append(Guide._from_geometry(geo, chrom, strand))
                     continue
-                out.append(Guide._from_geometry(geo, chrom, strand))
+                # bulk path: guide_geometry inlined for p >= 24 (no negative slice index anywhere)
+                if minus:
+                    cut, rs, re = p + P + 3, p, p + P + 20
+                    guide_seq = rc[max(n - re, 0):n - rs]
+                    if "N" in guide_seq:
+                        continue
+                    long_seq = rc[max(n - re - 4, 0):n - rs + 3]
+                else:
+                    cut, rs, re = p - 3, p - 20, p + P
+                    guide_seq = fwd_seq[rs:re]
+                    if "N" in guide_seq:
+                        continue
+                    long_seq = fwd_seq[rs - 4:re + 3]
+                lo = cut - 75
+                if lo < 0:
+                    window, rel_cut = fwd_seq[0:cut + 75], cut
+                else:
+                    window, rel_cut = fwd_seq[lo:cut + 75], 75
+                out.append(make(window, guide_seq, long_seq, P, chrom, start + rs, start + re - 1,
+                                strand, rel_cut, start + cut))
         return out
 
     def _find_guides_in_interval(self, sequence, start, pam):
@@ -147,20 +172,21 @@ class Locus:
             sub = upper[a:b]
             m = len(sub)
 
-            def rel(arr):
+            def rel(arr, minus):
                 if m < P:
                     return []
                 lo = np.searchsorted(arr, a, side="left")
                 hi = np.searchsorted(arr, a + m - P, side="right")
-                return (arr[lo:hi] - a).tolist()
+                p = arr[lo:hi].astype(np.int64) - a
+                # exactly the post-filter of locus.py:313-319 (23-nt guide, cut inside the
+                # interval), evaluated on the position column before any record is built
+                if minus:
+                    cut, whole_guide = seq_start + p + P + 3, p + P + 20 <= m
+                else:
+                    cut, whole_guide = seq_start + p - 3, p >= 20
+                return p[whole_guide & (cut >= interval_start) & (cut <= interval_end)].tolist()
 
-            def keep(strand, p, _s=seq_start, _lo=interval_start, _hi=interval_end, _m=m):
-                # exactly the post-filter of locus.py:313-319, evaluated before building the record
-                if strand == "+":
-                    return p >= 20 and _lo <= _s + p - 3 <= _hi
-                return p + P + 20 <= _m and _lo <= _s + p + P + 3 <= _hi
-
-            found = self._guides_from_pam_positions(sub, seq_start, pam, rel(all_fw), rel(all_rv), keep)
+            found = self._guides_from_pam_positions(sub, seq_start, pam, rel(all_fw, False), rel(all_rv, True))
             self.guides.extend(g for g in found
                                if len(g.guide_seq) == 23 and interval_start <= g.absolute_cut_pos <= interval_end)
 

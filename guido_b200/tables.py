@@ -20,9 +20,10 @@ class GuideTable:
     """All gRNAs of a genome image for one PAM, as columns.
 
     Equivalent, contig by contig, to ``Locus(sequence=<contig>, name=<contig name>).find_guides(pam)``
-    of the reference (i.e. ``locus_from_sequence``; note that passing ``end=len(contig)`` explicitly
-    makes the reference drop the contig's last base, ``locus.py:298-307``): same guides, same order (cut position, '+' before '-' on ties), same ids
-    per contig.  Only 3-nt PAMs give guides (reference ``locus.py:316``).
+    of the reference (i.e. ``locus_from_sequence``): same guides, same order (cut position, '+'
+    before '-' on ties), same ids per contig.  Passing ``end=len(contig)`` explicitly makes the
+    reference drop the contig's last base (``locus.py:298-307``); the table follows the default.
+    Only 3-nt PAMs give guides (reference ``locus.py:316``).
     """
 
     def __init__(self, image, pam="NGG"):
