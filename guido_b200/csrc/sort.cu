@@ -32,6 +32,20 @@ __global__ void __launch_bounds__(256) merge_hits_kernel(const unsigned long lon
     }
 }
 
+__global__ void __launch_bounds__(256) mark_guides_kernel(const guido_ot_hit *hits, uint64_t n, uint8_t *flags) {
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull)
+        flags[hits[i].guide] = 1;
+}
+
+// flags[g] = 1 for every guide that owns at least one hit (flags must be zeroed by the caller)
+int mark_hit_guides(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uint8_t *d_flags, cudaStream_t stream) {
+    if (n == 0) return GUIDO_OK;
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ds->sm_count * 16);
+    mark_guides_kernel<<<grid, 256, 0, stream>>>(d_hits, n, d_flags);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
 // sort d_hits[0..n) in place; scratch comes from ds->d_out[1]
 int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t n_guides, cudaStream_t stream,
                      int *n_launches) {

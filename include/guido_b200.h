@@ -47,6 +47,7 @@ extern "C" {
 #define GUIDO_OT_AUTO 0
 #define GUIDO_OT_SCAN 1  /* brute-force: every PAM-valid window against every guide (XOR + popc)     */
 #define GUIDO_OT_INDEX 2 /* guide-side seed index: windows look up their core k-mer                  */
+#define GUIDO_OT_TABLE 3 /* seed index joined with the genome's PAM-site table (guido_site_table_build) */
 
 typedef struct guido_image guido_image;
 
@@ -170,6 +171,16 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
 int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides,
                                const char *pam, int32_t core_len, int32_t core_mm, int32_t total_mm,
                                int32_t algo, void *d_hits, int64_t cap, void *d_count, void *stream);
+/* Genome-side index of the off-target search, the counterpart of the `bowtie-build` index files
+ * (guido/genome.py:156-171): every PAM-valid window of the uploaded shard (both strands, guide
+ * orientation) grouped by its core_len PAM-proximal bases, 12 bytes per window in HBM.  Guide
+ * independent; depends on the PAM's base sets and on core_len only.  GUIDO_OT_AUTO/TABLE searches
+ * build it on first use; this call builds it ahead of time (Genome.build / benchmarks) and reports
+ * its size and build time.  GUIDO_ERR_CAPACITY: more than 2^31 windows or not enough free HBM
+ * (AUTO then streams the genome through the seed index instead). */
+int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, int64_t *n_sites,
+                           double *build_ms);
+int guido_site_table_free(guido_image *img);
 /* encode n x 20 letters into the {hi, lo} plane words the _dev call takes (host helper) */
 int guido_encode_guides(const char *protos, int64_t n_guides, uint32_t *out_hi_lo);
 

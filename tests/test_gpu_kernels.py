@@ -130,13 +130,13 @@ def _protos_from_genome(rng, contigs, n, mutate=3):
     ("NRG", dict(core_mismatches=1)),
     ("TGG", dict(core_mismatches=3, total_mismatches=4)),
 ])
-@pytest.mark.parametrize("algo", ["scan", "index"])
+@pytest.mark.parametrize("algo", ["scan", "index", "table"])
 def test_offtarget_scan_matches_oracle(native, oracle, pam, kw, algo):
     contigs = util.synthetic_contigs(21, [60000, 25000, 300], n_runs=4, iupac=5)
     rng = np.random.default_rng(3)
     protos = _protos_from_genome(rng, contigs, 60)
     img = native.Image.from_seqs(contigs).upload()
-    hits, flags = img.offtarget_search(protos, pam=pam, algo={"scan": native.OT_SCAN, "index": native.OT_INDEX}[algo], **kw)
+    hits, flags = img.offtarget_search(protos, pam=pam, algo={"scan": native.OT_SCAN, "index": native.OT_INDEX, "table": native.OT_TABLE}[algo], **kw)
     valid, keys = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
     assert util.gpu_hit_set(img, hits) == valid
     assert len(hits) == len(valid)
@@ -188,6 +188,8 @@ def test_offtarget_index_equals_scan(native, core_length, core_mismatches):
     a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
     b, _ = img.offtarget_search(protos, algo=native.OT_INDEX, **kw)
     assert len(a) > 0 and np.array_equal(a, b)
+    c, _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)   # join with the PAM-site table
+    assert np.array_equal(a, c)
 
 
 def test_offtarget_index_rejects_unsupported_core(native):
@@ -208,3 +210,45 @@ def test_offtarget_index_lookup_variants(native, monkeypatch, wide):
     a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
     b, _ = img.offtarget_search(protos, algo=native.OT_INDEX, want_raw_flags=False)
     assert len(a) > 0 and np.array_equal(a, b)
+
+
+def test_site_table_lifecycle(native):
+    """the PAM-site table is built once per (PAM sets, core length), reused, rebuilt on change,
+    and a sharded image tables only its own shard"""
+    contigs = util.synthetic_contigs(27, [200000, 70000], n_runs=4, iupac=3)
+    rng = np.random.default_rng(8)
+    protos = _protos_from_genome(rng, contigs, 200, mutate=4)
+    img = native.Image.from_seqs(contigs).upload()
+    fw, rv = img.pam_scan_genome("NGG", native.SCAN_STRICT)
+    n, ms = img.site_table_build("NGG", 10)
+    assert n == len(fw) + len(rv) and ms > 0
+    assert img.site_table_build("NGG", 10) == (n, 0.0)            # reused
+    ref, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    got, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    assert np.array_equal(ref, got)
+    n8, ms8 = img.site_table_build("NGG", 8)                      # other core length: rebuilt
+    assert n8 == n and ms8 > 0
+    got, _ = img.offtarget_search(protos, pam="NAG", algo=native.OT_TABLE, want_raw_flags=False)
+    ref, _ = img.offtarget_search(protos, pam="NAG", algo=native.OT_SCAN, want_raw_flags=False)
+    assert np.array_equal(ref, got)                               # other PAM: rebuilt on the fly
+    img.site_table_free()
+    got, _ = img.offtarget_search(protos, pam="NAG", algo=native.OT_AUTO, want_raw_flags=False)
+    assert np.array_equal(ref, got)
+    parts = []
+    for i in range(3):
+        sh = native.Image.from_seqs(contigs).upload(shard_ix=i, n_shards=3)
+        parts.append(sh.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)[0])
+    merged = np.concatenate(parts)
+    merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+    whole, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    assert np.array_equal(merged, whole)
+
+
+def test_site_table_empty_and_tiny(native):
+    img = native.Image.from_seqs([("c", "ACGT" * 4)]).upload()      # shorter than a window
+    assert img.site_table_build("NGG", 10)[0] == 0
+    hits, flags = img.offtarget_search(["ACGT" * 5], algo=native.OT_TABLE)
+    assert len(hits) == 0 and flags.tolist() == [0]
+    img = native.Image.from_seqs([("c", "T" * 30 + "ACGTACGTACGTACGTACGTAGG" + "T" * 30)]).upload()
+    hits, flags = img.offtarget_search(["ACGTACGTACGTACGTACGT", "GGGGGGGGGGCCCCCCCCCC"], algo=native.OT_TABLE)
+    assert hits["guide"].tolist() == [0] and flags.tolist()[0] == 1
