@@ -1,5 +1,7 @@
 // capi.cu -- the extern "C" entry points that touch the device (see include/guido_b200.h).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -432,15 +434,36 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
     DeviceState *ds = img->dev;
     cudaStream_t st = ds->stream;
-    std::vector<uint32_t> enc((size_t)(2 * n_guides));
-    if ((rc = guido_encode_guides(protos, n_guides, enc.data()))) return rc;
-    if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, std::max<int64_t>(8 * n_guides, 8)))) return rc;
+    // GUIDO_TRACE=1: host wall-clock of the call's phases on stderr (tools/e2e_probe.py)
+    const bool trace = getenv("GUIDO_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace) fprintf(stderr, "[guido] %-18s %8.3f ms\n", what,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
+    // the letters go to the device as they are and are packed into plane words there (a host loop
+    // over 2e6 letters costs more than the whole search); d_guides = [n x uint2][n x 20 letters]
+    if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, std::max<int64_t>(28 * n_guides, 8) + 64))) return rc;
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
     if ((rc = resolve_ot_algo(img, op, r, n_guides, algo, st, &algo))) return rc;
     const bool use_index = algo != GUIDO_OT_SCAN;
     int launches = 0;
     GUIDO_CUDA(cudaEventRecord(ds->ev[0], st));
-    GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, enc.data(), (size_t)(8 * n_guides), cudaMemcpyHostToDevice, st));
+    {
+        char *d_letters = (char *)ds->d_guides + 8 * n_guides;
+        GUIDO_CUDA(cudaMemcpyAsync(d_letters, protos, (size_t)(kProto * n_guides), cudaMemcpyHostToDevice, st));
+        GUIDO_CUDA(cudaMemsetAsync(ds->d_counts + 6, 0xff, sizeof(unsigned long long), st));
+        if ((rc = encode_guides_device(ds, d_letters, n_guides, (uint2 *)ds->d_guides, ds->d_counts + 6, st))) return rc;
+        unsigned long long bad = 0;
+        GUIDO_CUDA(cudaMemcpyAsync(&bad, ds->d_counts + 6, sizeof bad, cudaMemcpyDeviceToHost, st));
+        GUIDO_CUDA(cudaStreamSynchronize(st));
+        if (bad != ~0ull) {
+            set_error("guide %lld holds a letter outside A/C/G/T at position %d", (long long)(bad / 32), (int)(bad % 32) + 1);
+            return GUIDO_ERR_ARG;
+        }
+        launches += 1;
+    }
+    lap("guides on device");
     // device-side capacity: the caller's, a per-guide guess, or what the previous search needed
     int64_t dcap = std::max<int64_t>(std::max<int64_t>(cap, 64 * n_guides), std::max<int64_t>(1 << 16, ds->hits_hint + ds->hits_hint / 16));
     unsigned long long found = 0, sites = 0, visited = 0;
@@ -468,6 +491,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
         kernel_ms += ms;
         found = c2[0]; sites = c2[1]; visited = c2[2];
+        lap("search done");
         if ((int64_t)found <= dcap) break;
         dcap = (int64_t)found;  // exact size known now: one more pass
     }
@@ -476,9 +500,10 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     // canonical (guide, gpos, strand) order on the device, then one copy straight into the
     // caller's buffer (fast when that buffer is pinned, see guido_host_alloc)
     if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;
+    if (trace) { cudaStreamSynchronize(st); lap("sort done"); }
     int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
     if (ncopy) GUIDO_CUDA(cudaMemcpyAsync(hits, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
-    int64_t d2h = 16 + ncopy * 16, h2d = 8 * n_guides;
+    int64_t d2h = 16 + ncopy * 16, h2d = kProto * n_guides;
     if (raw_flags && n_guides > 0) {
         // a valid hit is a raw alignment: mark the guides that own one (on the device -- walking
         // 1e7 hit records on the host costs more than the search)
@@ -492,6 +517,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     }
     GUIDO_CUDA(cudaEventRecord(ds->ev[3], st));
     GUIDO_CUDA(cudaStreamSynchronize(st));
+    lap("copy done");
     if ((int64_t)found > cap) {
         set_error("output capacity too small: need %lld hits", (long long)found);
         return GUIDO_ERR_CAPACITY;
@@ -507,7 +533,9 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
             if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, true, &rp))) return rc;
             std::vector<uint32_t> sub(2 * todo.size());
             for (size_t i = 0; i < todo.size(); i++) {
-                uint32_t hi = enc[(size_t)(2 * todo[i])], lo = enc[(size_t)(2 * todo[i] + 1)];
+                uint32_t hl[2];
+                if ((rc = guido_encode_guides(protos + kProto * todo[i], 1, hl))) return rc;
+                uint32_t hi = hl[0], lo = hl[1];
                 for (int k = 0; k < rp.pam.len; k++)
                     if (rp.pam.fixed_mask & (1u << k)) {
                         hi |= (uint32_t)(rp.pam.code[k] >> 1) << (kProto + k);

@@ -451,21 +451,19 @@ int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64
 }
 
 int guido_encode_guides(const char *protos, int64_t n, uint32_t *out) {
+    uint8_t code[256];  // table lookup: a switch on random letters mispredicts on every second one
+    memset(code, 0xff, sizeof code);
+    code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2; code['T'] = code['t'] = 3;
     for (int64_t g = 0; g < n; g++) {
         uint32_t hi = 0, lo = 0;
         for (int i = 0; i < kProto; i++) {
-            int c;
-            switch (protos[g * kProto + i]) {
-                case 'A': case 'a': c = 0; break;
-                case 'C': case 'c': c = 1; break;
-                case 'G': case 'g': c = 2; break;
-                case 'T': case 't': c = 3; break;
-                default:
-                    set_error("guide %lld holds a letter outside A/C/G/T at position %d", (long long)g, i + 1);
-                    return GUIDO_ERR_ARG;
+            const uint32_t c = code[(unsigned char)protos[g * kProto + i]];
+            if (c > 3) {
+                set_error("guide %lld holds a letter outside A/C/G/T at position %d", (long long)g, i + 1);
+                return GUIDO_ERR_ARG;
             }
-            lo |= (uint32_t)(c & 1) << i;
-            hi |= (uint32_t)(c >> 1) << i;
+            lo |= (c & 1) << i;
+            hi |= (c >> 1) << i;
         }
         out[2 * g] = hi;
         out[2 * g + 1] = lo;

@@ -27,6 +27,7 @@
 namespace guido {
 
 constexpr int kSitesPerThread = 8;
+constexpr int kSliceWords = 24;  // words per 32-key block of the bit-sliced index (see idx_transpose_kernel)
 
 // guide-side seed index (built per search call by the idx_* kernels below), structure of arrays:
 // the search streams `keys` only and touches `guides` on a hit
@@ -37,6 +38,7 @@ struct OtIndex {
     int cl, dl;               // core / distal length (cl + dl = 20)
     int field;                // bits per plane field of a key: dl + core_mm pseudo-positions
     int wide;                 // average bucket is large: walk buckets warp-wide
+    const uint4 *planes;      // bit-sliced copy of the keys (join over the site table), or null
 };
 
 struct OtScanArgs {
@@ -553,6 +555,106 @@ __global__ void __launch_bounds__(kThreads, kMode == kModeScan ? 3 : 5) ot_kerne
     }
 }
 
+// ---- join against the bit-sliced index ----------------------------------------------------------
+
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t lop3_nor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+// a | (b ^ c)
+__device__ __forceinline__ uint32_t lop3_or_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+
+// 0 / ~0 according to bit j of x
+__device__ __forceinline__ uint32_t bit_mask(uint32_t x, int j) { return (uint32_t)((int32_t)(x << (31 - j)) >> 31); }
+
+// One block of 32 keys against one window: bit k of the result is set when key k is a hit, i.e.
+// (distal mismatches + c') <= 7.  kh/kl = the window's distal planes as 0/~0 words per base.
+__device__ __forceinline__ uint32_t sliced_block_hits(const uint4 *__restrict__ p, const uint32_t (&wh)[10],
+                                                      const uint32_t (&wl)[10]) {
+    const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
+    const uint32_t kh[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
+    const uint32_t kl[10] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+    uint32_t m[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) m[j] = lop3_or_xor(kh[j] ^ wh[j], kl[j], wl[j]);
+    // carry-save count of m[0..9] + c' (q5.x..w = weights 1, 2, 4, 8); only "reaches 8" matters,
+    // so sums that feed nothing are never formed
+    // weight 1: eleven inputs -> five carries
+    const uint32_t s0 = lop3_xor3(m[0], m[1], m[2]), c0 = lop3_maj(m[0], m[1], m[2]);
+    const uint32_t s1 = lop3_xor3(m[3], m[4], m[5]), c1 = lop3_maj(m[3], m[4], m[5]);
+    const uint32_t s2 = lop3_xor3(m[6], m[7], m[8]), c2 = lop3_maj(m[6], m[7], m[8]);
+    const uint32_t s3 = lop3_xor3(s0, s1, s2), c3 = lop3_maj(s0, s1, s2);
+    const uint32_t c4 = lop3_maj(s3, m[9], q5.x);
+    // weight 2: five carries + c' bit 1 -> three carries
+    const uint32_t t0 = lop3_xor3(c0, c1, c2), d0 = lop3_maj(c0, c1, c2);
+    const uint32_t t1 = lop3_xor3(c3, c4, q5.y), d1 = lop3_maj(c3, c4, q5.y);
+    const uint32_t d2 = t0 & t1;
+    // weight 4: three carries + c' bit 2 -> two carries
+    const uint32_t u0 = lop3_xor3(d0, d1, d2), e0 = lop3_maj(d0, d1, d2);
+    const uint32_t e1 = u0 & q5.z;
+    // weight 8: any carry or c' bit 3 = more than 7
+    return lop3_nor3(e0, e1, q5.w);
+}
+
+constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
+
+__global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtScanArgs a) {
+    __shared__ HitBuf s_hits;
+    if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
+    __syncthreads();
+    constexpr uint32_t kChunk = kJoinPerThread * kThreads;
+    const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
+    const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
+    const uint4 *__restrict__ planes = a.ix.planes;
+    unsigned long long visited = 0;
+    for (uint32_t c = c0; c < c1; c++) {
+        for (uint32_t k = 0; k < kJoinPerThread; k++) {
+            const uint32_t i = c * kChunk + k * kThreads + threadIdx.x;
+            if (i >= a.tab_n) continue;
+            const uint32_t A = __ldg(&a.tab_a[i]), B = __ldg(&a.tab_b[i]);
+            const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
+            const uint32_t v = __ldg(&a.ix.offsets[key]), w = __ldg(&a.ix.offsets[key + 1]);
+            const uint32_t start = v & ~31u, len = (w & ~31u) - start - (v & 31u);
+            if (len == 0) continue;
+            visited += len;
+            uint32_t wh[10], wl[10];
+#pragma unroll
+            for (int j = 0; j < 10; j++) { wh[j] = bit_mask(A, j); wl[j] = bit_mask(B, j); }
+            const uint32_t blk0 = start >> 5, n_blk = (len + 31) >> 5;
+            for (uint32_t b = 0; b < n_blk; b++) {
+                uint32_t r = sliced_block_hits(planes + (size_t)(blk0 + b) * (kSliceWords / 4), wh, wl);
+                while (r) {  // rare: 1.4 % of (window, block) pairs
+                    const int kk = __ffs((int)r) - 1;
+                    r &= r - 1;
+                    guido_ot_hit h;
+                    h.guide = __ldg(&a.ix.guides[(size_t)(blk0 + b) * 32 + kk]);
+                    h.gpos = __ldg(&a.tab_q[i]); h.hi = A; h.lo = B;
+                    push_hit(a, s_hits, h);
+                }
+            }
+        }
+        __syncthreads();
+        flush_hits(a, s_hits, false);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_hits.visited, visited);
+    __syncthreads();
+    flush_hits(a, s_hits, true);
+    if (threadIdx.x == 0 && a.site_count) {
+        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)a.tab_n);
+        atomicAdd(a.site_count + 1, s_hits.visited);
+    }
+}
+
 template <int kMode>
 static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream) {
     a.first_block = a.r.lo / 64;
@@ -596,7 +698,6 @@ __device__ __forceinline__ void join_init(const OtScanArgs &a, uint32_t i, Bucke
     if (w.len) walk_load<true>(w, 0);
 }
 
-constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
 
 __global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a) {
     __shared__ HitBuf s_hits;
@@ -635,7 +736,7 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
     a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
@@ -664,6 +765,9 @@ struct IdxArgs {
     uint32_t *fill;            // n_buckets
     uint32_t *keys, *ids;      // n_entries each
     uint32_t key_lo, key_hi;   // fill pass: only buckets in [key_lo, key_hi) are written
+    uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7 or 31)
+    int sliced;                // 1: row-major staging format of the bit-sliced index (see below)
+    uint32_t cbias;            // sliced: 7 - total_max, added to the variant's core mismatch count
 };
 
 template <bool kFill>
@@ -680,31 +784,38 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
         if constexpr (!kFill) {
             atomicAdd(&a.counts[key], 1u);
         } else {
-            // offsets are multiples of 8 with the padding in the low 3 bits
-            const uint32_t pos = (a.counts[key] & ~7u) + atomicAdd(&a.fill[key], 1u);
-            // key = distal planes in two fields of `field` bits; the core mismatches of this variant
-            // are appended to the hi field as that many 1-bits, which the window's zeros turn into
-            // mismatches -- so popc of the folded XOR is the TOTAL mismatch count, no extra add
+            // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
+            const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
             const uint32_t cmm = (uint32_t)__popc(xh | xl);
-            a.keys[pos] = (G.x & dmask) | (((1u << cmm) - 1u) << a.dl) | ((G.y & dmask) << a.field);
+            if (a.sliced) {
+                // staging word of the bit-sliced index: distal hi plane, distal lo plane, then the
+                // biased core mismatch count c' = c + 7 - total_max (a hit is d + c' <= 7)
+                a.keys[pos] = (G.x & dmask) | ((G.y & dmask) << a.dl) | ((cmm + a.cbias) << (2 * a.dl));
+            } else {
+                // key = distal planes in two fields of `field` bits; the core mismatches of this
+                // variant are appended to the hi field as that many 1-bits, which the window's zeros
+                // turn into mismatches -- so popc of the folded XOR is the TOTAL mismatch count
+                a.keys[pos] = (G.x & dmask) | (((1u << cmm) - 1u) << a.dl) | ((G.y & dmask) << a.field);
+            }
             a.ids[pos] = g;
         }
     }
 }
 
 // in-place exclusive scan of n u32 values: 4096 per block, then the block sums, then the fix-up
-// With pad8 every value is rounded up to a multiple of 8 before it is scanned (bucket starts stay
-// 32-byte aligned for the 256-bit key loads) and the padding (0..7) is kept in the low 3 bits of the
-// result: start = v & ~7, true length = next start - start - (v & 7).
+// With pad = 8 or 32 every value is rounded up to a multiple of pad before it is scanned (bucket
+// starts stay aligned for the 256-bit key loads / for whole 32-key blocks) and the padding
+// (0..pad-1) is kept in the low bits of the result: start = v & ~(pad-1), true length = next
+// start - start - (v & (pad-1)).
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t *data, uint32_t n, uint32_t *block_sums,
-                                                            int pad8) {
+                                                            uint32_t pad) {
     __shared__ uint32_t s_w[32];
     const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
     uint32_t v[4], odd[4], sum = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t c = (base + i < n) ? data[base + i] : 0;
-        odd[i] = pad8 ? ((8u - (c & 7u)) & 7u) : 0u;
+        odd[i] = pad ? ((pad - (c & (pad - 1u))) & (pad - 1u)) : 0u;
         v[i] = c + odd[i];
         sum += v[i];
     }
@@ -784,9 +895,39 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
     return (double)v.size() * (double)n_guides < 1.5e9;  // entries are addressed with 32 bits (12 GB)
 }
 
-// builds the guide-side seed index of this search in ds->d_bucket / ds->d_index
+// ---- bit-sliced copy of the index (join over the site table, core 10 / distal 10 only) ----------
+//
+// The popc compare costs ~8 issue slots per key (XOR, shift, OR/AND, POPC, min/compare, register
+// rotation) and the join is bound by exactly that.  Transposing the keys removes most of it: per
+// block of 32 keys the index holds 24 words -- bit j of word w belongs to key j: 10 words of the
+// distal hi plane, 10 of the lo plane, 4 of c' = core mismatches + 7 - total_max -- and a window
+// thread evaluates all 32 keys at once: 20 LOP3 give the 10 per-base mismatch words, an 18-LOP3
+// carry-save tree tells where d + c' reaches 8 (= no hit).  ~50 issue slots per 32 keys, no POPC.
+// Pad slots of a bucket's last block hold c' = 15 and never hit.
+
+__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint32_t *keys, uint32_t n_blocks, uint32_t *planes) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * 8u;
+    for (uint32_t blk = blockIdx.x * 8u + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
+        const uint32_t k = __ldg(&keys[(size_t)blk * 32 + lane]);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < kSliceWords; j++) {
+            const uint32_t w = __ballot_sync(kFull, (k >> j) & 1u);
+            if ((int)lane == j) mine = w;
+        }
+        if (lane < kSliceWords) planes[(size_t)blk * kSliceWords + lane] = mine;
+    }
+}
+
+static bool ot_sliced_applicable(const OtParams &op) {
+    return op.core_len == 10 && op.total_max >= 0 && op.total_max <= 7 && op.core_max <= 3 && !getenv("GUIDO_OT_NO_SLICED");
+}
+
+// builds the guide-side seed index of this search in ds->d_bucket / ds->d_index; with `sliced` the
+// keys are additionally transposed into 32-key bit-plane blocks (buckets padded to whole blocks)
 static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
-                             cudaStream_t stream, int *n_launches, OtIndex *out) {
+                             bool sliced, cudaStream_t stream, int *n_launches, OtIndex *out) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
         return GUIDO_ERR_ARG;
@@ -801,12 +942,16 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
-    // every bucket is padded to a multiple of 8 slots
-    const uint64_t n_slots = (n_entries + 7ull * n_buckets + 7) & ~(uint64_t)7;
-    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_slots * 8))) return rc;
+    // every bucket is padded to a multiple of 8 slots (32 when sliced); worst case allocated
+    const uint32_t pad = sliced ? 32u : 8u;
+    const uint64_t n_slots = (n_entries + (uint64_t)(pad - 1) * n_buckets + 31) & ~(uint64_t)31;
+    if (n_slots >= (1ull << 32)) { set_error("seed index too large"); return GUIDO_ERR_ARG; }
+    // d_index: [keys n_slots][ids n_slots][planes n_slots / 32 * 24 (sliced)]
+    const int64_t index_bytes = (int64_t)n_slots * 8 + (sliced ? (int64_t)(n_slots / 32) * kSliceWords * 4 : 0);
+    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, index_bytes))) return rc;
     uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
              *d_var = sums + n_scan_blocks;
-    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots;
+    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots, *planes = ids + n_slots;
     const int field = dl + op.core_max;  // <= 16, checked by ot_index_applicable
     GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
     // variants are tiny; a pageable async copy is staged by the driver before it returns
@@ -815,17 +960,21 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     ia.guides = d_guides; ia.n_guides = (uint32_t)n_guides; ia.variants = d_var; ia.n_variants = (uint32_t)variants.size();
     ia.key_lo = 0; ia.key_hi = n_buckets;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
+    ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
     const int bgrid = (int)std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)ds->sm_count * 32);
     idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
-    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 1);
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    // expected slots actually used (uniform keys: half a pad unit per bucket) -- sizes the passes
+    const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
+    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 4, stream));  // pads: c' = 15
     // The fill scatters 4-byte keys/ids all over a 350 MB index: done in one go every store dirties
     // its own 32-byte sector in DRAM (8x write amplification, 2.7 ms for 100 k guides).  Filling one
     // slice of the bucket range at a time keeps the slice L2-resident, so DRAM sees whole lines.
     {
         const uint64_t slice_bytes = 40ull << 20;
-        uint32_t passes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (n_slots * 8 + slice_bytes - 1) / slice_bytes));
+        uint32_t passes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (used_slots * 8 + slice_bytes - 1) / slice_bytes));
         for (uint32_t p = 0; p < passes; p++) {
             ia.key_lo = (uint32_t)((uint64_t)n_buckets * p / passes);
             ia.key_hi = (uint32_t)((uint64_t)n_buckets * (p + 1) / passes);
@@ -833,12 +982,19 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         }
         if (n_launches) *n_launches += (int)passes + 4;
     }
+    if (sliced) {
+        // all n_slots / 32 blocks are transposed (the tail beyond the last bucket is pad anyway)
+        const uint32_t n_blocks = (uint32_t)(n_slots / 32);
+        const int tgrid = (int)std::min<uint32_t>((n_blocks + 7) / 8, (uint32_t)ds->sm_count * 16);
+        idx_transpose_kernel<<<tgrid, 256, 0, stream>>>(keys, n_blocks, planes);
+        if (n_launches) *n_launches += 1;
+    }
     GUIDO_CUDA(cudaGetLastError());
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
     const int wide = force ? atoi(force) : 2;
-    *out = OtIndex{counts, keys, ids, cl, dl, field, wide};
+    *out = OtIndex{counts, keys, ids, cl, dl, field, wide, sliced ? (const uint4 *)planes : nullptr};
     return GUIDO_OK;
 }
 
@@ -848,7 +1004,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
                     cudaStream_t stream, int *n_launches) {
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
-    int rc = build_guide_index(ds, op, d_guides, n_guides, stream, n_launches, &a.ix);
+    int rc = build_guide_index(ds, op, d_guides, n_guides, false, stream, n_launches, &a.ix);
     if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
@@ -904,7 +1060,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     GUIDO_CUDA(cudaEventRecord(ds->ev[1], stream));
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0};
+    a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0, nullptr};
     a.guides = nullptr; a.n_guides = 0;
     a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr; a.site_count = ds->d_counts + 4;
     a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
@@ -948,7 +1104,8 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (!site_table_matches(ds, op)) { set_error("PAM-site table was not built for these parameters"); return GUIDO_ERR_ARG; }
     if (ds->site_n == 0) return GUIDO_OK;
     OtScanArgs a;
-    int rc = build_guide_index(ds, op, d_guides, n_guides, stream, n_launches, &a.ix);
+    const bool sliced = ot_sliced_applicable(op);
+    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, stream, n_launches, &a.ix);
     if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
@@ -957,12 +1114,14 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     a.tab_counts = a.tab_fill = nullptr; a.tab_n = (uint32_t)ds->site_n;
     a.first_block = 0; a.n_tiles = 0;
     int per_sm = 0;
-    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
+    if (sliced) GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_sliced_kernel, kThreads, 0));
+    else GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
     const uint32_t n_chunks = (a.tab_n + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
     int grid = ds->sm_count * std::max(per_sm, 1) * 4;  // 4 waves' worth of CTAs evens out the tail
     if ((uint32_t)grid > n_chunks) grid = (int)n_chunks;
     kev_begin(ds, stream);
-    ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+    if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
+    else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
     kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
     if (n_launches) *n_launches += 1;

@@ -46,6 +46,33 @@ int mark_hit_guides(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uin
     return GUIDO_OK;
 }
 
+// n x 20 letters -> n x {hi, lo} plane words; *bad = smallest (guide * 32 + position) holding a
+// letter outside A/C/G/T (left untouched when every letter is fine)
+__global__ void __launch_bounds__(256) encode_guides_kernel(const char *letters, uint32_t n, uint2 *out,
+                                                             unsigned long long *bad) {
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= n) return;
+    const char *p = letters + (size_t)g * kProto;
+    uint32_t hi = 0, lo = 0;
+#pragma unroll
+    for (int i = 0; i < kProto; i++) {
+        const uint32_t c = (uint32_t)(unsigned char)p[i] & 0xDFu;  // upper case
+        // A 0x41, C 0x43, G 0x47, T 0x54: hi plane = bit 2, lo plane = bit 1 ^ bit 2
+        if (c != 0x41 && c != 0x43 && c != 0x47 && c != 0x54) atomicMin(bad, (unsigned long long)g * 32ull + i);
+        hi |= ((c >> 2) & 1u) << i;
+        lo |= (((c >> 1) ^ (c >> 2)) & 1u) << i;
+    }
+    out[g] = make_uint2(hi, lo);
+}
+
+int encode_guides_device(DeviceState *ds, const char *d_letters, int64_t n, uint2 *d_out, unsigned long long *d_bad,
+                         cudaStream_t stream) {
+    if (n == 0) return GUIDO_OK;
+    encode_guides_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_letters, (uint32_t)n, d_out, d_bad);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
 // sort d_hits[0..n) in place; scratch comes from ds->d_out[1]
 int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t n_guides, cudaStream_t stream,
                      int *n_launches) {

@@ -252,3 +252,32 @@ def test_site_table_empty_and_tiny(native):
     img = native.Image.from_seqs([("c", "T" * 30 + "ACGTACGTACGTACGTACGTAGG" + "T" * 30)]).upload()
     hits, flags = img.offtarget_search(["ACGTACGTACGTACGTACGT", "GGGGGGGGGGCCCCCCCCCC"], algo=native.OT_TABLE)
     assert hits["guide"].tolist() == [0] and flags.tolist()[0] == 1
+
+
+def test_offtarget_guides_are_packed_on_the_device(native):
+    """letters travel as they are; packing and validation happen in a kernel"""
+    img = native.Image.from_seqs([("c", "T" * 30 + "ACGTACGTACGTACGTACGTAGG" + "T" * 30)]).upload()
+    with pytest.raises(ValueError, match=r"guide 1 holds a letter outside A/C/G/T at position 5"):
+        img.offtarget_search(["ACGTACGTACGTACGTACGT", "ACGTNCGTACGTACGTACGT"])
+    lower, _ = img.offtarget_search(["acgtacgtacgtacgtacgt"])
+    upper, _ = img.offtarget_search(["ACGTACGTACGTACGTACGT"])
+    assert len(upper) == 1 and np.array_equal(lower, upper)
+    enc = native.encode_guides(["ACGTACGTACGTACGTACGT"])
+    assert enc.tolist() == native.encode_guides(["acgtacgtacgtacgtacgt"]).tolist()
+
+
+@pytest.mark.parametrize("total", [0, 2, 4, 6, 8])
+@pytest.mark.parametrize("sliced", [True, False])
+def test_offtarget_join_variants(native, monkeypatch, total, sliced):
+    """the table join has a bit-sliced compare (core 10, total <= 7) and a popc compare: both must
+    give the brute-force hit list, whatever the mismatch budget"""
+    if not sliced:
+        monkeypatch.setenv("GUIDO_OT_NO_SLICED", "1")
+    contigs = util.synthetic_contigs(28, [180000, 20000], n_runs=3)
+    rng = np.random.default_rng(9)
+    protos = _protos_from_genome(rng, contigs, 400, mutate=5)
+    img = native.Image.from_seqs(contigs).upload()
+    kw = dict(core_length=10, core_mismatches=min(2, total), total_mismatches=total, want_raw_flags=False)
+    a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
+    b, _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)
+    assert len(a) > 0 and np.array_equal(a, b)
