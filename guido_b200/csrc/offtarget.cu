@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
                     const int kk = __ffs((int)r) - 1;
                     r &= r - 1;
                     guido_ot_hit h;
-                    h.guide = __ldg(&a.ix.guides[(size_t)(blk0 + b) * 32 + kk]);
+                    h.guide = __ldg(&reinterpret_cast<const uint2 *>(a.ix.keys)[(size_t)(blk0 + b) * 32 + kk]).y;
                     h.gpos = __ldg(&a.tab_q[i]); h.hi = A; h.lo = B;
                     push_hit(a, s_hits, h);
                 }
@@ -770,34 +770,48 @@ struct IdxArgs {
     uint32_t cbias;            // sliced: 7 - total_max, added to the variant's core mismatch count
 };
 
+// One warp per guide: the guide is read once, the lanes walk the variant list (staged in shared
+// memory) -- no per-entry division, and the scatter is the only memory traffic that matters.
+constexpr int kMaxVariants = 4096;  // core 12 / 3 mismatches: 6535 would not fit -> falls back to global reads
+
 template <bool kFill>
 __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
-    const unsigned long long total = (unsigned long long)a.n_guides * a.n_variants;
+    __shared__ uint32_t s_var[kMaxVariants];
+    const bool staged = a.n_variants <= (uint32_t)kMaxVariants;
+    if (staged)
+        for (uint32_t v = threadIdx.x; v < a.n_variants; v += 256) s_var[v] = __ldg(&a.variants[v]);
+    __syncthreads();
     const uint32_t cmask = (1u << a.cl) - 1, dmask = (1u << a.dl) - 1;
-    for (unsigned long long t = blockIdx.x * 256ull + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * 256ull) {
-        const uint32_t g = (uint32_t)(t / a.n_variants), v = (uint32_t)(t % a.n_variants);
+    const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * 8u;
+    uint2 *ent = reinterpret_cast<uint2 *>(a.keys);  // sliced staging: {key word, guide} per slot
+    for (uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5); g < a.n_guides; g += warps) {
         const uint2 G = __ldg(&a.guides[g]);
-        const uint32_t var = __ldg(&a.variants[v]);
-        const uint32_t xh = var & 0xffff, xl = var >> 16;
-        const uint32_t key = ((((G.x >> a.dl) & cmask) ^ xh) << a.cl) | (((G.y >> a.dl) & cmask) ^ xl);
-        if constexpr (kFill) { if (key < a.key_lo || key >= a.key_hi) continue; }
-        if constexpr (!kFill) {
-            atomicAdd(&a.counts[key], 1u);
-        } else {
-            // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
-            const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
-            const uint32_t cmm = (uint32_t)__popc(xh | xl);
-            if (a.sliced) {
-                // staging word of the bit-sliced index: distal hi plane, distal lo plane, then the
-                // biased core mismatch count c' = c + 7 - total_max (a hit is d + c' <= 7)
-                a.keys[pos] = (G.x & dmask) | ((G.y & dmask) << a.dl) | ((cmm + a.cbias) << (2 * a.dl));
+        const uint32_t ch = (G.x >> a.dl) & cmask, cl_ = (G.y >> a.dl) & cmask;
+        const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
+        for (uint32_t v = lane; v < a.n_variants; v += 32) {
+            const uint32_t var = staged ? s_var[v] : __ldg(&a.variants[v]);
+            const uint32_t xh = var & 0xffff, xl = var >> 16;
+            const uint32_t key = ((ch ^ xh) << a.cl) | (cl_ ^ xl);
+            if constexpr (!kFill) {
+                atomicAdd(&a.counts[key], 1u);
             } else {
-                // key = distal planes in two fields of `field` bits; the core mismatches of this
-                // variant are appended to the hi field as that many 1-bits, which the window's zeros
-                // turn into mismatches -- so popc of the folded XOR is the TOTAL mismatch count
-                a.keys[pos] = (G.x & dmask) | (((1u << cmm) - 1u) << a.dl) | ((G.y & dmask) << a.field);
+                if (key < a.key_lo || key >= a.key_hi) continue;
+                // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
+                const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
+                const uint32_t cmm = (uint32_t)__popc(xh | xl);
+                if (a.sliced) {
+                    // staging word of the bit-sliced index: distal hi plane, distal lo plane, then the
+                    // biased core mismatch count c' = c + 7 - total_max (a hit is d + c' <= 7);
+                    // one 8-byte store per entry
+                    ent[pos] = make_uint2(dh | (dlo << a.dl) | ((cmm + a.cbias) << (2 * a.dl)), g);
+                } else {
+                    // key = distal planes in two fields of `field` bits; the core mismatches of this
+                    // variant are appended to the hi field as that many 1-bits, which the window's
+                    // zeros turn into mismatches -- popc of the folded XOR is the TOTAL mismatch count
+                    a.keys[pos] = dh | (((1u << cmm) - 1u) << a.dl) | (dlo << a.field);
+                    a.ids[pos] = g;
+                }
             }
-            a.ids[pos] = g;
         }
     }
 }
@@ -905,11 +919,12 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 // carry-save tree tells where d + c' reaches 8 (= no hit).  ~50 issue slots per 32 keys, no POPC.
 // Pad slots of a bucket's last block hold c' = 15 and never hit.
 
-__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint32_t *keys, uint32_t n_blocks, uint32_t *planes) {
+__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *slots_used, uint32_t *planes) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * 8u;
+    const uint32_t n_blocks = (__ldg(slots_used) & ~31u) >> 5;  // offsets[n_buckets]: end of the last bucket
     for (uint32_t blk = blockIdx.x * 8u + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
-        const uint32_t k = __ldg(&keys[(size_t)blk * 32 + lane]);
+        const uint32_t k = __ldg(&ent[(size_t)blk * 32 + lane]).x;
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < kSliceWords; j++) {
@@ -920,8 +935,15 @@ __global__ void __launch_bounds__(256) idx_transpose_kernel(const uint32_t *keys
     }
 }
 
-static bool ot_sliced_applicable(const OtParams &op) {
-    return op.core_len == 10 && op.total_max >= 0 && op.total_max <= 7 && op.core_max <= 3 && !getenv("GUIDO_OT_NO_SLICED");
+// Worth it when buckets hold at least half a block on average: below that the padding to whole
+// 32-key blocks (memset, transpose, compare) costs more than the popc walk over 8-key sectors.
+// GUIDO_OT_SLICED=0/1 forces the choice (tests, tuning).
+static bool ot_sliced_applicable(const OtParams &op, int64_t n_guides) {
+    if (op.core_len != 10 || op.total_max < 0 || op.total_max > 7 || op.core_max > 3) return false;
+    if (const char *f = getenv("GUIDO_OT_SLICED")) return atoi(f) != 0;
+    std::vector<uint32_t> v;
+    enumerate_variants(op.core_len, op.core_max, &v);
+    return (double)v.size() * (double)n_guides >= 16.0 * (double)(1u << (2 * op.core_len));
 }
 
 // builds the guide-side seed index of this search in ds->d_bucket / ds->d_index; with `sliced` the
@@ -961,14 +983,14 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     ia.key_lo = 0; ia.key_hi = n_buckets;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
-    const int bgrid = (int)std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)ds->sm_count * 32);
+    const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
     idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
     // expected slots actually used (uniform keys: half a pad unit per bucket) -- sizes the passes
     const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
-    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 4, stream));  // pads: c' = 15
+    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 8, stream));  // pads: c' = 15
     // The fill scatters 4-byte keys/ids all over a 350 MB index: done in one go every store dirties
     // its own 32-byte sector in DRAM (8x write amplification, 2.7 ms for 100 k guides).  Filling one
     // slice of the bucket range at a time keeps the slice L2-resident, so DRAM sees whole lines.
@@ -983,10 +1005,10 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         if (n_launches) *n_launches += (int)passes + 4;
     }
     if (sliced) {
-        // all n_slots / 32 blocks are transposed (the tail beyond the last bucket is pad anyway)
+        // blocks up to the end of the last bucket (read from the scanned offsets on the device)
         const uint32_t n_blocks = (uint32_t)(n_slots / 32);
         const int tgrid = (int)std::min<uint32_t>((n_blocks + 7) / 8, (uint32_t)ds->sm_count * 16);
-        idx_transpose_kernel<<<tgrid, 256, 0, stream>>>(keys, n_blocks, planes);
+        idx_transpose_kernel<<<tgrid, 256, 0, stream>>>((const uint2 *)keys, counts + n_buckets, planes);
         if (n_launches) *n_launches += 1;
     }
     GUIDO_CUDA(cudaGetLastError());
@@ -1104,7 +1126,7 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (!site_table_matches(ds, op)) { set_error("PAM-site table was not built for these parameters"); return GUIDO_ERR_ARG; }
     if (ds->site_n == 0) return GUIDO_OK;
     OtScanArgs a;
-    const bool sliced = ot_sliced_applicable(op);
+    const bool sliced = ot_sliced_applicable(op, n_guides);
     int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, stream, n_launches, &a.ix);
     if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
