@@ -439,18 +439,21 @@ def main():
         gps = args.guides / (r["ms_per_step"] * 1e-3)
         use_index = algo != N.OT_SCAN
         use_table = r["table"] is not None
-        kernel = "ot_join_kernel" if use_table else "ot_kernel<index>" if use_index else "ot_kernel<scan>"
+        # the join compares bit-sliced (32 keys per LOP3 lane) once buckets hold >= 16 keys on average
+        sliced = use_table and 436 * args.guides >= 16 * 4 ** OT_KW["core_length"]
+        kernel = ("ot_join_sliced_kernel" if sliced else "ot_join_kernel" if use_table else
+                  "ot_kernel<index>" if use_index else "ot_kernel<scan>")
         algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
                      "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
         alg_desc = ("per GPU: 8 B per window of the site table + 4 B per index key and bucket offset (each once) + "
-                    "24 B per hit; the compare itself is POPC-pipe bound, see int_pipe" if use_table else
+                    "24 B per hit; the compare itself is integer-pipe bound, see int_pipe" if use_table else
                     "per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
                     "key compared + 16 B per hit" if use_index else
                     "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
                     "integer-issue bound, see int_pipe)")
         out.update({
             "value": gps, "unit": "guides/s", "ms_per_step": r["ms_per_step"],
-            "dtype": "u32 bit planes (XOR/OR + popc)", "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "dtype": "u32 bit planes (bit-sliced LOP3 carry-save count)" if sliced else "u32 bit planes (XOR/OR + popc)", "gpu_launches": r["launches"], "clocks": r["clocks"],
             "config": {"workload": f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
                                    + (" (BASELINE configs[3] on N GPUs)" if args.genome == "human" else " (BASELINE configs[2])"),
                        "pam": PAM, "algo": algo_desc,
@@ -467,12 +470,21 @@ def main():
                          "kernel": kernel, "kernel_ms": r["kernel_ms"], "algorithmic_bytes": alg_desc},
         })
         if use_index and r["visited"]:
-            # the index kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
             sm_mhz = (r["clocks"] or {}).get("sm_mhz") or 1965.0
             per_gpu = r["visited"] / world / (r["kernel_ms"] * 1e-3)
-            out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),
-                               "popc_peak_per_clk_per_sm": 16, "sm_mhz": sm_mhz,
-                               "note": "XOR, fold (SHF+LOP3), POPC, ISETP per key; padding keys of the 8-key sectors not counted"}
+            if sliced:
+                # 38 LOP3 per block of 32 keys on the ALU pipe (64 lanes/clk/SM = 2 warp-instr/clk/SM);
+                # blocks are counted from the true keys (the pad slots of each bucket's last block ride along)
+                out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "lop3_per_32_keys": 38,
+                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 38 / 148 / (sm_mhz * 1e6),
+                                   "alu_peak_warp_instr_per_clk_per_sm": 2, "sm_mhz": sm_mhz,
+                                   "note": "20 LOP3 mismatch words + 18 LOP3 carry-save count per 32 keys, no POPC; "
+                                           "ncu: ALU pipe ~70 % busy overall (profiles/)"}
+            else:
+                # the popc kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
+                out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),
+                                   "popc_peak_per_clk_per_sm": 16, "sm_mhz": sm_mhz,
+                                   "note": "XOR, fold (SHF+LOP3), POPC, ISETP per key; padding keys of the 8-key sectors not counted"}
         if not use_index and r["pairs_scan"]:
             out["int_pipe"] = {"pairs_per_s_per_gpu": r["pairs_scan"] / (r["kernel_ms"] * 1e-3), "ops_per_pair": 4,
                                "note": "2 LOP3 + POPC + ISETP per (window, guide) pair"}

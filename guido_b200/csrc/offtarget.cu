@@ -605,42 +605,100 @@ __device__ __forceinline__ uint32_t sliced_block_hits(const uint4 *__restrict__ 
 
 constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
 
+__device__ __forceinline__ void cp_async4(const uint32_t *smem_dst, const uint32_t *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+
+// The join is a chain of dependent loads per window -- table entry (DRAM, streamed), bucket offsets
+// (L2), key planes (DRAM the first time a bucket is touched) -- and with ~50 issue slots of work
+// per 32 keys the loads, not the compare, set the pace.  So the chain is pulled one chunk ahead:
+// while a CTA works on chunk c its threads' table entries of chunk c+1 arrive through cp.async,
+// half-way through the chunk their bucket ranges are looked up and the first plane blocks are
+// prefetched into L2; by the time chunk c+1 starts everything it needs is on chip.  A thread only
+// ever reads the shared-memory words it wrote itself, so the stages need no CTA barrier.
 __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtScanArgs a) {
+    constexpr uint32_t kChunk = kJoinPerThread * kThreads;
     __shared__ HitBuf s_hits;
+    __shared__ uint32_t sA[2][kChunk], sB[2][kChunk], sStart[2][kChunk], sLen[2][kChunk];
     if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
     __syncthreads();
-    constexpr uint32_t kChunk = kJoinPerThread * kThreads;
     const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
     const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
     const uint4 *__restrict__ planes = a.ix.planes;
+    const uint2 *__restrict__ entries = reinterpret_cast<const uint2 *>(a.ix.keys);
     unsigned long long visited = 0;
-    for (uint32_t c = c0; c < c1; c++) {
-        for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t i = c * kChunk + k * kThreads + threadIdx.x;
-            if (i >= a.tab_n) continue;
-            const uint32_t A = __ldg(&a.tab_a[i]), B = __ldg(&a.tab_b[i]);
-            const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
-            const uint32_t v = __ldg(&a.ix.offsets[key]), w = __ldg(&a.ix.offsets[key + 1]);
-            const uint32_t start = v & ~31u, len = (w & ~31u) - start - (v & 31u);
-            if (len == 0) continue;
-            visited += len;
-            uint32_t wh[10], wl[10];
+
+    auto fetch = [&](uint32_t c, int buf) {  // this thread's table entries of chunk c -> shared memory
 #pragma unroll
-            for (int j = 0; j < 10; j++) { wh[j] = bit_mask(A, j); wl[j] = bit_mask(B, j); }
-            const uint32_t blk0 = start >> 5, n_blk = (len + 31) >> 5;
-            for (uint32_t b = 0; b < n_blk; b++) {
-                uint32_t r = sliced_block_hits(planes + (size_t)(blk0 + b) * (kSliceWords / 4), wh, wl);
-                while (r) {  // rare: 1.4 % of (window, block) pairs
-                    const int kk = __ffs((int)r) - 1;
-                    r &= r - 1;
-                    guido_ot_hit h;
-                    h.guide = __ldg(&reinterpret_cast<const uint2 *>(a.ix.keys)[(size_t)(blk0 + b) * 32 + kk]).y;
-                    h.gpos = __ldg(&a.tab_q[i]); h.hi = A; h.lo = B;
-                    push_hit(a, s_hits, h);
-                }
+        for (uint32_t k = 0; k < kJoinPerThread; k++) {
+            const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
+            if (i < a.tab_n) { cp_async4(&sA[buf][idx], a.tab_a + i); cp_async4(&sB[buf][idx], a.tab_b + i); }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    auto resolve = [&](uint32_t c, int buf) {  // bucket ranges of those entries; planes towards L2
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        uint32_t v[kJoinPerThread], w[kJoinPerThread];
+#pragma unroll
+        for (uint32_t k = 0; k < kJoinPerThread; k++) {
+            const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
+            v[k] = w[k] = 0;
+            if (i < a.tab_n) {
+                const uint32_t A = sA[buf][idx], B = sB[buf][idx];
+                const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
+                v[k] = __ldg(&a.ix.offsets[key]); w[k] = __ldg(&a.ix.offsets[key + 1]);
             }
         }
+#pragma unroll
+        for (uint32_t k = 0; k < kJoinPerThread; k++) {
+            const uint32_t idx = k * kThreads + threadIdx.x;
+            const uint32_t start = v[k] & ~31u, len = (w[k] & ~31u) - start - (v[k] & 31u);
+            sStart[buf][idx] = start; sLen[buf][idx] = len;
+            const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
+            for (uint32_t o = 0; o < ((len + 31) >> 5) * (kSliceWords * 4); o += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        }
+    };
+    auto process = [&](uint32_t c, int buf, uint32_t k) {
+        const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
+        if (i >= a.tab_n) return;
+        const uint32_t len = sLen[buf][idx];
+        if (len == 0) return;
+        const uint32_t A = sA[buf][idx], B = sB[buf][idx];
+        visited += len;
+        uint32_t wh[10], wl[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            wh[j] = bit_mask(A, j); wl[j] = bit_mask(B, j);
+            // opaque to the compiler: keeps the masks in registers instead of re-deriving all 20 of
+            // them (2 issue slots each) in every iteration of the block loop
+            asm volatile("" : "+r"(wh[j]), "+r"(wl[j]));
+        }
+        const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
+        for (uint32_t b = 0; b < n_blk; b++) {
+            uint32_t r = sliced_block_hits(planes + (size_t)(blk0 + b) * (kSliceWords / 4), wh, wl);
+            while (r) {  // rare: 1.4 % of (window, block) pairs
+                const int kk = __ffs((int)r) - 1;
+                r &= r - 1;
+                guido_ot_hit h;
+                h.guide = __ldg(&entries[(size_t)(blk0 + b) * 32 + kk]).y;
+                h.gpos = __ldg(&a.tab_q[i]); h.hi = A; h.lo = B;
+                push_hit(a, s_hits, h);
+            }
+        }
+    };
+
+    if (c0 < c1) { fetch(c0, 0); resolve(c0, 0); }
+    for (uint32_t c = c0; c < c1; c++) {
+        const int buf = (int)((c - c0) & 1u);
+        const bool more = c + 1 < c1;
+        if (more) fetch(c + 1, buf ^ 1);
+        process(c, buf, 0);
+        process(c, buf, 1);
+        if (more) resolve(c + 1, buf ^ 1);
+        process(c, buf, 2);
+        process(c, buf, 3);
         __syncthreads();
         flush_hits(a, s_hits, false);
     }
@@ -654,6 +712,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         atomicAdd(a.site_count + 1, s_hits.visited);
     }
 }
+static_assert(kJoinPerThread == 4, "the stage schedule of ot_join_sliced_kernel is written for 4 windows per thread");
 
 template <int kMode>
 static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream) {
@@ -920,18 +979,25 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 // Pad slots of a bucket's last block hold c' = 15 and never hit.
 
 __global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *slots_used, uint32_t *planes) {
+    constexpr int U = 4;  // blocks per warp iteration: independent loads in flight
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * 8u;
     const uint32_t n_blocks = (__ldg(slots_used) & ~31u) >> 5;  // offsets[n_buckets]: end of the last bucket
-    for (uint32_t blk = blockIdx.x * 8u + (threadIdx.x >> 5); blk < n_blocks; blk += warps) {
-        const uint32_t k = __ldg(&ent[(size_t)blk * 32 + lane]).x;
-        uint32_t mine = 0;
+    for (uint32_t blk = (blockIdx.x * 8u + (threadIdx.x >> 5)) * U; blk < n_blocks; blk += warps * U) {
+        uint32_t k[U];
 #pragma unroll
-        for (int j = 0; j < kSliceWords; j++) {
-            const uint32_t w = __ballot_sync(kFull, (k >> j) & 1u);
-            if ((int)lane == j) mine = w;
+        for (int u = 0; u < U; u++) k[u] = blk + u < n_blocks ? __ldg(&ent[(size_t)(blk + u) * 32 + lane]).x : 0u;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (blk + u >= n_blocks) break;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < kSliceWords; j++) {
+                const uint32_t w = __ballot_sync(kFull, (k[u] >> j) & 1u);
+                if ((int)lane == j) mine = w;
+            }
+            if (lane < kSliceWords) planes[(size_t)(blk + u) * kSliceWords + lane] = mine;
         }
-        if (lane < kSliceWords) planes[(size_t)blk * kSliceWords + lane] = mine;
     }
 }
 
@@ -995,7 +1061,8 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     // its own 32-byte sector in DRAM (8x write amplification, 2.7 ms for 100 k guides).  Filling one
     // slice of the bucket range at a time keeps the slice L2-resident, so DRAM sees whole lines.
     {
-        const uint64_t slice_bytes = 40ull << 20;
+        const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
+        const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
         uint32_t passes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (used_slots * 8 + slice_bytes - 1) / slice_bytes));
         for (uint32_t p = 0; p < passes; p++) {
             ia.key_lo = (uint32_t)((uint64_t)n_buckets * p / passes);
@@ -1007,7 +1074,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     if (sliced) {
         // blocks up to the end of the last bucket (read from the scanned offsets on the device)
         const uint32_t n_blocks = (uint32_t)(n_slots / 32);
-        const int tgrid = (int)std::min<uint32_t>((n_blocks + 7) / 8, (uint32_t)ds->sm_count * 16);
+        const int tgrid = (int)std::min<uint32_t>((n_blocks + 31) / 32, (uint32_t)ds->sm_count * 8);
         idx_transpose_kernel<<<tgrid, 256, 0, stream>>>((const uint2 *)keys, counts + n_buckets, planes);
         if (n_launches) *n_launches += 1;
     }
