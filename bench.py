@@ -476,7 +476,7 @@ def main():
                 # 38 LOP3 per block of 32 keys on the ALU pipe (64 lanes/clk/SM = 2 warp-instr/clk/SM);
                 # blocks are counted from the true keys (the pad slots of each bucket's last block ride along)
                 out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "lop3_per_32_keys": 38,
-                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 38 / 148 / (sm_mhz * 1e6),
+                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 38 / 32 / 148 / (sm_mhz * 1e6),
                                    "alu_peak_warp_instr_per_clk_per_sm": 2, "sm_mhz": sm_mhz,
                                    "note": "20 LOP3 mismatch words + 18 LOP3 carry-save count per 32 keys, no POPC; "
                                            "ncu: ALU pipe ~70 % busy overall (profiles/)"}
