@@ -978,25 +978,30 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 // carry-save tree tells where d + c' reaches 8 (= no hit).  ~50 issue slots per 32 keys, no POPC.
 // Pad slots of a bucket's last block hold c' = 15 and never hit.
 
+// One warp per block of 32 staged keys: lane k loads key k, a 5-stage butterfly (shuffle + masked
+// merge, the recursive 2x2 block transpose of a 32x32 bit matrix) leaves lane j with word j -- bit
+// k of it is bit j of key k -- and lanes 0..23 store the block's 96 bytes.
 __global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *slots_used, uint32_t *planes) {
     constexpr int U = 4;  // blocks per warp iteration: independent loads in flight
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * 8u;
     const uint32_t n_blocks = (__ldg(slots_used) & ~31u) >> 5;  // offsets[n_buckets]: end of the last bucket
     for (uint32_t blk = (blockIdx.x * 8u + (threadIdx.x >> 5)) * U; blk < n_blocks; blk += warps * U) {
-        uint32_t k[U];
+        uint32_t x[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) k[u] = blk + u < n_blocks ? __ldg(&ent[(size_t)(blk + u) * 32 + lane]).x : 0u;
+        for (int u = 0; u < U; u++) x[u] = blk + u < n_blocks ? __ldg(&ent[(size_t)(blk + u) * 32 + lane]).x : 0u;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (blk + u >= n_blocks) break;
-            uint32_t mine = 0;
+            uint32_t m = 0x0000ffffu;
 #pragma unroll
-            for (int j = 0; j < kSliceWords; j++) {
-                const uint32_t w = __ballot_sync(kFull, (k[u] >> j) & 1u);
-                if ((int)lane == j) mine = w;
+            for (int j = 16; j; j >>= 1) {
+                const uint32_t y = __shfl_xor_sync(kFull, x[u], j);
+                // rows without bit j keep their low columns and take the partner's low columns as
+                // their high ones; rows with bit j do the opposite
+                x[u] = (lane & j) ? ((x[u] & ~m) | ((y & ~m) >> j)) : ((x[u] & m) | ((y & m) << j));
+                m ^= m << (j >> 1);
             }
-            if (lane < kSliceWords) planes[(size_t)(blk + u) * kSliceWords + lane] = mine;
+            if (blk + u < n_blocks && lane < kSliceWords) planes[(size_t)(blk + u) * kSliceWords + lane] = x[u];
         }
     }
 }
