@@ -605,6 +605,49 @@ __device__ __forceinline__ uint32_t sliced_block_hits(const uint4 *__restrict__ 
 
 constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
 
+// Hits of the sliced join are parked as (table row, index slot) pairs -- two words, no loads in the
+// divergent hit path -- and turned into records (guide id, position, planes: four scattered
+// loads) by the whole CTA when the queue is flushed.
+constexpr int kHitQueue = 768;
+struct HitQueue {
+    uint32_t n;
+    unsigned long long base;
+    unsigned long long visited;
+    uint2 q[kHitQueue];
+};
+
+__device__ __forceinline__ guido_ot_hit resolve_hit(const OtScanArgs &a, uint32_t row, uint32_t slot) {
+    guido_ot_hit h;
+    h.guide = __ldg(&reinterpret_cast<const uint2 *>(a.ix.keys)[slot]).y;
+    h.gpos = __ldg(&a.tab_q[row]); h.hi = __ldg(&a.tab_a[row]); h.lo = __ldg(&a.tab_b[row]);
+    return h;
+}
+
+__device__ __forceinline__ void queue_hit(const OtScanArgs &a, HitQueue &hq, uint32_t row, uint32_t slot) {
+    const uint32_t i = atomicAdd(&hq.n, 1u);
+    if (i < kHitQueue) {
+        hq.q[i] = make_uint2(row, slot);
+    } else {  // queue full until the next flush: straight to the global list
+        unsigned long long dst = atomicAdd(a.count, 1ull);
+        if (dst < a.cap) a.hits[dst] = resolve_hit(a, row, slot);
+    }
+}
+
+// whole CTA, after a barrier that ends the queueing phase
+__device__ __forceinline__ void flush_queue(const OtScanArgs &a, HitQueue &hq, bool force) {
+    const uint32_t n = min(hq.n, (uint32_t)kHitQueue);
+    __syncthreads();  // everybody has looked at the fill level before anybody queues another hit
+    if (n == 0 || (!force && n < kHitQueue / 2)) return;
+    if (threadIdx.x == 0) hq.base = atomicAdd(a.count, (unsigned long long)n);
+    __syncthreads();
+    const unsigned long long base = hq.base;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads)
+        if (base + i < a.cap) a.hits[base + i] = resolve_hit(a, hq.q[i].x, hq.q[i].y);
+    __syncthreads();
+    if (threadIdx.x == 0) hq.n = 0;
+    __syncthreads();
+}
+
 __device__ __forceinline__ void cp_async4(const uint32_t *smem_dst, const uint32_t *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
@@ -618,7 +661,7 @@ __device__ __forceinline__ void cp_async4(const uint32_t *smem_dst, const uint32
 // ever reads the shared-memory words it wrote itself, so the stages need no CTA barrier.
 __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtScanArgs a) {
     constexpr uint32_t kChunk = kJoinPerThread * kThreads;
-    __shared__ HitBuf s_hits;
+    __shared__ HitQueue s_hits;
     __shared__ uint32_t sA[2][kChunk], sB[2][kChunk], sStart[2][kChunk], sLen[2][kChunk];
     if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
     __syncthreads();
@@ -626,14 +669,16 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
     const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
     const uint4 *__restrict__ planes = a.ix.planes;
-    const uint2 *__restrict__ entries = reinterpret_cast<const uint2 *>(a.ix.keys);
     unsigned long long visited = 0;
 
+    // (the table arrays are allocated with a chunk of slack, so the last chunk reads past tab_n
+    // without a bounds check per row; such rows get an empty bucket range below)
     auto fetch = [&](uint32_t c, int buf) {  // this thread's table entries of chunk c -> shared memory
+        const uint32_t *ga = a.tab_a + (size_t)c * kChunk + threadIdx.x, *gb = a.tab_b + (size_t)c * kChunk + threadIdx.x;
 #pragma unroll
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
-            if (i < a.tab_n) { cp_async4(&sA[buf][idx], a.tab_a + i); cp_async4(&sB[buf][idx], a.tab_b + i); }
+            cp_async4(&sA[buf][k * kThreads + threadIdx.x], ga + k * kThreads);
+            cp_async4(&sB[buf][k * kThreads + threadIdx.x], gb + k * kThreads);
         }
         asm volatile("cp.async.commit_group;");
     };
@@ -642,29 +687,28 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         uint32_t v[kJoinPerThread], w[kJoinPerThread];
 #pragma unroll
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
-            v[k] = w[k] = 0;
-            if (i < a.tab_n) {
-                const uint32_t A = sA[buf][idx], B = sB[buf][idx];
-                const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
-                v[k] = __ldg(&a.ix.offsets[key]); w[k] = __ldg(&a.ix.offsets[key + 1]);
-            }
+            const uint32_t idx = k * kThreads + threadIdx.x;
+            const uint32_t A = sA[buf][idx], B = sB[buf][idx];
+            const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
+            v[k] = __ldg(&a.ix.offsets[key]); w[k] = __ldg(&a.ix.offsets[key + 1]);
         }
 #pragma unroll
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
             const uint32_t idx = k * kThreads + threadIdx.x;
-            const uint32_t start = v[k] & ~31u, len = (w[k] & ~31u) - start - (v[k] & 31u);
+            const uint32_t start = v[k] & ~31u;
+            const uint32_t len = c * kChunk + idx < a.tab_n ? (w[k] & ~31u) - start - (v[k] & 31u) : 0u;
             sStart[buf][idx] = start; sLen[buf][idx] = len;
-            const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
-            for (uint32_t o = 0; o < ((len + 31) >> 5) * (kSliceWords * 4); o += 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            if (len) {  // the first two lines of the bucket's planes (one or two 96-byte blocks)
+                const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            }
         }
     };
     auto process = [&](uint32_t c, int buf, uint32_t k) {
         const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
-        if (i >= a.tab_n) return;
         const uint32_t len = sLen[buf][idx];
-        if (len == 0) return;
+        if (len == 0) return;  // empty bucket, or a row past the end of the table
         const uint32_t A = sA[buf][idx], B = sB[buf][idx];
         visited += len;
         uint32_t wh[10], wl[10];
@@ -681,10 +725,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
             while (r) {  // rare: 1.4 % of (window, block) pairs
                 const int kk = __ffs((int)r) - 1;
                 r &= r - 1;
-                guido_ot_hit h;
-                h.guide = __ldg(&entries[(size_t)(blk0 + b) * 32 + kk]).y;
-                h.gpos = __ldg(&a.tab_q[i]); h.hi = A; h.lo = B;
-                push_hit(a, s_hits, h);
+                queue_hit(a, s_hits, i, (blk0 + b) * 32 + (uint32_t)kk);
             }
         }
     };
@@ -700,13 +741,13 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         process(c, buf, 2);
         process(c, buf, 3);
         __syncthreads();
-        flush_hits(a, s_hits, false);
+        flush_queue(a, s_hits, false);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(&s_hits.visited, visited);
     __syncthreads();
-    flush_hits(a, s_hits, true);
+    flush_queue(a, s_hits, true);
     if (threadIdx.x == 0 && a.site_count) {
         if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)a.tab_n);
         atomicAdd(a.site_count + 1, s_hits.visited);
