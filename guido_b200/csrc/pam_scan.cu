@@ -283,6 +283,29 @@ __device__ __forceinline__ uint32_t emit_word(uint32_t m, uint32_t base, uint32_
     return next;
 }
 
+// The same into the shared-memory stage, with the four straight-line stores written as predicated
+// stores by hand: left to itself the compiler wraps each of them in a divergence region
+// (BSSY / BRA / BSYNC), which triples the instruction count of the emission.
+__device__ __forceinline__ uint32_t emit_word_staged(uint32_t m, uint32_t base, uint32_t stage_addr, uint32_t off) {
+    uint32_t addr = stage_addr + 4u * off;  // shared-window byte address of the word's first slot
+    const uint32_t next = off + __popc(m);
+    const uint32_t b1 = base - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t pos = b1 + __ffs(m);
+        asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u32 [%1], %2; }"
+                     ::"r"(m), "r"(addr + 4u * k), "r"(pos) : "memory");
+        m &= m - 1;  // 0 stays 0
+    }
+    addr += 16;
+    while (m) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(b1 + __ffs(m)) : "memory");
+        addr += 4;
+        m &= m - 1;
+    }
+    return next;
+}
+
 // staged hits [a0, a0+n) of s -> g[a0 .. a0+n); s and g agree modulo 16 bytes, so whole uint4s
 // move in the middle and at most 3 scalars at either end
 __device__ __forceinline__ void copy_out(const uint32_t *s, uint32_t a0, uint32_t n, uint32_t *g, int vec_ok) {
@@ -304,6 +327,8 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
     __shared__ unsigned long long s_warp[kThreads / 32], s_part[kThreads / 32];
     __shared__ __align__(16) uint32_t s_stage[2][kStage + 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sa_f = (uint32_t)__cvta_generic_to_shared(s_stage[0]);
+    const uint32_t sa_r = (uint32_t)__cvta_generic_to_shared(s_stage[1]);
     // running output offsets of the current tile = counts of all tiles before it
     unsigned long long ef = 0, er = 0;
     uint32_t summed = 0;  // tiles [0, summed) are in (ef, er)
@@ -355,14 +380,14 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
         const bool stage_f = agg_f <= kStage, stage_r = agg_r <= kStage;
         if (stage_f) {
 #pragma unroll
-            for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, s_stage[0], of);
+            for (int w = 0; w < kWpt; w++) of = emit_word_staged(hf[w], base + 32 * w, sa_f, of);
         } else if (fits_f) {  // unusually dense tile: straight from registers to HBM
 #pragma unroll
             for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, a.out_fw + ef - pf, of);
         }
         if (stage_r) {
 #pragma unroll
-            for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, s_stage[1], orv);
+            for (int w = 0; w < kWpt; w++) orv = emit_word_staged(hr[w], base + 32 * w, sa_r, orv);
         } else if (fits_r) {
 #pragma unroll
             for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, a.out_rv + er - pr, orv);
