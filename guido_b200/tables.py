@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _native
 from .guides import Guide, guide_geometry
-from .helpers import rev_comp_fast
+from .helpers import load_cfd_scoring_matrix, rev_comp, rev_comp_fast
 from .off_targets import decode_hits
 
 _WEIGHTS = np.array([10, 5, 4, 3, 1], dtype=np.int64)  # calculate_ot_sum_score, off_targets.py:9-18
@@ -126,6 +126,7 @@ class OffTargetTable:
         self.n_mismatches = n_mm[keep]          # len(record["mismatches"]) incl. the PAM's N
         self.has_key = np.asarray(raw_flags, bool) if raw_flags is not None else None
         self.n_guides = len(protos_u8)
+        self._protos = np.ascontiguousarray(protos_u8, dtype=np.uint8)
 
     def __len__(self):
         return len(self.guide)
@@ -140,6 +141,57 @@ class OffTargetTable:
         m = np.zeros((self.n_guides, 5), np.int64)
         np.add.at(m, (self.guide, np.clip(self.n_mismatches - 1, 0, 4)), 1)
         return m
+
+    def cfd_scores(self, guide_pams=None, mm_scores=None, pam_scores=None):
+        """CFD score of every hit (``calculate_cfd_score``, off_targets.py:31-61), vectorised.
+
+        The reference multiplies, position by position, the mismatch factors of the 20 protospacer
+        positions and then the factor of the GUIDE's own PAM dinucleotide, in float64.  Here the
+        same factors are taken from a (20, 4, 4) table (1.0 where the bases agree -- multiplying
+        by 1.0 is exact) and multiplied column by column in the same order, so every score is
+        bit-identical.  ``guide_pams``: the guides' own PAM strings (default: ``pam`` for every
+        guide, which needs a PAM whose last two letters are A/C/G/T).
+        """
+        if mm_scores is None or pam_scores is None:
+            mm_scores, pam_scores = load_cfd_scoring_matrix()
+        factor = np.ones((20, 4, 4), dtype=np.float64)     # [position, guide base, off-target base]
+        for i in range(20):
+            for a, wt in enumerate("ACGU"):
+                for b, base in enumerate("ACGU"):
+                    if wt != base:
+                        factor[i, a, b] = mm_scores["r" + wt + ":d" + rev_comp(base, rna=True) + "," + str(i + 1)]
+        code = np.zeros(256, np.intp)
+        for k, c in enumerate(b"ACGT"):
+            code[c] = k
+        wt = code[self._protos[self.guide]]                  # (n, 20)
+        ot = code[self.letters[:, :20]]
+        score = np.ones(len(self), dtype=np.float64)
+        for i in range(20):
+            score = score * factor[i, wt[:, i], ot[:, i]]
+        if guide_pams is None:
+            pam_factor = np.full(self.n_guides, pam_scores[self.pam[1:]], dtype=np.float64)
+        else:
+            pam_factor = np.array([pam_scores[p[1:]] for p in guide_pams], dtype=np.float64)
+        return score * pam_factor[self.guide]
+
+    def cfd_layers(self, guide_pams=None):
+        """per-guide (mean, max, sum) of the CFD scores -- the ``ot_cfd_score_*`` layers of
+        ``Locus.find_off_targets`` (NaN for guides without a hit).  Sums run left to right over a
+        guide's hits; numpy's pairwise ``sum()`` in the reference can differ in the last ulp."""
+        cfd = self.cfd_scores(guide_pams)
+        order = np.argsort(self.guide, kind="stable")
+        g, c = self.guide[order], cfd[order]
+        n = np.bincount(g, minlength=self.n_guides)
+        total = np.zeros(self.n_guides, np.float64)
+        best = np.full(self.n_guides, np.nan)
+        if len(c):
+            starts = np.concatenate(([0], np.cumsum(n)[:-1]))
+            has = n > 0
+            total[has] = np.add.reduceat(c, starts[has])
+            best[has] = np.maximum.reduceat(c, starts[has])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = np.where(n > 0, total / np.maximum(n, 1), np.nan)
+        return mean, best, np.where(n > 0, total, np.nan)
 
     def records(self, ix):
         """the reference's list of off-target dicts for guide ``ix`` (no ``cfd_score``)"""

@@ -58,3 +58,16 @@ def test_offtarget_table_equals_run_bowtie(tmp_path):
         assert "|".join(str(c) for c in counts[ix]) == guides[ix].off_target_str
         total += len(recs)
     assert total == len(t) and total > 50
+    # vectorised CFD: every per-hit score bit-identical to the per-guide loop, aggregates to 1e-12
+    cfd = t.cfd_scores(guide_pams=[g.guide_pam for g in guides])
+    mean, best, tot = t.cfd_layers(guide_pams=[g.guide_pam for g in guides])
+    for ix, recs in found.items():
+        mine = sorted(zip((key(r) for r in t.records(ix)), cfd[t.guide == ix].tolist()))
+        want = sorted((key(r), r["cfd_score"]) for r in recs)
+        assert mine == want
+        if recs:
+            assert best[ix] == guides[ix].layers["ot_cfd_score_max"]
+            assert np.isclose(mean[ix], guides[ix].layers["ot_cfd_score_mean"], rtol=1e-12, atol=0)
+            assert np.isclose(tot[ix], guides[ix].layers["ot_cfd_score_sum"], rtol=1e-12, atol=0)
+        else:
+            assert np.isnan(mean[ix]) and np.isnan(best[ix])
