@@ -72,20 +72,45 @@ struct ThreadRaw {
     ulonglong2 halo;                 // lane 31 only: the block after the warp's last
 };
 
-__device__ __forceinline__ void issue_thread_loads(const PlanesView &pv, int64_t block0, int lane, ThreadRaw &raw) {
+// Shared-memory staging of one tile's planes: kBpt rows of kThreads blocks (thread t owns column
+// t, so its 16-byte reads and cp.async writes are conflict free) + one halo block per warp.  A
+// thread reads back only what it requested itself, so waiting for its own cp.async group is all
+// the synchronisation there is.  (Keeping the next tile in registers instead looked cheaper and
+// was not: the compiler parked those registers in local memory, and the store waited for the load.)
+constexpr int kStageBlocks = kBpt * kThreads + kThreads / 32;
+
+__device__ __forceinline__ void cp_async16(ulonglong2 *smem_dst, const ulonglong2 *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+
+// request the planes of the thread's kBpt blocks starting at block0 (+ the warp's halo block)
+__device__ __forceinline__ void stage_issue(const PlanesView &pv, int64_t block0, int lane, ulonglong2 *buf) {
     const int64_t i = block0 - pv.blk_lo;
     if (i >= 0 && i + kBpt <= pv.blk_n) {
-        const ulonglong2 *p = pv.planes + i;  // 32-byte aligned: blk_lo and block0 are multiples of 4
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(raw.q[0]), "=l"(raw.q[1]), "=l"(raw.q[2]), "=l"(raw.q[3]) : "l"(p));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                     : "=l"(raw.q[4]), "=l"(raw.q[5]), "=l"(raw.q[6]), "=l"(raw.q[7]) : "l"(p + 2));
-    } else {
 #pragma unroll
-        for (int k = 0; k < kBpt; k++) { ulonglong2 b = load_block(pv, block0 + k); raw.q[2 * k] = b.x; raw.q[2 * k + 1] = b.y; }
+        for (int k = 0; k < kBpt; k++) cp_async16(buf + k * kThreads + threadIdx.x, pv.planes + i + k);
+    } else {  // tile sticks out of the resident range: zeros outside
+#pragma unroll
+        for (int k = 0; k < kBpt; k++) buf[k * kThreads + threadIdx.x] = load_block(pv, block0 + k);
+    }
+    if (lane == 31) {
+        ulonglong2 *h = buf + kBpt * kThreads + (threadIdx.x >> 5);
+        if (i + kBpt >= 0 && i + kBpt < pv.blk_n) cp_async16(h, pv.planes + i + kBpt);
+        else *h = make_ulonglong2(0ull, 0ull);
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+// the thread's own requests have landed: move them to registers
+__device__ __forceinline__ void stage_read(const ulonglong2 *buf, int lane, ThreadRaw &raw) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < kBpt; k++) {
+        const ulonglong2 b = buf[k * kThreads + threadIdx.x];
+        raw.q[2 * k] = b.x; raw.q[2 * k + 1] = b.y;
     }
     raw.halo = make_ulonglong2(0ull, 0ull);
-    if (lane == 31) raw.halo = load_block(pv, block0 + kBpt);
+    if (lane == 31) raw.halo = buf[kBpt * kThreads + (threadIdx.x >> 5)];
 }
 
 __device__ __forceinline__ void expand_thread_words(const ThreadRaw &raw, int lane, ThreadWords &t) {
@@ -199,7 +224,7 @@ __device__ __forceinline__ int64_t tile_block0(const PamScanArgs &a, uint32_t ti
     return (int64_t)(a.first_tile + tile) * kScanTileBlocks + threadIdx.x * kBpt;
 }
 
-// `raw` holds the thread's planes of this tile, requested one tile earlier (issue_thread_loads)
+// `raw` holds the thread's planes of this tile, requested one tile earlier (stage_issue / stage_read)
 __device__ __forceinline__ void tile_hit_words(const PamScanArgs &a, uint32_t tile, const ThreadRaw &raw,
                                                uint32_t hf[kWpt], uint32_t hr[kWpt]) {
     const int lane = threadIdx.x & 31;
@@ -249,20 +274,23 @@ __device__ __forceinline__ unsigned long long cta_sum(unsigned long long v, unsi
     return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) pam_count_kernel(const PamScanArgs a) {
-    __shared__ unsigned long long s_warp[kThreads / 32];
+__global__ void __launch_bounds__(kThreads, 4) pam_count_kernel(const PamScanArgs a) {
+    __shared__ __align__(16) ulonglong2 s_planes[2][kStageBlocks];
     const int lane = threadIdx.x & 31;
-    ThreadRaw raw;
-    if (blockIdx.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, blockIdx.x), lane, raw);
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        // request the next tile's planes before touching this tile's: one tile of loads is always in flight
-        ThreadRaw nxt = raw;
-        if (tile + gridDim.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, tile + gridDim.x), lane, nxt);
+    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes[0]);
+    int buf = 0;
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
+        ThreadRaw raw;
+        stage_read(s_planes[buf], lane, raw);
+        // request the next tile's planes before working on this tile's: one tile is always in flight
+        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes[buf ^ 1]);
         uint32_t hf[kWpt], hr[kWpt];
         tile_hit_words(a, tile, raw, hf, hr);
-        const unsigned long long t = cta_sum(popc_words(hf, hr), s_warp);
-        if (threadIdx.x == 0) a.tiles[tile] = t;
-        raw = nxt;
+        // no CTA barrier anywhere in this kernel: warps add their counts to the (zeroed) tile slot
+        unsigned long long v = popc_words(hf, hr);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0 && v) atomicAdd(&a.tiles[tile], v);
     }
 }
 
@@ -323,20 +351,28 @@ __device__ __forceinline__ void copy_out(const uint32_t *s, uint32_t a0, uint32_
     }
 }
 
+constexpr int kFillPlaneBytes = 2 * kStageBlocks * (int)sizeof(ulonglong2);
+constexpr int kFillSmemBytes = kFillPlaneBytes + 2 * (kStage + 8) * (int)sizeof(uint32_t);
+
 __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs a) {
     __shared__ unsigned long long s_warp[kThreads / 32], s_part[kThreads / 32];
-    __shared__ __align__(16) uint32_t s_stage[2][kStage + 8];
+    // dynamic shared memory (74 KB, above the static limit): [2 plane buffers][2 hit stages]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    ulonglong2 (*s_planes)[kStageBlocks] = reinterpret_cast<ulonglong2 (*)[kStageBlocks]>(s_dyn);
+    uint32_t (*s_stage)[kStage + 8] = reinterpret_cast<uint32_t (*)[kStage + 8]>(s_dyn + kFillPlaneBytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sa_f = (uint32_t)__cvta_generic_to_shared(s_stage[0]);
     const uint32_t sa_r = (uint32_t)__cvta_generic_to_shared(s_stage[1]);
     // running output offsets of the current tile = counts of all tiles before it
     unsigned long long ef = 0, er = 0;
     uint32_t summed = 0;  // tiles [0, summed) are in (ef, er)
-    ThreadRaw raw;
-    if (blockIdx.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, blockIdx.x), lane, raw);
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        ThreadRaw nxt = raw;  // next tile's planes fly while this tile is scanned, staged and stored
-        if (tile + gridDim.x < a.n_tiles) issue_thread_loads(a.pv, tile_block0(a, tile + gridDim.x), lane, nxt);
+    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes[0]);
+    int buf = 0;
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
+        ThreadRaw raw;
+        stage_read(s_planes[buf], lane, raw);
+        // next tile's planes fly while this tile is scanned, staged and stored
+        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes[buf ^ 1]);
         // advance (ef, er) over the tiles [summed, tile): at most gridDim.x counts (<= 2^16 each, so
         // the packed 32-bit halves cannot overflow), L2 resident; reduced alongside the CTA scan
         unsigned long long part = 0;
@@ -346,7 +382,6 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
         uint32_t hf[kWpt], hr[kWpt];
         tile_hit_words(a, tile, raw, hf, hr);
-        raw = nxt;
         const unsigned long long mine = popc_words(hf, hr);
         // CTA exclusive scan of the packed (fw, rv) counts
         unsigned long long inc = mine;
@@ -452,12 +487,14 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         int per_sm = 0;
         GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_count_kernel, kThreads, 0));
         ds->scan_grid[0] = ds->sm_count * std::max(per_sm, 1);
-        GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_fill_kernel, kThreads, 0));
+        GUIDO_CUDA(cudaFuncSetAttribute(pam_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFillSmemBytes));
+        GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_fill_kernel, kThreads, kFillSmemBytes));
         ds->scan_grid[1] = ds->sm_count * std::max(per_sm, 1);
     }
+    GUIDO_CUDA(cudaMemsetAsync(a.tiles, 0, (size_t)a.n_tiles * sizeof(unsigned long long), stream));
     kev_begin(ds, stream);
     pam_count_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[0]), kThreads, 0, stream>>>(a);
-    pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, 0, stream>>>(a);
+    pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, kFillSmemBytes, stream>>>(a);
     kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
     if (n_launches) *n_launches += 2;
