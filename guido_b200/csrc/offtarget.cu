@@ -864,7 +864,8 @@ struct IdxArgs {
     uint32_t *counts;          // n_buckets + 1 (pass 1), becomes offsets after the scan
     uint32_t *fill;            // n_buckets
     uint32_t *keys, *ids;      // n_entries each
-    uint32_t key_lo, key_hi;   // fill pass: only buckets in [key_lo, key_hi) are written
+    uint32_t slice_bits, slice;  // fill pass: only buckets whose top slice_bits key bits == slice
+    uint16_t group_off[33];      // variants sorted by the top slice_bits of their hi-plane mask
     uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7 or 31)
     int sliced;                // 1: row-major staging format of the bit-sliced index (see below)
     uint32_t cbias;            // sliced: 7 - total_max, added to the variant's core mismatch count
@@ -888,14 +889,22 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
         const uint2 G = __ldg(&a.guides[g]);
         const uint32_t ch = (G.x >> a.dl) & cmask, cl_ = (G.y >> a.dl) & cmask;
         const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
-        for (uint32_t v = lane; v < a.n_variants; v += 32) {
+        // A fill pass writes the buckets whose top `slice_bits` key bits equal `slice`; the variants
+        // are grouped by the same bits of their hi-plane mask, so the group (top bits of the
+        // guide's core ^ slice) holds exactly this pass's variants: every lane of every iteration
+        // does a store, and the eight passes together walk the variant list once.
+        uint32_t v0 = 0, v1 = a.n_variants;
+        if constexpr (kFill) {
+            const uint32_t grp = ((ch >> (a.cl - a.slice_bits)) ^ a.slice) & ((1u << a.slice_bits) - 1u);
+            v0 = a.group_off[grp]; v1 = a.group_off[grp + 1];
+        }
+        for (uint32_t v = v0 + lane; v < v1; v += 32) {
             const uint32_t var = staged ? s_var[v] : __ldg(&a.variants[v]);
             const uint32_t xh = var & 0xffff, xl = var >> 16;
             const uint32_t key = ((ch ^ xh) << a.cl) | (cl_ ^ xl);
             if constexpr (!kFill) {
                 atomicAdd(&a.counts[key], 1u);
             } else {
-                if (key < a.key_lo || key >= a.key_hi) continue;
                 // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
                 const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
                 const uint32_t cmm = (uint32_t)__popc(xh | xl);
@@ -1088,11 +1097,33 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots, *planes = ids + n_slots;
     const int field = dl + op.core_max;  // <= 16, checked by ot_index_applicable
     GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
+    // The fill scatters 8-byte entries all over a ~0.5 GB index: done in one go every store dirties
+    // its own 32-byte sector in DRAM (8x write amplification).  Filling one slice of the bucket
+    // range at a time -- the buckets that share their top slice_bits key bits -- keeps the slice
+    // L2-resident, so DRAM sees whole lines.  Expected slots actually used (uniform keys: half a
+    // pad unit per bucket) size the slices.
+    const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
+    const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
+    const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
+    int slice_bits = 0;
+    while (slice_bits < 5 && slice_bits < cl && ((used_slots * 8) >> slice_bits) > slice_bytes) slice_bits++;
+    // variants grouped by the top slice_bits of their hi-plane mask (see idx_build_kernel)
+    IdxArgs ia;
+    {
+        const uint32_t n_groups = 1u << slice_bits;
+        auto group_of = [&](uint32_t var) { return ((var & 0xffffu) >> (cl - slice_bits)) & (n_groups - 1u); };
+        std::stable_sort(variants.begin(), variants.end(), [&](uint32_t x, uint32_t y) { return group_of(x) < group_of(y); });
+        uint32_t at = 0;
+        for (uint32_t grp = 0; grp <= n_groups; grp++) {
+            while (at < variants.size() && group_of(variants[at]) < grp) at++;
+            ia.group_off[grp] = (uint16_t)at;
+        }
+        for (uint32_t grp = n_groups + 1; grp < 33; grp++) ia.group_off[grp] = (uint16_t)variants.size();
+    }
     // variants are tiny; a pageable async copy is staged by the driver before it returns
     GUIDO_CUDA(cudaMemcpyAsync(d_var, variants.data(), variants.size() * 4, cudaMemcpyHostToDevice, stream));
-    IdxArgs ia;
     ia.guides = d_guides; ia.n_guides = (uint32_t)n_guides; ia.variants = d_var; ia.n_variants = (uint32_t)variants.size();
-    ia.key_lo = 0; ia.key_hi = n_buckets;
+    ia.slice_bits = (uint32_t)slice_bits; ia.slice = 0;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
     const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
@@ -1100,23 +1131,13 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
-    // expected slots actually used (uniform keys: half a pad unit per bucket) -- sizes the passes
-    const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
-    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 8, stream));  // pads: c' = 15
-    // The fill scatters 4-byte keys/ids all over a 350 MB index: done in one go every store dirties
-    // its own 32-byte sector in DRAM (8x write amplification, 2.7 ms for 100 k guides).  Filling one
-    // slice of the bucket range at a time keeps the slice L2-resident, so DRAM sees whole lines.
-    {
-        const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
-        const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
-        uint32_t passes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, (used_slots * 8 + slice_bytes - 1) / slice_bytes));
-        for (uint32_t p = 0; p < passes; p++) {
-            ia.key_lo = (uint32_t)((uint64_t)n_buckets * p / passes);
-            ia.key_hi = (uint32_t)((uint64_t)n_buckets * (p + 1) / passes);
-            idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
-        }
-        if (n_launches) *n_launches += (int)passes + 4;
+    // pads: c' = 15 (a per-bucket pad writer was measured slower than this memset)
+    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 8, stream));
+    for (uint32_t p = 0; p < (1u << slice_bits); p++) {
+        ia.slice = p;
+        idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
     }
+    if (n_launches) *n_launches += (1 << slice_bits) + 4;
     if (sliced) {
         // blocks up to the end of the last bucket (read from the scanned offsets on the device)
         const uint32_t n_blocks = (uint32_t)(n_slots / 32);
