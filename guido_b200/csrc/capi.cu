@@ -369,12 +369,21 @@ static int resolve_ot_algo(guido_image *img, const OtParams &op, const ScanRange
         set_error("unknown off-target algorithm %d", (int)algo);
         return GUIDO_ERR_ARG;
     }
+    const int32_t algo_in = algo;
     if (algo == GUIDO_OT_AUTO) algo = ot_index_applicable(op, n_guides) ? GUIDO_OT_TABLE : GUIDO_OT_SCAN;
     else if (algo == GUIDO_OT_TABLE && !ot_index_applicable(op, n_guides)) algo = GUIDO_OT_INDEX;  // reports the reason
     if (algo == GUIDO_OT_TABLE && r.hi > r.lo && n_guides > 0) {
+        const bool requested = algo_in == GUIDO_OT_TABLE;
         int rc = ensure_site_table(ds, view_of(ds), op, r, st, nullptr);
-        if (rc == GUIDO_ERR_CAPACITY) algo = GUIDO_OT_INDEX;  // too many windows for HBM: stream instead
-        else if (rc) return rc;
+        if (rc == GUIDO_ERR_CAPACITY && !requested) {
+            algo = GUIDO_OT_INDEX;  // AUTO: too many windows for HBM, stream the genome instead
+        } else if (rc == GUIDO_ERR_CAPACITY) {
+            // not GUIDO_ERR_CAPACITY: that code means "output buffer too small, call again"
+            set_error("PAM-site table does not fit: more than 2^31 windows or not enough free device memory");
+            return GUIDO_ERR_NOMEM;
+        } else if (rc) {
+            return rc;
+        }
     }
     *out = algo;
     return GUIDO_OK;
@@ -389,7 +398,10 @@ int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, 
     ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
     bool built = false;
     rc = ensure_site_table(ds, view_of(ds), op, r, ds->stream, &built);
-    if (rc == GUIDO_ERR_CAPACITY) set_error("PAM-site table does not fit: core_length outside 6..12, more than 2^31 windows or not enough free device memory");
+    if (rc == GUIDO_ERR_CAPACITY) {
+        set_error("PAM-site table does not fit: core_length outside 6..12, more than 2^31 windows or not enough free device memory");
+        return GUIDO_ERR_NOMEM;
+    }
     if (rc) return rc;
     if (n_sites) *n_sites = ds->site_n;
     if (build_ms) *build_ms = built ? (double)ds->site_build_ms : 0.0;

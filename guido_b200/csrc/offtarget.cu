@@ -1231,6 +1231,9 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
         GUIDO_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const int64_t cap = (int64_t)total + 1024;
         if ((uint64_t)cap * 12 + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
+        // GUIDO_SITE_TABLE_MAX_MB: cap on the table size (tests of the streaming fallback, shared GPUs)
+        if (const char *lim = getenv("GUIDO_SITE_TABLE_MAX_MB"))
+            if ((uint64_t)cap * 12 > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
         GUIDO_CUDA(cudaMalloc(&ds->d_site_a, (size_t)cap * 4));
         GUIDO_CUDA(cudaMalloc(&ds->d_site_b, (size_t)cap * 4));
         GUIDO_CUDA(cudaMalloc(&ds->d_site_q, (size_t)cap * 4));

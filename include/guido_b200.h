@@ -176,7 +176,7 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
  * orientation) grouped by its core_len PAM-proximal bases, 12 bytes per window in HBM.  Guide
  * independent; depends on the PAM's base sets and on core_len only.  GUIDO_OT_AUTO/TABLE searches
  * build it on first use; this call builds it ahead of time (Genome.build / benchmarks) and reports
- * its size and build time.  GUIDO_ERR_CAPACITY: more than 2^31 windows or not enough free HBM
+ * its size and build time.  GUIDO_ERR_NOMEM: more than 2^31 windows or not enough free HBM
  * (AUTO then streams the genome through the seed index instead). */
 int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, int64_t *n_sites,
                            double *build_ms);

@@ -283,3 +283,23 @@ def test_offtarget_join_variants(native, monkeypatch, total, sliced):
     a, _ = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
     b, _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)
     assert len(a) > 0 and np.array_equal(a, b)
+
+
+def test_site_table_capacity_fallback(native, monkeypatch):
+    """when the PAM-site table cannot be held, AUTO streams the genome through the seed index
+    (same hits); an explicit TABLE request says why it cannot run"""
+    contigs = util.synthetic_contigs(29, [300000], n_runs=2)
+    rng = np.random.default_rng(10)
+    protos = _protos_from_genome(rng, contigs, 200, mutate=4)
+    img = native.Image.from_seqs(contigs).upload()
+    ref, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    monkeypatch.setenv("GUIDO_SITE_TABLE_MAX_MB", "0")
+    got, _ = img.offtarget_search(protos, algo=native.OT_AUTO, want_raw_flags=False)
+    assert len(ref) > 0 and np.array_equal(ref, got)
+    with pytest.raises(MemoryError, match="PAM-site table does not fit"):
+        img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    with pytest.raises(MemoryError, match="does not fit"):
+        img.site_table_build("NGG", 10)
+    monkeypatch.delenv("GUIDO_SITE_TABLE_MAX_MB")
+    got, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    assert np.array_equal(ref, got)
