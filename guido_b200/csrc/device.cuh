@@ -49,6 +49,7 @@ struct DeviceState {
     // core k-mer -- the genome-side index of the off-target search, built once per (PAM, core
     // length) and kept with the image like bowtie's index files (offtarget.cu)
     uint32_t *d_site_a = nullptr, *d_site_b = nullptr, *d_site_q = nullptr;
+    uint2 *d_site_kd = nullptr;  // per row {core key, distal bases as interleaved 2-bit codes}: what the sliced join streams
     int64_t site_cap = 0;       // entries allocated
     int64_t site_n = -1;        // entries valid (-1: no table)
     uint8_t site_fw[8] = {}, site_rv[8] = {};  // the PAM sets the table was built for

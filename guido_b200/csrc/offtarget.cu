@@ -27,7 +27,8 @@
 namespace guido {
 
 constexpr int kSitesPerThread = 8;
-constexpr int kSliceWords = 24;  // words per 32-key block of the bit-sliced index (see idx_transpose_kernel)
+constexpr int kSiteRowBytes = 20;  // PAM-site table: hi plane, lo plane, position, {core key, distal codes}
+constexpr int kSliceWords = 44;  // words per 32-key block of the bit-sliced index (see idx_transpose_kernel)
 
 // guide-side seed index (built per search call by the idx_* kernels below), structure of arrays:
 // the search streams `keys` only and touches `guides` on a hit
@@ -57,6 +58,7 @@ struct OtScanArgs {
     unsigned long long *site_count;
     // PAM-site table (genome-side index): windows grouped by core key, structure of arrays
     uint32_t *tab_a, *tab_b, *tab_q;   // hi plane (+ strand in bit 31), lo plane, global position
+    uint2 *tab_kd;                     // {core key, distal bases as interleaved 2-bit codes (lo bit first)}
     uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts, fill cursors (build only)
     uint32_t tab_n;
 };
@@ -408,6 +410,14 @@ __device__ __forceinline__ void lookup_round_thread(const OtScanArgs &a, const u
     if ((threadIdx.x & 31) == 0) atomicAdd(&hb.visited, visited);
 }
 
+// bit j of x (j < 16) -> bit 2j
+__device__ __forceinline__ uint32_t spread_bits(uint32_t x) {
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return (x | (x << 1)) & 0x55555555u;
+}
+
 // PAM-site table build: the core key of every window of the round is counted (pass 1) or the
 // window is scattered to its bucket (pass 2).  Order inside a bucket is arbitrary; hit lists are
 // sorted canonically afterwards.
@@ -425,6 +435,7 @@ __device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t 
         } else {
             const uint32_t slot = a.tab_counts[key] + atomicAdd(&a.tab_fill[key], 1u);
             a.tab_a[slot] = A; a.tab_b[slot] = B; a.tab_q[slot] = sQ[idx];
+            a.tab_kd[slot] = make_uint2(key, spread_bits(B & ((1u << dl) - 1u)) | (spread_bits(A & ((1u << dl) - 1u)) << 1));
         }
     }
 }
@@ -571,38 +582,6 @@ __device__ __forceinline__ uint32_t lop3_or_xor(uint32_t a, uint32_t b, uint32_t
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
 
-// 0 / ~0 according to bit j of x
-__device__ __forceinline__ uint32_t bit_mask(uint32_t x, int j) { return (uint32_t)((int32_t)(x << (31 - j)) >> 31); }
-
-// One block of 32 keys against one window: bit k of the result is set when key k is a hit, i.e.
-// (distal mismatches + c') <= 7.  kh/kl = the window's distal planes as 0/~0 words per base.
-__device__ __forceinline__ uint32_t sliced_block_hits(const uint4 *__restrict__ p, const uint32_t (&wh)[10],
-                                                      const uint32_t (&wl)[10]) {
-    const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
-    const uint32_t kh[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-    const uint32_t kl[10] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
-    uint32_t m[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) m[j] = lop3_or_xor(kh[j] ^ wh[j], kl[j], wl[j]);
-    // carry-save count of m[0..9] + c' (q5.x..w = weights 1, 2, 4, 8); only "reaches 8" matters,
-    // so sums that feed nothing are never formed
-    // weight 1: eleven inputs -> five carries
-    const uint32_t s0 = lop3_xor3(m[0], m[1], m[2]), c0 = lop3_maj(m[0], m[1], m[2]);
-    const uint32_t s1 = lop3_xor3(m[3], m[4], m[5]), c1 = lop3_maj(m[3], m[4], m[5]);
-    const uint32_t s2 = lop3_xor3(m[6], m[7], m[8]), c2 = lop3_maj(m[6], m[7], m[8]);
-    const uint32_t s3 = lop3_xor3(s0, s1, s2), c3 = lop3_maj(s0, s1, s2);
-    const uint32_t c4 = lop3_maj(s3, m[9], q5.x);
-    // weight 2: five carries + c' bit 1 -> three carries
-    const uint32_t t0 = lop3_xor3(c0, c1, c2), d0 = lop3_maj(c0, c1, c2);
-    const uint32_t t1 = lop3_xor3(c3, c4, q5.y), d1 = lop3_maj(c3, c4, q5.y);
-    const uint32_t d2 = t0 & t1;
-    // weight 4: three carries + c' bit 2 -> two carries
-    const uint32_t u0 = lop3_xor3(d0, d1, d2), e0 = lop3_maj(d0, d1, d2);
-    const uint32_t e1 = u0 & q5.z;
-    // weight 8: any carry or c' bit 3 = more than 7
-    return lop3_nor3(e0, e1, q5.w);
-}
-
 constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
 
 // Hits of the sliced join are parked as (table row, index slot) pairs -- two words, no loads in the
@@ -648,48 +627,74 @@ __device__ __forceinline__ void flush_queue(const OtScanArgs &a, HitQueue &hq, b
     __syncthreads();
 }
 
-__device__ __forceinline__ void cp_async4(const uint32_t *smem_dst, const uint32_t *gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+__device__ __forceinline__ void cp_async8(const uint2 *smem_dst, const uint2 *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
-// The join is a chain of dependent loads per window -- table entry (DRAM, streamed), bucket offsets
-// (L2), key planes (DRAM the first time a bucket is touched) -- and with ~50 issue slots of work
+// One block of 32 keys against one window: bit k of the result is set when key k is a hit, i.e.
+// (distal mismatches + c') <= 7.  A block stores, per distal base j, the four words "key k differs
+// from letter c at base j" (c = 0..3) next to each other: the window picks, per base, the word of
+// its own letter -- ten 4-byte loads deliver the ten mismatch words, there is no XOR / OR stage,
+// and the lanes of a warp (same bucket, different letters) stay inside one 16-byte chunk per load.
+// p[j] = address of that word in the block at hand; cw = the block's four c' words.
+__device__ __forceinline__ uint32_t sliced_block_hits(const uint32_t *const (&p)[10], const uint4 *cw, uint32_t word_off) {
+    uint32_t m[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) m[j] = __ldg(p[j] + word_off);
+    const uint4 q5 = __ldg(cw + word_off / 4);
+    // carry-save count of m[0..9] + c' (q5.x..w = weights 1, 2, 4, 8); only "reaches 8" matters,
+    // so sums that feed nothing are never formed
+    // weight 1: eleven inputs -> five carries
+    const uint32_t s0 = lop3_xor3(m[0], m[1], m[2]), c0 = lop3_maj(m[0], m[1], m[2]);
+    const uint32_t s1 = lop3_xor3(m[3], m[4], m[5]), c1 = lop3_maj(m[3], m[4], m[5]);
+    const uint32_t s2 = lop3_xor3(m[6], m[7], m[8]), c2 = lop3_maj(m[6], m[7], m[8]);
+    const uint32_t s3 = lop3_xor3(s0, s1, s2), c3 = lop3_maj(s0, s1, s2);
+    const uint32_t c4 = lop3_maj(s3, m[9], q5.x);
+    // weight 2: five carries + c' bit 1 -> three carries
+    const uint32_t t0 = lop3_xor3(c0, c1, c2), d0 = lop3_maj(c0, c1, c2);
+    const uint32_t t1 = lop3_xor3(c3, c4, q5.y), d1 = lop3_maj(c3, c4, q5.y);
+    const uint32_t d2 = t0 & t1;
+    // weight 4: three carries + c' bit 2 -> two carries
+    const uint32_t u0 = lop3_xor3(d0, d1, d2), e0 = lop3_maj(d0, d1, d2);
+    const uint32_t e1 = u0 & q5.z;
+    // weight 8: any carry or c' bit 3 = more than 7
+    return lop3_nor3(e0, e1, q5.w);
+}
+
+// The join is a chain of dependent loads per window -- table row (DRAM, streamed), bucket offsets
+// (L2), key planes (DRAM the first time a bucket is touched) -- and with ~35 issue slots of work
 // per 32 keys the loads, not the compare, set the pace.  So the chain is pulled one chunk ahead:
-// while a CTA works on chunk c its threads' table entries of chunk c+1 arrive through cp.async,
+// while a CTA works on chunk c its threads' table rows of chunk c+1 arrive through cp.async,
 // half-way through the chunk their bucket ranges are looked up and the first plane blocks are
 // prefetched into L2; by the time chunk c+1 starts everything it needs is on chip.  A thread only
 // ever reads the shared-memory words it wrote itself, so the stages need no CTA barrier.
 __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtScanArgs a) {
     constexpr uint32_t kChunk = kJoinPerThread * kThreads;
     __shared__ HitQueue s_hits;
-    __shared__ uint32_t sA[2][kChunk], sB[2][kChunk], sStart[2][kChunk], sLen[2][kChunk];
+    __shared__ uint2 sKD[2][kChunk];                       // {core key, interleaved distal codes}
+    __shared__ uint32_t sStart[2][kChunk], sLen[2][kChunk];
     if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
     __syncthreads();
     const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
     const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
-    const uint4 *__restrict__ planes = a.ix.planes;
+    const uint32_t *__restrict__ planes = reinterpret_cast<const uint32_t *>(a.ix.planes);
     unsigned long long visited = 0;
 
     // (the table arrays are allocated with a chunk of slack, so the last chunk reads past tab_n
     // without a bounds check per row; such rows get an empty bucket range below)
-    auto fetch = [&](uint32_t c, int buf) {  // this thread's table entries of chunk c -> shared memory
-        const uint32_t *ga = a.tab_a + (size_t)c * kChunk + threadIdx.x, *gb = a.tab_b + (size_t)c * kChunk + threadIdx.x;
+    auto fetch = [&](uint32_t c, int buf) {  // this thread's table rows of chunk c -> shared memory
+        const uint2 *g = a.tab_kd + (size_t)c * kChunk + threadIdx.x;
 #pragma unroll
-        for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            cp_async4(&sA[buf][k * kThreads + threadIdx.x], ga + k * kThreads);
-            cp_async4(&sB[buf][k * kThreads + threadIdx.x], gb + k * kThreads);
-        }
+        for (uint32_t k = 0; k < kJoinPerThread; k++) cp_async8(&sKD[buf][k * kThreads + threadIdx.x], g + k * kThreads);
         asm volatile("cp.async.commit_group;");
     };
-    auto resolve = [&](uint32_t c, int buf) {  // bucket ranges of those entries; planes towards L2
+    auto resolve = [&](uint32_t c, int buf) {  // bucket ranges of those rows; planes towards L2
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         uint32_t v[kJoinPerThread], w[kJoinPerThread];
 #pragma unroll
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t idx = k * kThreads + threadIdx.x;
-            const uint32_t A = sA[buf][idx], B = sB[buf][idx];
-            const uint32_t key = (((A >> 10) & 1023u) << 10) | ((B >> 10) & 1023u);
+            const uint32_t key = sKD[buf][k * kThreads + threadIdx.x].x & 0xfffffu;
             v[k] = __ldg(&a.ix.offsets[key]); w[k] = __ldg(&a.ix.offsets[key + 1]);
         }
 #pragma unroll
@@ -698,10 +703,11 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
             const uint32_t start = v[k] & ~31u;
             const uint32_t len = c * kChunk + idx < a.tab_n ? (w[k] & ~31u) - start - (v[k] & 31u) : 0u;
             sStart[buf][idx] = start; sLen[buf][idx] = len;
-            if (len) {  // the first two lines of the bucket's planes (one or two 96-byte blocks)
+            if (len) {  // the first lines of the bucket's planes (one or two 176-byte blocks)
                 const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256));
             }
         }
     };
@@ -709,24 +715,38 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
         const uint32_t len = sLen[buf][idx];
         if (len == 0) return;  // empty bucket, or a row past the end of the table
-        const uint32_t A = sA[buf][idx], B = sB[buf][idx];
+        const uint32_t D = sKD[buf][idx].y;
         visited += len;
-        uint32_t wh[10], wl[10];
+        const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
+        const uint32_t *base = planes + (size_t)blk0 * kSliceWords;
+        // per distal base: the word of the window's own letter (code = 2 bits of D) in block 0
+        const uint32_t *p[10];
 #pragma unroll
         for (int j = 0; j < 10; j++) {
-            wh[j] = bit_mask(A, j); wl[j] = bit_mask(B, j);
-            // opaque to the compiler: keeps the masks in registers instead of re-deriving all 20 of
-            // them (2 issue slots each) in every iteration of the block loop
-            asm volatile("" : "+r"(wh[j]), "+r"(wl[j]));
+            const uint32_t code4 = j ? ((D >> (2 * j - 2)) & 12u) : ((D << 2) & 12u);  // 4 * letter code
+            p[j] = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(base + 4 * j) + code4);
+            // opaque to the compiler: keeps the ten pointers in registers instead of re-deriving
+            // them (5 issue slots each) in every iteration of the block loop
+            asm volatile("" : "+l"(p[j]));
         }
-        const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
-        for (uint32_t b = 0; b < n_blk; b++) {
-            uint32_t r = sliced_block_hits(planes + (size_t)(blk0 + b) * (kSliceWords / 4), wh, wl);
-            while (r) {  // rare: 1.4 % of (window, block) pairs
+        const uint4 *cw = reinterpret_cast<const uint4 *>(base + 40);
+        auto report = [&](uint32_t r, uint32_t blk) {  // rare: 1.4 % of (window, block) pairs
+            while (r) {
                 const int kk = __ffs((int)r) - 1;
                 r &= r - 1;
-                queue_hit(a, s_hits, i, (blk0 + b) * 32 + (uint32_t)kk);
+                queue_hit(a, s_hits, i, blk * 32 + (uint32_t)kk);
             }
+        };
+        // two blocks per round at compile-time offsets from the ten pointers (a bucket of the
+        // 100 k-guide index has 1.9 blocks on average); the pointers move only for a third block
+        for (uint32_t b = 0;;) {
+            report(sliced_block_hits(p, cw, 0), blk0 + b);
+            if (b + 1 < n_blk) report(sliced_block_hits(p, cw, kSliceWords), blk0 + b + 1);
+            b += 2;
+            if (b >= n_blk) break;
+#pragma unroll
+            for (int j = 0; j < 10; j++) p[j] += 2 * kSliceWords;
+            cw += 2 * kSliceWords / 4;
         }
     };
 
@@ -839,7 +859,7 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
-    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
+    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_kd = nullptr; a.tab_n = 0;
     int rc = launch_ot_kernel<kModeScan>(ds, a, stream);
     if (rc) return rc;
     if (n_launches) *n_launches += 1;
@@ -1051,7 +1071,18 @@ __global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, co
                 x[u] = (lane & j) ? ((x[u] & ~m) | ((y & ~m) >> j)) : ((x[u] & m) | ((y & m) << j));
                 m ^= m << (j >> 1);
             }
-            if (blk + u < n_blocks && lane < kSliceWords) planes[(size_t)(blk + u) * kSliceWords + lane] = x[u];
+            // lane j < 10 holds the hi-plane word of base j and fetches the lo-plane word from lane
+            // j + 10; it writes the four "differs from letter c" words, c = 2 * hi + lo
+            const uint32_t kl = __shfl_down_sync(kFull, x[u], 10);
+            if (blk + u < n_blocks) {
+                uint32_t *blockp = planes + (size_t)(blk + u) * kSliceWords;
+                if (lane < 10) {
+                    const uint32_t kh = x[u];
+                    reinterpret_cast<uint4 *>(blockp)[lane] = make_uint4(kh | kl, kh | ~kl, ~kh | kl, ~kh | ~kl);
+                } else if (lane >= 20 && lane < 24) {
+                    blockp[40 + (lane - 20)] = x[u];
+                }
+            }
         }
     }
 }
@@ -1165,7 +1196,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
-    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
+    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_kd = nullptr; a.tab_n = 0;
     rc = launch_ot_kernel<kModeIndex>(ds, a, stream);
     if (rc) return rc;
     if (n_launches) *n_launches += 1;
@@ -1185,7 +1216,9 @@ void release_site_table(DeviceState *ds) {
     if (ds->d_site_a) cudaFree(ds->d_site_a);
     if (ds->d_site_b) cudaFree(ds->d_site_b);
     if (ds->d_site_q) cudaFree(ds->d_site_q);
+    if (ds->d_site_kd) cudaFree(ds->d_site_kd);
     ds->d_site_a = ds->d_site_b = ds->d_site_q = nullptr;
+    ds->d_site_kd = nullptr;
     ds->site_cap = 0;
     ds->site_n = -1;
 }
@@ -1219,7 +1252,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0, nullptr};
     a.guides = nullptr; a.n_guides = 0;
     a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr; a.site_count = ds->d_counts + 4;
-    a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
+    a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_kd = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
     if ((rc = launch_ot_kernel<kModeTabCount>(ds, a, stream))) return rc;
     unsigned long long total = 0;
     GUIDO_CUDA(cudaMemcpyAsync(&total, ds->d_counts + 4, sizeof total, cudaMemcpyDeviceToHost, stream));
@@ -1230,19 +1263,20 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
         size_t free_b = 0, total_b = 0;
         GUIDO_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const int64_t cap = (int64_t)total + 1024;
-        if ((uint64_t)cap * 12 + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
+        if ((uint64_t)cap * kSiteRowBytes + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
         // GUIDO_SITE_TABLE_MAX_MB: cap on the table size (tests of the streaming fallback, shared GPUs)
         if (const char *lim = getenv("GUIDO_SITE_TABLE_MAX_MB"))
-            if ((uint64_t)cap * 12 > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
+            if ((uint64_t)cap * kSiteRowBytes > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
         GUIDO_CUDA(cudaMalloc(&ds->d_site_a, (size_t)cap * 4));
         GUIDO_CUDA(cudaMalloc(&ds->d_site_b, (size_t)cap * 4));
         GUIDO_CUDA(cudaMalloc(&ds->d_site_q, (size_t)cap * 4));
+        GUIDO_CUDA(cudaMalloc(&ds->d_site_kd, (size_t)cap * 8));
         ds->site_cap = cap;
     }
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
-    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q;
+    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
     a.site_count = nullptr;
     if ((rc = launch_ot_kernel<kModeTabFill>(ds, a, stream))) return rc;
     GUIDO_CUDA(cudaEventRecord(ds->ev[2], stream));
@@ -1269,7 +1303,7 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
-    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q;
+    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
     a.tab_counts = a.tab_fill = nullptr; a.tab_n = (uint32_t)ds->site_n;
     a.first_block = 0; a.n_tiles = 0;
     int per_sm = 0;
