@@ -640,7 +640,7 @@ __device__ __forceinline__ void cp_async8(const uint2 *smem_dst, const uint2 *gm
 __device__ __forceinline__ uint32_t sliced_block_hits(const uint32_t *const (&p)[10], const uint4 *cw, uint32_t word_off) {
     uint32_t m[10];
 #pragma unroll
-    for (int j = 0; j < 10; j++) m[j] = __ldg(p[j] + word_off);
+    for (int j = 0; j < 10; j++) m[j] = __ldg(p[j] + word_off + 4 * j);
     const uint4 q5 = __ldg(cw + word_off / 4);
     // carry-save count of m[0..9] + c' (q5.x..w = weights 1, 2, 4, 8); only "reaches 8" matters,
     // so sums that feed nothing are never formed
@@ -719,15 +719,16 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         visited += len;
         const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
         const uint32_t *base = planes + (size_t)blk0 * kSliceWords;
-        // per distal base: the word of the window's own letter (code = 2 bits of D) in block 0
+        // per distal base: the word of the window's own letter (code = 2 bits of D) in block 0.
+        // p[j] = base + 4 * code bytes as ONE 64-bit multiply-add on the FMA pipe (the ALU pipe is
+        // the busy one); the base's own offset 16 * j rides in the loads' immediate field.
         const uint32_t *p[10];
 #pragma unroll
         for (int j = 0; j < 10; j++) {
             const uint32_t code4 = j ? ((D >> (2 * j - 2)) & 12u) : ((D << 2) & 12u);  // 4 * letter code
-            p[j] = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(base + 4 * j) + code4);
-            // opaque to the compiler: keeps the ten pointers in registers instead of re-deriving
-            // them (5 issue slots each) in every iteration of the block loop
-            asm volatile("" : "+l"(p[j]));
+            unsigned long long addr;
+            asm volatile("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(code4), "l"(base));
+            p[j] = reinterpret_cast<const uint32_t *>(addr);
         }
         const uint4 *cw = reinterpret_cast<const uint4 *>(base + 40);
         auto report = [&](uint32_t r, uint32_t blk) {  // rare: 1.4 % of (window, block) pairs
