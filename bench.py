@@ -294,7 +294,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     table = None
     if algo in (N.OT_AUTO, N.OT_TABLE):
         n_sites, build_ms = img.site_table_build(PAM, OT_KW["core_length"])
-        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 12 * n_sites, "build_ms": build_ms}
+        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 20 * n_sites, "build_ms": build_ms}
     # kernels per search: one host-API call reports its launches; the device sort (split + radix
     # passes + merge) belongs to that call only
     st0 = N.Stats()
