@@ -351,12 +351,16 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
     hits_rank = float(d_count.item())
     if table is not None:
-        # join over the site table: 8 B per window (its two plane words), every index key and
-        # bucket offset once (re-reads are L1/L2 hits by construction: table order = bucket
-        # order), 24 B per hit (position + guide id read, 16-byte record written)
+        # join over the site table: 8 B per window (core key + distal codes), the index once
+        # (re-reads are L1/L2 hits by construction: table order = bucket order) -- 176 B per 32-key
+        # block of the bit-sliced index (buckets padded to whole blocks: + 16 slots on average), or
+        # 4 B per key for the popc walk -- 4 B per bucket offset, and 36 B per hit (guide id,
+        # position and the two plane words read at flush time, 16-byte record written)
         from math import comb
         n_keys = float(n_guides) * sum(comb(OT_KW["core_length"], k) * 3 ** k for k in range(OT_KW["core_mismatches"] + 1))
-        alg_bytes_rank = 8.0 * sites + 4.0 * n_keys + 4.0 * 4 ** OT_KW["core_length"] + 24.0 * hits_rank
+        n_buckets = 4.0 ** OT_KW["core_length"]
+        index_bytes = (176.0 / 32.0) * (n_keys + 16.0 * n_buckets) if n_keys >= 16.0 * n_buckets else 4.0 * n_keys
+        alg_bytes_rank = 8.0 * sites + index_bytes + 4.0 * n_buckets + 36.0 * hits_rank
     else:
         alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
     return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "table": table,
@@ -445,8 +449,9 @@ def main():
                   "ot_kernel<index>" if use_index else "ot_kernel<scan>")
         algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
                      "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
-        alg_desc = ("per GPU: 8 B per window of the site table + 4 B per index key and bucket offset (each once) + "
-                    "24 B per hit; the compare itself is integer-pipe bound, see int_pipe" if use_table else
+        alg_desc = ("per GPU: 8 B per window of the site table + the index once (176 B per 32-key block, or 4 B per "
+                    "key for the popc walk) + 4 B per bucket offset + 36 B per hit; the compare itself is "
+                    "integer-pipe bound, see int_pipe" if use_table else
                     "per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
                     "key compared + 16 B per hit" if use_index else
                     "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
@@ -473,13 +478,15 @@ def main():
             sm_mhz = (r["clocks"] or {}).get("sm_mhz") or 1965.0
             per_gpu = r["visited"] / world / (r["kernel_ms"] * 1e-3)
             if sliced:
-                # 38 LOP3 per block of 32 keys on the ALU pipe (64 lanes/clk/SM = 2 warp-instr/clk/SM);
+                # per block of 32 keys: 10 four-byte loads (the mismatch words of the window's own letters)
+                # + 18 LOP3 of carry-save counting on the ALU pipe (64 lanes/clk/SM = 2 warp-instr/clk/SM);
                 # blocks are counted from the true keys (the pad slots of each bucket's last block ride along)
-                out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "lop3_per_32_keys": 38,
-                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 38 / 32 / 148 / (sm_mhz * 1e6),
+                out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "lop3_per_32_keys": 18, "loads_per_32_keys": 11,
+                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 18 / 32 / 148 / (sm_mhz * 1e6),
                                    "alu_peak_warp_instr_per_clk_per_sm": 2, "sm_mhz": sm_mhz,
-                                   "note": "20 LOP3 mismatch words + 18 LOP3 carry-save count per 32 keys, no POPC; "
-                                           "ncu: ALU pipe ~70 % busy overall (profiles/)"}
+                                   "note": "no XOR/OR stage and no POPC: per-letter mismatch words are loaded, an 18-LOP3 "
+                                           "carry-save tree counts them; ncu: ALU pipe ~60 %, issue slots ~67 % busy "
+                                           "overall incl. per-window set-up (profiles/r1_join_sliced_ncu.txt)"}
             else:
                 # the popc kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
                 out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),
