@@ -1208,7 +1208,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
 //
 // Genome-side index: the PAM-valid windows of the resident shard in guide orientation, grouped by
 // core key (counting sort: histogram pass, scan, scatter pass -- both passes are the search front
-// end with a different consumer).  12 bytes per window (4.7 GB for NGG on 3.1 Gb), built once per
+// end with a different consumer).  20 bytes per window (7.7 GB for NGG on 3.1 Gb), built once per
 // (PAM sets, core length) and kept until the image is released or other parameters are asked for.
 // It plays the role of the reference's bowtie index files (genome.py:157-168): guide-independent,
 // part of the built genome.

@@ -173,7 +173,7 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
                                int32_t algo, void *d_hits, int64_t cap, void *d_count, void *stream);
 /* Genome-side index of the off-target search, the counterpart of the `bowtie-build` index files
  * (guido/genome.py:156-171): every PAM-valid window of the uploaded shard (both strands, guide
- * orientation) grouped by its core_len PAM-proximal bases, 12 bytes per window in HBM.  Guide
+ * orientation) grouped by its core_len PAM-proximal bases, 20 bytes per window in HBM.  Guide
  * independent; depends on the PAM's base sets and on core_len only.  GUIDO_OT_AUTO/TABLE searches
  * build it on first use; this call builds it ahead of time (Genome.build / benchmarks) and reports
  * its size and build time.  GUIDO_ERR_NOMEM: more than 2^31 windows or not enough free HBM
