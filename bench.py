@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
                     [--workload offtarget|pam] [--genome human|agam|<Mb>] [--guides G] [--algo auto|scan|index|table]
+                    [--shard key|position]
 
 One "step" = one pass of the hot path over one batch:
   offtarget  (default) 100 000 SpCas9 guides, <=4 mismatches (core 10 / 2), against a synthetic
@@ -13,9 +14,12 @@ One "step" = one pass of the hot path over one batch:
              `--algo index` streams the genome instead and needs no table).
   pam        whole-genome NGG scan, both strands, synthetic 273 Mb genome -- configs[1].
              The default run also measures this one and reports it under "pam_scan".
-Multi-GPU: one process per GPU (torchrun); the genome is sharded in contiguous, tile-aligned
-chunks with a 256-base halo, the guides are replicated, and the per-rank hit lists are merged with
-an NCCL all-gather inside the step.  Total work is fixed as N grows ("strong").
+Multi-GPU: one process per GPU (torchrun).  Off-target search: every rank holds the whole image and
+1/N of the PAM-site table, split by core k-mer range, and builds the guide index for that range
+only (`--shard key`, default); or the genome is sharded in contiguous, tile-aligned chunks with a
+256-base halo and the guides are replicated (`--shard position`; always for the PAM scan).  The
+per-rank hit lists are merged with an NCCL all-gather inside the step.  Total work is fixed as N
+grows ("strong").
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with inputs resident in HBM;
 `e2e` goes through the host-buffer C-ABI call (guides H2D, hits sorted on the device, D2H into
@@ -360,7 +364,8 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
         n_keys = float(n_guides) * sum(comb(OT_KW["core_length"], k) * 3 ** k for k in range(OT_KW["core_mismatches"] + 1))
         n_buckets = 4.0 ** OT_KW["core_length"]
         index_bytes = (176.0 / 32.0) * (n_keys + 16.0 * n_buckets) if n_keys >= 16.0 * n_buckets else 4.0 * n_keys
-        alg_bytes_rank = 8.0 * sites + index_bytes + 4.0 * n_buckets + 36.0 * hits_rank
+        parts = R.world if getattr(R.a, "key_sharded", False) else 1  # key-sharded ranks build 1/N of the index
+        alg_bytes_rank = 8.0 * sites + (index_bytes + 4.0 * n_buckets) / parts + 36.0 * hits_rank
     else:
         alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
     return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "table": table,
@@ -380,6 +385,8 @@ def main():
     ap.add_argument("--genome", default=None)
     ap.add_argument("--guides", type=int, default=None)
     ap.add_argument("--algo", default="auto", choices=["auto", "scan", "index", "table"])
+    ap.add_argument("--shard", default="key", choices=["key", "position"],
+                    help="multi-GPU off-target search: split the core-key space (default) or the genome")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pam", action="store_true", help="skip the secondary PAM-scan measurement")
     args = ap.parse_args()
@@ -411,7 +418,17 @@ def main():
     peak, peak_src = measured_peak_gbs()
 
     img = N.Image.synth(lens, seed=seed, n_frac=n_frac)
-    img.upload(device=local_rank, shard_ix=rank, n_shards=world)
+    # Multi-GPU off-target search: by default every rank keeps the whole image (0.8 GB) and tables /
+    # searches 1/N of the core-key space (guido_site_table_partition), so the per-search guide index
+    # is built in N parts instead of N times.  `--shard position` gives every rank a stretch of
+    # the genome instead (north_star's layout; what the PAM scan always uses).
+    key_sharded = (args.workload == "offtarget" and world > 1 and args.shard == "key"
+                   and algo in (N.OT_AUTO, N.OT_TABLE) and world & (world - 1) == 0 and world <= 32)
+    if key_sharded:
+        img.upload(device=local_rank).site_table_partition(rank, world)
+    else:
+        img.upload(device=local_rank, shard_ix=rank, n_shards=world)
+    args.key_sharded = key_sharded
     G = img.info.total_bases
     out = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic"}
@@ -463,7 +480,10 @@ def main():
                                    + (" (BASELINE configs[3] on N GPUs)" if args.genome == "human" else " (BASELINE configs[2])"),
                        "pam": PAM, "algo": algo_desc,
                        "l2": "flushed between steps; the shard's site table / planes + index keys exceed L2",
-                       "parallelism": f"genome sharded x{world}, guides replicated, NCCL all-gather of hit lists",
+                       "parallelism": (f"PAM-site table partitioned by core k-mer range x{world} (whole image on every "
+                                       "rank), guide index built in the same parts, NCCL all-gather of hit lists"
+                                       if key_sharded else
+                                       f"genome sharded x{world}, guides replicated, NCCL all-gather of hit lists"),
                        "hits": r["hits"], "windows": r["sites"], "index_keys_compared": r["visited"],
                        "site_table": r["table"]},
             "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],

@@ -72,6 +72,7 @@ _SIGNATURES = {
                                                   _i64, _vp, _vp]),
     "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
     "guido_site_table_free": (ctypes.c_int, [_vp]),
+    "guido_site_table_partition": (ctypes.c_int, [_vp, _i32, _i32]),
     "guido_encode_guides": (ctypes.c_int, [_cp, _i64, _vp]),
     "guido_mmej_batch": (ctypes.c_int, [_cp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _P(Stats)]),
 }
@@ -340,6 +341,12 @@ class Image:
 
     def site_table_free(self):
         check(lib().guido_site_table_free(self._h))
+
+    def site_table_partition(self, part_ix, n_parts):
+        """Restrict this handle's PAM-site table -- and therefore its TABLE/AUTO searches -- to part
+        ``part_ix`` of ``n_parts`` (a power of two) of the core-key space; see the header."""
+        check(lib().guido_site_table_partition(self._h, part_ix, n_parts))
+        return self
 
     def offtarget_search(self, protos, pam="NGG", core_length=10, core_mismatches=2,
                          total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False):

@@ -385,7 +385,24 @@ static int resolve_ot_algo(guido_image *img, const OtParams &op, const ScanRange
             return rc;
         }
     }
+    if (ds->site_n_parts > 1 && algo != GUIDO_OT_TABLE) {
+        set_error("this handle covers 1/%d of the core-key space (guido_site_table_partition): only the "
+                  "table join can search it", ds->site_n_parts);
+        return GUIDO_ERR_ARG;
+    }
     *out = algo;
+    return GUIDO_OK;
+}
+
+int guido_site_table_partition(guido_image *img, int32_t part_ix, int32_t n_parts) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_parts < 1 || n_parts > 32 || (n_parts & (n_parts - 1)) || part_ix < 0 || part_ix >= n_parts) {
+        set_error("bad partition %d of %d: the number of parts must be a power of two <= 32", (int)part_ix, (int)n_parts);
+        return GUIDO_ERR_ARG;
+    }
+    img->dev->site_part_ix = part_ix;  // the cached table (if any) no longer matches and is rebuilt on demand
+    img->dev->site_n_parts = n_parts;
     return GUIDO_OK;
 }
 

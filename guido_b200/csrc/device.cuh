@@ -55,6 +55,12 @@ struct DeviceState {
     uint8_t site_fw[8] = {}, site_rv[8] = {};  // the PAM sets the table was built for
     int site_pam_len = 0, site_core_len = 0;
     float site_build_ms = 0;
+    // Partition of the table by core-key range (multi-GPU off-target search): this handle tables --
+    // and therefore searches -- only the windows whose core key has its top log2(n_parts) bits equal
+    // to part_ix.  `site_part_*` is what the caller asked for, `site_tab_part_*` what the cached
+    // table was built with.
+    int site_part_ix = 0, site_n_parts = 1;
+    int site_tab_part_ix = 0, site_tab_n_parts = 1;
 };
 
 int device_init(DeviceState *ds, int device);

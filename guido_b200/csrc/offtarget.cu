@@ -61,6 +61,7 @@ struct OtScanArgs {
     uint2 *tab_kd;                     // {core key, distal bases as interleaved 2-bit codes (lo bit first)}
     uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts, fill cursors (build only)
     uint32_t tab_n;
+    uint32_t tab_key_lo, tab_key_span;  // table build: only core keys in [lo, lo + span) are tabled
 };
 
 // what the consumer of the front end does with a round of windows
@@ -430,6 +431,7 @@ __device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t 
         const uint32_t idx = (head + j) & (RING - 1);
         const uint32_t A = sA[idx], B = sB[idx];
         const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
+        if (key - a.tab_key_lo >= a.tab_key_span) continue;  // another rank's share of the key space
         if constexpr (!kFill) {
             atomicAdd(&a.tab_counts[key], 1u);
         } else {
@@ -887,6 +889,8 @@ struct IdxArgs {
     uint32_t *keys, *ids;      // n_entries each
     uint32_t slice_bits, slice;  // fill pass: only buckets whose top slice_bits key bits == slice
     uint16_t group_off[33];      // variants sorted by the top slice_bits of their hi-plane mask
+    uint32_t part_shift, part_ix; // histogram pass: only keys with key >> part_shift == part_ix (when part_on)
+    bool part_on;
     uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7 or 31)
     int sliced;                // 1: row-major staging format of the bit-sliced index (see below)
     uint32_t cbias;            // sliced: 7 - total_max, added to the variant's core mismatch count
@@ -924,7 +928,7 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
             const uint32_t xh = var & 0xffff, xl = var >> 16;
             const uint32_t key = ((ch ^ xh) << a.cl) | (cl_ ^ xl);
             if constexpr (!kFill) {
-                atomicAdd(&a.counts[key], 1u);
+                if (!a.part_on || (key >> a.part_shift) == a.part_ix) atomicAdd(&a.counts[key], 1u);
             } else {
                 // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
                 const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
@@ -1099,10 +1103,19 @@ static bool ot_sliced_applicable(const OtParams &op, int64_t n_guides) {
     return (double)v.size() * (double)n_guides >= 16.0 * (double)(1u << (2 * op.core_len));
 }
 
+__global__ void __launch_bounds__(256) idx_pad_fill_kernel(uint4 *ent2, const uint32_t *slots_used) {
+    const uint32_t n = (__ldg(slots_used) & ~31u) / 2;  // two 8-byte entries per uint4
+    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) ent2[i] = ff;
+}
+
 // builds the guide-side seed index of this search in ds->d_bucket / ds->d_index; with `sliced` the
 // keys are additionally transposed into 32-key bit-plane blocks (buckets padded to whole blocks)
+// `part_bits` / `part_ix`: only the buckets whose top part_bits key bits equal part_ix are built (the
+// share of the key space this handle's site table covers); 0 / 0 = everything
 static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
-                             bool sliced, cudaStream_t stream, int *n_launches, OtIndex *out) {
+                             bool sliced, int part_bits, int part_ix, cudaStream_t stream, int *n_launches,
+                             OtIndex *out) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
         return GUIDO_ERR_ARG;
@@ -1137,7 +1150,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
     const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
     const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
-    int slice_bits = 0;
+    int slice_bits = part_bits;  // a partition is a union of slices
     while (slice_bits < 5 && slice_bits < cl && ((used_slots * 8) >> slice_bits) > slice_bytes) slice_bits++;
     // variants grouped by the top slice_bits of their hi-plane mask (see idx_build_kernel)
     IdxArgs ia;
@@ -1156,6 +1169,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     GUIDO_CUDA(cudaMemcpyAsync(d_var, variants.data(), variants.size() * 4, cudaMemcpyHostToDevice, stream));
     ia.guides = d_guides; ia.n_guides = (uint32_t)n_guides; ia.variants = d_var; ia.n_variants = (uint32_t)variants.size();
     ia.slice_bits = (uint32_t)slice_bits; ia.slice = 0;
+    ia.part_shift = (uint32_t)(2 * cl - part_bits); ia.part_ix = (uint32_t)part_ix; ia.part_on = part_bits > 0;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
     const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
@@ -1163,13 +1177,16 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
-    // pads: c' = 15 (a per-bucket pad writer was measured slower than this memset)
-    if (sliced) GUIDO_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)n_slots * 8, stream));
-    for (uint32_t p = 0; p < (1u << slice_bits); p++) {
+    // pads: c' = 15.  All slots up to the end of the last bucket are set (the bound is read on the
+    // device: a partitioned index uses a fraction of the worst-case allocation); the fill then
+    // overwrites the real entries.  (A per-bucket pad writer was measured slower.)
+    if (sliced) idx_pad_fill_kernel<<<ds->sm_count * 8, 256, 0, stream>>>(reinterpret_cast<uint4 *>(keys), counts + n_buckets);
+    const uint32_t per_part = 1u << (slice_bits - part_bits);
+    for (uint32_t p = (uint32_t)part_ix * per_part; p < ((uint32_t)part_ix + 1) * per_part; p++) {
         ia.slice = p;
         idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
     }
-    if (n_launches) *n_launches += (1 << slice_bits) + 4;
+    if (n_launches) *n_launches += (int)per_part + 4 + (sliced ? 1 : 0);
     if (sliced) {
         // blocks up to the end of the last bucket (read from the scanned offsets on the device)
         const uint32_t n_blocks = (uint32_t)(n_slots / 32);
@@ -1192,7 +1209,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
                     cudaStream_t stream, int *n_launches) {
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
-    int rc = build_guide_index(ds, op, d_guides, n_guides, false, stream, n_launches, &a.ix);
+    int rc = build_guide_index(ds, op, d_guides, n_guides, false, 0, 0, stream, n_launches, &a.ix);
     if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
@@ -1226,9 +1243,17 @@ void release_site_table(DeviceState *ds) {
 
 static bool site_table_matches(const DeviceState *ds, const OtParams &op) {
     if (ds->site_n < 0 || ds->site_core_len != op.core_len || ds->site_pam_len != op.pam.len) return false;
+    if (ds->site_tab_part_ix != ds->site_part_ix || ds->site_tab_n_parts != ds->site_n_parts) return false;
     for (int k = 0; k < op.pam.len; k++)
         if (ds->site_fw[k] != op.pam.fw[k] || ds->site_rv[k] != op.pam.rv[k]) return false;
     return true;
+}
+
+// bits of the core key that select the partition (n_parts is a power of two, checked when it is set)
+static int part_bits_of(const DeviceState *ds) {
+    int b = 0;
+    while ((1 << b) < ds->site_n_parts) b++;
+    return b;
 }
 
 // GUIDO_ERR_CAPACITY (without touching the last error text) when a table cannot be held: more than
@@ -1252,13 +1277,22 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     a.pv = pv; a.op = op; a.r = r;
     a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0, nullptr};
     a.guides = nullptr; a.n_guides = 0;
-    a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr; a.site_count = ds->d_counts + 4;
+    a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr;
+    a.site_count = ds->d_counts + 4;  // every PAM-valid window of the shard, 64-bit: guards the 32-bit scan
     a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_kd = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
+    a.tab_key_span = n_buckets >> part_bits_of(ds);
+    a.tab_key_lo = a.tab_key_span * (uint32_t)ds->site_part_ix;
     if ((rc = launch_ot_kernel<kModeTabCount>(ds, a, stream))) return rc;
-    unsigned long long total = 0;
-    GUIDO_CUDA(cudaMemcpyAsync(&total, ds->d_counts + 4, sizeof total, cudaMemcpyDeviceToHost, stream));
+    // bucket starts; the entry behind the last bucket is the number of rows
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    uint32_t total = 0;
+    unsigned long long all_windows = 0;
+    GUIDO_CUDA(cudaMemcpyAsync(&total, counts + n_buckets, sizeof total, cudaMemcpyDeviceToHost, stream));
+    GUIDO_CUDA(cudaMemcpyAsync(&all_windows, ds->d_counts + 4, sizeof all_windows, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
-    if (total >= (1ull << 31)) return GUIDO_ERR_CAPACITY;
+    if (all_windows >= (1ull << 31)) return GUIDO_ERR_CAPACITY;  // 32-bit row numbers (and the scan) end here
     if ((int64_t)total > ds->site_cap) {
         release_site_table(ds);
         size_t free_b = 0, total_b = 0;
@@ -1274,9 +1308,6 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
         GUIDO_CUDA(cudaMalloc(&ds->d_site_kd, (size_t)cap * 8));
         ds->site_cap = cap;
     }
-    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
     a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
     a.site_count = nullptr;
     if ((rc = launch_ot_kernel<kModeTabFill>(ds, a, stream))) return rc;
@@ -1285,6 +1316,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     cudaEventElapsedTime(&ds->site_build_ms, ds->ev[1], ds->ev[2]);
     ds->site_n = (int64_t)total;
     ds->site_core_len = cl; ds->site_pam_len = op.pam.len;
+    ds->site_tab_part_ix = ds->site_part_ix; ds->site_tab_n_parts = ds->site_n_parts;
     for (int k = 0; k < kMaxPam; k++) { ds->site_fw[k] = op.pam.fw[k]; ds->site_rv[k] = op.pam.rv[k]; }
     if (built) *built = true;
     return GUIDO_OK;
@@ -1299,7 +1331,7 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (ds->site_n == 0) return GUIDO_OK;
     OtScanArgs a;
     const bool sliced = ot_sliced_applicable(op, n_guides);
-    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, stream, n_launches, &a.ix);
+    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, stream, n_launches, &a.ix);
     if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;

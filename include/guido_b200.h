@@ -181,6 +181,14 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
 int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, int64_t *n_sites,
                            double *build_ms);
 int guido_site_table_free(guido_image *img);
+/* Multi-GPU off-target search without replicated work: instead of giving every process a stretch of
+ * the genome (guido_image_upload shards; every process then needs the whole guide index), give
+ * every process the WHOLE image and 1/n_parts of the core-key space.  The handle then tables only
+ * the windows whose core k-mer falls into part `part_ix` (top log2(n_parts) bits of the key;
+ * n_parts a power of two <= 32), builds only that part of the guide index per search, and its
+ * TABLE/AUTO searches return exactly the hits of those windows: the union over the parts is the
+ * hit list of the image.  Other algorithms refuse to run on a partitioned handle. */
+int guido_site_table_partition(guido_image *img, int32_t part_ix, int32_t n_parts);
 /* encode n x 20 letters into the {hi, lo} plane words the _dev call takes (host helper) */
 int guido_encode_guides(const char *protos, int64_t n_guides, uint32_t *out_hi_lo);
 

@@ -303,3 +303,33 @@ def test_site_table_capacity_fallback(native, monkeypatch):
     monkeypatch.delenv("GUIDO_SITE_TABLE_MAX_MB")
     got, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
     assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("sliced", ["0", "1"])
+def test_site_table_partition_union(native, monkeypatch, sliced):
+    """key-range partition of the site table (the multi-GPU mode without replicated index builds):
+    the parts' hit lists are disjoint and their union is the whole image's hit list"""
+    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    contigs = util.synthetic_contigs(30, [250000, 60000], n_runs=3)
+    rng = np.random.default_rng(11)
+    protos = _protos_from_genome(rng, contigs, 300, mutate=4)
+    img = native.Image.from_seqs(contigs).upload()
+    whole, _ = img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    n_all, _ = img.site_table_build("NGG", 10)
+    for n_parts in (2, 8):
+        parts, rows = [], 0
+        for p in range(n_parts):
+            img.site_table_partition(p, n_parts)
+            rows += img.site_table_build("NGG", 10)[0]
+            parts.append(img.offtarget_search(protos, algo=native.OT_AUTO, want_raw_flags=False)[0])
+        assert rows == n_all
+        merged = np.concatenate(parts)
+        merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+        assert len(whole) > 0 and np.array_equal(merged, whole)
+    with pytest.raises(ValueError, match="only the table join"):
+        img.offtarget_search(protos, algo=native.OT_SCAN, want_raw_flags=False)
+    with pytest.raises(ValueError, match="power of two"):
+        img.site_table_partition(0, 3)
+    img.site_table_partition(0, 1)
+    back, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    assert np.array_equal(back, whole)
