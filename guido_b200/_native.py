@@ -70,6 +70,7 @@ _SIGNATURES = {
                                               _P(_i64), _vp, _P(Stats)]),
     "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
                                                   _i64, _vp, _vp]),
+    "guido_offtarget_raw_flags": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _vp]),
     "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
     "guido_site_table_free": (ctypes.c_int, [_vp]),
     "guido_site_table_partition": (ctypes.c_int, [_vp, _i32, _i32]),
@@ -379,6 +380,18 @@ class Image:
             check(rc)
             self._ot_hint = nh.value + nh.value // 16 + 16  # right-size the next call's buffer
             return hits[:nh.value], flags
+
+    def offtarget_raw_flags(self, protos, pam="NGG", core_length=10, core_mismatches=2, total_mismatches=4):
+        """uint8[n]: 1 where the guide has any raw bowtie alignment in this handle's stretch of the
+        genome (brute force over every window; for the few guides without a valid hit)."""
+        protos = list(protos)
+        for p in protos:
+            if len(p) != 20:
+                raise ValueError(f"protospacer must be 20 nt, got {len(p)}: {p!r}")
+        flags = np.zeros(len(protos), np.uint8)
+        check(lib().guido_offtarget_raw_flags(self._h, "".join(protos).encode(), len(protos), pam.encode(),
+                                              core_length, core_mismatches, total_mismatches, _ptr(flags)))
+        return flags
 
     def offtarget_search_dev(self, d_guides, n_guides, pam, core_length, core_mismatches,
                              total_mismatches, algo, d_hits, cap, d_count, stream=0):

@@ -452,6 +452,63 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
                           (uint64_t)cap, (unsigned long long *)d_count, nullptr, nullptr, st, nullptr);
 }
 
+// Key presence (off_targets.py:183-184) for the guides listed in `todo`: does the guide have ANY raw
+// bowtie alignment in this handle's stretch of the genome -- PAM mismatches allowed inside the seed
+// budget?  Brute force over every window (the PAM's fixed letters join the compare), flags[todo[i]].
+static int relaxed_flag_pass(guido_image *img, const char *protos, const std::vector<int64_t> &todo, const char *pam,
+                             int core_len, int core_mm, int total_mm, uint8_t *flags, float *kernel_ms,
+                             int *launches, int64_t *h2d, int64_t *d2h) {
+    if (todo.empty()) return GUIDO_OK;
+    DeviceState *ds = img->dev;
+    cudaStream_t st = ds->stream;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    OtParams rp;
+    int rc;
+    if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, true, &rp))) return rc;
+    std::vector<uint32_t> sub(2 * todo.size());
+    for (size_t i = 0; i < todo.size(); i++) {
+        uint32_t hl[2];
+        if ((rc = guido_encode_guides(protos + kProto * todo[i], 1, hl))) return rc;
+        uint32_t hi = hl[0], lo = hl[1];
+        for (int k = 0; k < rp.pam.len; k++)
+            if (rp.pam.fixed_mask & (1u << k)) {
+                hi |= (uint32_t)(rp.pam.code[k] >> 1) << (kProto + k);
+                lo |= (uint32_t)(rp.pam.code[k] & 1) << (kProto + k);
+            }
+        sub[2 * i] = hi; sub[2 * i + 1] = lo;
+    }
+    if ((rc = ensure_bytes(&ds->d_flags, &ds->flags_cap, (int64_t)todo.size()))) return rc;
+    if ((rc = ensure_bytes(&ds->d_guides, &ds->guides_cap, (int64_t)sub.size() * 4))) return rc;
+    GUIDO_CUDA(cudaMemsetAsync(ds->d_flags, 0, todo.size(), st));
+    GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, sub.data(), sub.size() * 4, cudaMemcpyHostToDevice, st));
+    GUIDO_CUDA(cudaEventRecord(ds->ev[1], st));
+    rc = launch_ot_scan(ds, view_of(ds), rp, r, (const uint2 *)ds->d_guides, (int64_t)todo.size(), nullptr, 0,
+                        ds->d_counts, (uint8_t *)ds->d_flags, nullptr, st, launches);
+    if (rc) return rc;
+    GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
+    std::vector<uint8_t> fl(todo.size());
+    GUIDO_CUDA(cudaMemcpyAsync(fl.data(), ds->d_flags, todo.size(), cudaMemcpyDeviceToHost, st));
+    GUIDO_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
+    if (kernel_ms) *kernel_ms += ms;
+    for (size_t i = 0; i < todo.size(); i++) flags[todo[i]] = fl[i];
+    if (h2d) *h2d += (int64_t)sub.size() * 4;
+    if (d2h) *d2h += (int64_t)todo.size();
+    return GUIDO_OK;
+}
+
+int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                              int32_t core_len, int32_t core_mm, int32_t total_mm, uint8_t *flags) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
+    std::vector<int64_t> todo((size_t)n_guides);
+    for (int64_t g = 0; g < n_guides; g++) todo[(size_t)g] = g;
+    memset(flags, 0, (size_t)n_guides);
+    return relaxed_flag_pass(img, protos, todo, pam, core_len, core_mm, total_mm, flags, nullptr, nullptr, nullptr, nullptr);
+}
+
 int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
                            int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                            guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
@@ -552,43 +609,17 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         return GUIDO_ERR_CAPACITY;
     }
 
-    if (raw_flags) {
+    // On a handle that covers 1/n of the core-key space the flags stay "has a valid hit in this
+    // part": most guides have none in a given part, and the relaxed pass below would brute-force
+    // all of them against the whole genome on every rank.  The caller ORs the flags of the parts and
+    // asks an unpartitioned handle about the guides that are left (guido_b200/parallel.py).
+    if (raw_flags && ds->site_n_parts == 1) {
         // key presence (off_targets.py:183-184): any raw bowtie alignment, PAM mismatches allowed
         // inside the seed budget.  Only guides without a valid hit need the relaxed all-window pass.
         std::vector<int64_t> todo;
         for (int64_t g = 0; g < n_guides; g++) if (!raw_flags[g]) todo.push_back(g);
-        if (!todo.empty()) {
-            OtParams rp;
-            if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, true, &rp))) return rc;
-            std::vector<uint32_t> sub(2 * todo.size());
-            for (size_t i = 0; i < todo.size(); i++) {
-                uint32_t hl[2];
-                if ((rc = guido_encode_guides(protos + kProto * todo[i], 1, hl))) return rc;
-                uint32_t hi = hl[0], lo = hl[1];
-                for (int k = 0; k < rp.pam.len; k++)
-                    if (rp.pam.fixed_mask & (1u << k)) {
-                        hi |= (uint32_t)(rp.pam.code[k] >> 1) << (kProto + k);
-                        lo |= (uint32_t)(rp.pam.code[k] & 1) << (kProto + k);
-                    }
-                sub[2 * i] = hi; sub[2 * i + 1] = lo;
-            }
-            if ((rc = ensure_bytes(&ds->d_flags, &ds->flags_cap, (int64_t)todo.size()))) return rc;
-            GUIDO_CUDA(cudaMemsetAsync(ds->d_flags, 0, todo.size(), st));
-            GUIDO_CUDA(cudaMemcpyAsync(ds->d_guides, sub.data(), sub.size() * 4, cudaMemcpyHostToDevice, st));
-            GUIDO_CUDA(cudaEventRecord(ds->ev[1], st));
-            rc = launch_ot_scan(ds, view_of(ds), rp, r, (const uint2 *)ds->d_guides, (int64_t)todo.size(), nullptr, 0,
-                                ds->d_counts, (uint8_t *)ds->d_flags, nullptr, st, &launches);
-            if (rc) return rc;
-            GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
-            std::vector<uint8_t> fl(todo.size());
-            GUIDO_CUDA(cudaMemcpyAsync(fl.data(), ds->d_flags, todo.size(), cudaMemcpyDeviceToHost, st));
-            GUIDO_CUDA(cudaStreamSynchronize(st));
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
-            kernel_ms += ms;
-            for (size_t i = 0; i < todo.size(); i++) raw_flags[todo[i]] = fl[i];
-            h2d += (int64_t)sub.size() * 4; d2h += (int64_t)todo.size();
-        }
+        if ((rc = relaxed_flag_pass(img, protos, todo, pam, core_len, core_mm, total_mm, raw_flags, &kernel_ms,
+                                    &launches, &h2d, &d2h))) return rc;
     }
     if (stats) {
         float t = 0;

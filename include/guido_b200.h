@@ -166,6 +166,12 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
                            int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                            guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                            guido_stats *stats);
+/* key presence alone: flags[g] = 1 when guide g has at least one RAW bowtie alignment in this
+ * handle's stretch of the genome (the relaxed all-window pass guido_offtarget_search runs for the
+ * guides without a valid hit; brute force, meant for the few guides that have none anywhere).
+ * Ignores a key-range partition of the handle. */
+int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                              int32_t core_len, int32_t core_mm, int32_t total_mm, uint8_t *flags);
 /* device-resident variant: d_guides = n_guides x {u32 hi, u32 lo} plane words (guide position
  * order, see guido_ot_hit), d_hits = cap x guido_ot_hit, d_count = 1 x u64; unsorted; async. */
 int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides,
@@ -187,7 +193,9 @@ int guido_site_table_free(guido_image *img);
  * the windows whose core k-mer falls into part `part_ix` (top log2(n_parts) bits of the key;
  * n_parts a power of two <= 32), builds only that part of the guide index per search, and its
  * TABLE/AUTO searches return exactly the hits of those windows: the union over the parts is the
- * hit list of the image.  Other algorithms refuse to run on a partitioned handle. */
+ * hit list of the image.  Other algorithms refuse to run on a partitioned handle, and raw_flags of
+ * guido_offtarget_search then only mean "has a valid hit in this part" (OR them over the parts and
+ * ask an unpartitioned handle about the guides that are left). */
 int guido_site_table_partition(guido_image *img, int32_t part_ix, int32_t n_parts);
 /* encode n x 20 letters into the {hi, lo} plane words the _dev call takes (host helper) */
 int guido_encode_guides(const char *protos, int64_t n_guides, uint32_t *out_hi_lo);

@@ -333,3 +333,20 @@ def test_site_table_partition_union(native, monkeypatch, sliced):
     img.site_table_partition(0, 1)
     back, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
     assert np.array_equal(back, whole)
+
+
+def test_offtarget_raw_flags_entry_point(native, oracle):
+    """guido_offtarget_raw_flags = the key-presence half of the search on its own"""
+    contigs = util.synthetic_contigs(31, [80000, 30000], n_runs=3, iupac=4)
+    rng = np.random.default_rng(12)
+    protos = _protos_from_genome(rng, contigs, 80, mutate=3)
+    img = native.Image.from_seqs(contigs).upload()
+    for pam, kw in (("NGG", {}), ("NAG", dict(core_mismatches=1, total_mismatches=3))):
+        _, keys = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
+        flags = img.offtarget_raw_flags(protos, pam=pam, **kw)
+        assert set(np.nonzero(flags)[0].tolist()) == keys
+        # a key-partitioned handle answers the same: the pass ignores the partition
+        img.site_table_partition(1, 4)
+        assert np.array_equal(img.offtarget_raw_flags(protos, pam=pam, **kw), flags)
+        img.site_table_partition(0, 1)
+    assert len(img.offtarget_raw_flags([])) == 0

@@ -22,7 +22,7 @@ from guido_b200 import _native as N, parallel
 rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
 d = np.load(sys.argv[2], allow_pickle=True)
-sg = parallel.ShardedGenome(N.Image.load(str(d["image"])))
+sg = parallel.ShardedGenome(N.Image.load(str(d["image"])), partition=sys.argv[4])
 hits, flags = sg.offtarget_search(list(d["protos"]))
 fw, rv = sg.pam_scan("NGG")
 if rank == 0:
@@ -32,7 +32,8 @@ dist.barrier(); dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_native.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_search_equals_one_gpu(tmp_path):
+@pytest.mark.parametrize("partition", ["position", "key"])
+def test_two_gpu_sharded_search_equals_one_gpu(tmp_path, partition):
     contigs = util.synthetic_contigs(51, [400000, 300000], n_runs=3)
     img = _native.Image.from_seqs(contigs)
     img.save(tmp_path / "g.g2b")
@@ -49,8 +50,8 @@ def test_two_gpu_sharded_search_equals_one_gpu(tmp_path):
     np.savez(tmp_path / "in.npz", image=str(tmp_path / "g.g2b"), protos=np.array(protos))
     (tmp_path / "worker.py").write_text(WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", str(tmp_path / "worker.py"), ROOT,
-           str(tmp_path / "in.npz"), str(tmp_path / "out.npz")]
+           "--master-addr", "127.0.0.1", "--master-port", "29533" if partition == "position" else "29534", str(tmp_path / "worker.py"), ROOT,
+           str(tmp_path / "in.npz"), str(tmp_path / "out.npz"), partition]
     subprocess.run(cmd, check=True, timeout=300)
     out = np.load(tmp_path / "out.npz")
     assert np.array_equal(out["hits"].view(_native.OT_HIT_DTYPE).reshape(-1), whole)
