@@ -350,3 +350,27 @@ def test_offtarget_raw_flags_entry_point(native, oracle):
         assert np.array_equal(img.offtarget_raw_flags(protos, pam=pam, **kw), flags)
         img.site_table_partition(0, 1)
     assert len(img.offtarget_raw_flags([])) == 0
+
+
+@pytest.mark.parametrize("sliced", ["0", "1"])
+def test_offtarget_join_big_buckets(native, monkeypatch, sliced):
+    """many copies of the same guides: buckets of several hundred keys, i.e. more than the two
+    32-key blocks the sliced join evaluates per round (pointer-advance path), and long popc walks"""
+    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    contigs = util.synthetic_contigs(32, [200000], n_runs=2)
+    rng = np.random.default_rng(13)
+    img = native.Image.from_seqs(contigs).upload()
+    fw, _ = img.pam_scan_genome("NGG", native.SCAN_STRICT)     # guides that do have sites: real NGG windows
+    S, off = contigs[0][1].upper(), img.contigs[0][2]
+    base = [S[int(p) - off - 20:int(p) - off] for p in rng.choice(fw, size=40, replace=False)]
+    protos = base[:2] * 170 + base[2:] + base[:1] * 37      # 340 + 38 + 37 guides, heavy duplication
+    a, fa = img.offtarget_search(protos, algo=native.OT_SCAN)
+    b, fb = img.offtarget_search(protos, algo=native.OT_TABLE)
+    assert len(a) > 300 and np.array_equal(a, b) and np.array_equal(fa, fb)
+    img.site_table_partition(1, 2)
+    c, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    img.site_table_partition(0, 2)
+    d, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+    merged = np.concatenate([c, d])
+    merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+    assert np.array_equal(merged, a)
