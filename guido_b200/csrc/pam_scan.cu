@@ -275,15 +275,16 @@ __device__ __forceinline__ unsigned long long cta_sum(unsigned long long v, unsi
 }
 
 __global__ void __launch_bounds__(kThreads, 4) pam_count_kernel(const PamScanArgs a) {
-    __shared__ __align__(16) ulonglong2 s_planes[2][kStageBlocks];
+    // one buffer is enough: a thread moves its slots to registers (stage_read) and only then asks
+    // for the next tile's planes in the same slots
+    __shared__ __align__(16) ulonglong2 s_planes[kStageBlocks];
     const int lane = threadIdx.x & 31;
-    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes[0]);
-    int buf = 0;
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes);
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         ThreadRaw raw;
-        stage_read(s_planes[buf], lane, raw);
+        stage_read(s_planes, lane, raw);
         // request the next tile's planes before working on this tile's: one tile is always in flight
-        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes[buf ^ 1]);
+        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes);
         uint32_t hf[kWpt], hr[kWpt];
         tile_hit_words(a, tile, raw, hf, hr);
         // no CTA barrier anywhere in this kernel: warps add their counts to the (zeroed) tile slot
@@ -351,14 +352,15 @@ __device__ __forceinline__ void copy_out(const uint32_t *s, uint32_t a0, uint32_
     }
 }
 
-constexpr int kFillPlaneBytes = 2 * kStageBlocks * (int)sizeof(ulonglong2);
+constexpr int kFillPlaneBytes = kStageBlocks * (int)sizeof(ulonglong2);
 constexpr int kFillSmemBytes = kFillPlaneBytes + 2 * (kStage + 8) * (int)sizeof(uint32_t);
 
+// (4 CTAs/SM -- 64 registers, a smaller stage -- was measured: spills, no gain)
 __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs a) {
     __shared__ unsigned long long s_warp[kThreads / 32], s_part[kThreads / 32];
-    // dynamic shared memory (74 KB, above the static limit): [2 plane buffers][2 hit stages]
+    // dynamic shared memory (above the static limit): [plane buffer][2 hit stages]
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    ulonglong2 (*s_planes)[kStageBlocks] = reinterpret_cast<ulonglong2 (*)[kStageBlocks]>(s_dyn);
+    ulonglong2 *s_planes = reinterpret_cast<ulonglong2 *>(s_dyn);
     uint32_t (*s_stage)[kStage + 8] = reinterpret_cast<uint32_t (*)[kStage + 8]>(s_dyn + kFillPlaneBytes);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sa_f = (uint32_t)__cvta_generic_to_shared(s_stage[0]);
@@ -366,13 +368,12 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
     // running output offsets of the current tile = counts of all tiles before it
     unsigned long long ef = 0, er = 0;
     uint32_t summed = 0;  // tiles [0, summed) are in (ef, er)
-    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes[0]);
-    int buf = 0;
-    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, buf ^= 1) {
+    if (blockIdx.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, blockIdx.x), lane, s_planes);
+    for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         ThreadRaw raw;
-        stage_read(s_planes[buf], lane, raw);
+        stage_read(s_planes, lane, raw);
         // next tile's planes fly while this tile is scanned, staged and stored
-        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes[buf ^ 1]);
+        if (tile + gridDim.x < a.n_tiles) stage_issue(a.pv, tile_block0(a, tile + gridDim.x), lane, s_planes);
         // advance (ef, er) over the tiles [summed, tile): at most gridDim.x counts (<= 2^16 each, so
         // the packed 32-bit halves cannot overflow), L2 resident; reduced alongside the CTA scan
         unsigned long long part = 0;
