@@ -579,10 +579,6 @@ __device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
 __device__ __forceinline__ uint32_t lop3_nor3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
-// a | (b ^ c)
-__device__ __forceinline__ uint32_t lop3_or_xor(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xf6;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
 
 constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
 
