@@ -93,6 +93,34 @@ class GuideTable:
             return [self.guide(k) for k in range(*i.indices(len(self)))]
         return self.guide(i)
 
+    # ---- exporters (helpers.py:66-92), straight from the columns -------------------------
+    def to_dataframe(self, with_sequences=False):
+        """One row per guide with the position columns of ``guides_to_dataframe`` (same names, same
+        values); ``with_sequences`` adds ``guide_seq`` (protospacer + genomic PAM, fetched from the
+        image).  Layers, MMEJ patterns and off-targets belong to materialised ``Guide`` records."""
+        import pandas as pd
+        names = np.array([c[0] for c in self.image.contigs], dtype=object)
+        ids = np.char.add("gRNA-", self.rank_in_contig.astype(str))
+        df = pd.DataFrame({
+            "guide_chrom": names[self.contig], "guide_start": self.guide_start, "guide_end": self.guide_end,
+            "guide_strand": np.where(self.strand_minus, "-", "+"), "absolute_cut_pos": self.absolute_cut_pos,
+            "rank_score": 0.0, "rank": 0, "id": ids})
+        if with_sequences and len(self):
+            goff = np.array([c[2] for c in self.image.contigs], dtype=np.int64)
+            w = self.image.fetch_windows(goff[self.contig] + self.guide_start - 1, 20 + len(self.pam))
+            comp = np.zeros(256, np.uint8)
+            for a, b in zip(b"ACGTN", b"TGCAN"):
+                comp[a] = b
+            w = np.where(self.strand_minus[:, None], comp[w[:, ::-1]], w)
+            df["guide_seq"] = [r.tobytes().decode() for r in w]
+        df.index = df["id"]
+        return df
+
+    def to_bed(self, file):
+        """chrom, start, end, id, rank, strand -- the columns and layout of ``guides_to_bed``"""
+        cols = ["guide_chrom", "guide_start", "guide_end", "id", "rank", "guide_strand"]
+        self.to_dataframe().loc[:, cols].to_csv(file, sep="\t", header=False, index=False)
+
 
 class OffTargetTable:
     """Off-target hits of a guide set as columns, with the reference's filters applied vectorised.

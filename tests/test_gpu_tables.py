@@ -10,7 +10,7 @@ from tests.test_host_logic import GUIDE_ATTRS
 pytestmark = pytest.mark.gpu
 
 
-def test_guide_table_equals_find_guides_per_contig():
+def test_guide_table_equals_find_guides_per_contig(tmp_path):
     contigs = util.synthetic_contigs(61, [30000, 12000, 50, 8000], n_runs=3, run_len=(5, 300), lower_frac=0.2)
     img = _native.Image.from_seqs(contigs).upload()
     t = tables.GuideTable(img, "NGG")
@@ -28,6 +28,24 @@ def test_guide_table_equals_find_guides_per_contig():
         assert [p.tobytes().decode() for p in protos] == [w.guide_seq[:20] for w in want]
         k += n
     assert k == len(t)
+    # exporters straight from the columns: same rows as the per-locus exporters, contig by contig
+    df = t.to_dataframe(with_sequences=True)
+    bed = tmp_path / "all.bed"
+    t.to_bed(bed)
+    bed_lines = bed.read_text().splitlines()
+    k = 0
+    for ci, (name, seq) in enumerate(contigs):
+        loc = guido.Locus(sequence=seq, name=name)
+        loc.find_guides()
+        ref = loc.guides_to_dataframe()
+        n = len(ref)
+        mine = df.iloc[k:k + n]
+        for col in ("guide_chrom", "guide_start", "guide_end", "guide_strand", "absolute_cut_pos", "id", "guide_seq"):
+            assert mine[col].tolist() == (ref[col].tolist() if n else []), (name, col)
+        if n:  # (an empty guide list has no columns to pick: guides_to_bed raises, as upstream)
+            loc.guides_to_bed(tmp_path / "one.bed")
+            assert bed_lines[k:k + n] == (tmp_path / "one.bed").read_text().splitlines()
+        k += n
     assert len(tables.GuideTable(img, "TTTV")) == 0  # upstream: only 3-nt PAMs give guides
     with pytest.raises(KeyError):
         tables.GuideTable(img, "NGX")
