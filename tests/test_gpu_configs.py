@@ -130,6 +130,41 @@ def test_config3_10k_guides_properties():
     assert np.array_equal(bh["hi"], ih["hi"]) and np.array_equal(bh["lo"], ih["lo"])
 
 
+def test_config4_full_size_properties():
+    """100 k guides, <=4 mm vs the 3.1 Gb genome (the bench workload) at full size: the table join
+    (bit-sliced compare) and the streaming index kernel return the same hit list byte for byte,
+    every guide finds the site it was taken from, hits come back in canonical order, a sample of
+    them is re-verified on the host, and two key-range parts of the site table add up to the whole"""
+    import bench
+    lens, seed, n_frac, _ = bench.genome_lens("human")
+    img = _native.Image.synth(lens, seed=seed, n_frac=n_frac).upload()
+    protos = bench.sample_guides(img, 100_000, seed + 1)
+    hits, _ = img.offtarget_search(protos, algo=_native.OT_TABLE, want_raw_flags=False, pinned=True)
+    hits = hits.copy()
+    assert 9_000_000 < len(hits) < 13_000_000
+    key = (hits["guide"].astype(np.uint64) << np.uint64(33)) | (hits["gpos"].astype(np.uint64) << np.uint64(1)) \
+        | (hits["hi"] >> 31).astype(np.uint64)
+    assert (np.diff(key.astype(np.int64)) > 0).all()            # canonical order, no duplicates
+    enc = _native.encode_guides([bytes(p).decode() for p in protos]).reshape(-1, 2)   # (hi, lo) planes
+    m20 = np.uint32((1 << 20) - 1)
+    zero = ((hits["hi"] & m20) == enc[hits["guide"], 0]) & ((hits["lo"] & m20) == enc[hits["guide"], 1])
+    assert len(np.unique(hits["guide"][zero])) == 100_000        # every guide finds its own site
+    rng = np.random.default_rng(4)
+    _verify_hits(img, hits[np.sort(rng.choice(len(hits), 200_000, replace=False))], protos)
+    streamed, _ = img.offtarget_search(protos, algo=_native.OT_INDEX, want_raw_flags=False, pinned=True)
+    assert np.array_equal(streamed, hits)
+    del streamed
+    n_parts, total = 2, 0
+    for p in range(n_parts):
+        img.site_table_partition(p, n_parts)
+        part, _ = img.offtarget_search(protos, algo=_native.OT_TABLE, want_raw_flags=False, pinned=True)
+        part_key = (part["guide"].astype(np.uint64) << np.uint64(33)) | (part["gpos"].astype(np.uint64) << np.uint64(1)) \
+            | (part["hi"] >> 31).astype(np.uint64)
+        assert np.isin(part_key, key, assume_unique=True).all()
+        total += len(part)
+    assert total == len(hits)
+
+
 def test_config5_tttv_scan_and_mmej(oracle):
     """Cas12a TTTV scan + MMEJ for the guides of an exon set (scaled: 40 genes)"""
     contigs = util.synthetic_contigs(1006, [600_000], n_runs=3, run_len=(50, 500))
