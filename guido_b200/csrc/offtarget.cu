@@ -926,8 +926,8 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
             if constexpr (!kFill) {
                 if (!a.part_on || (key >> a.part_shift) == a.part_ix) atomicAdd(&a.counts[key], 1u);
             } else {
-                // offsets are multiples of 8 (32) with the padding in the low 3 (5) bits
-                const uint32_t pos = (a.counts[key] & ~a.pad_mask) + atomicAdd(&a.fill[key], 1u);
+                // fill[] starts out as the bucket starts (scan_fixup_kernel): the atomic IS the slot
+                const uint32_t pos = atomicAdd(&a.fill[key], 1u);
                 const uint32_t cmm = (uint32_t)__popc(xh | xl);
                 if (a.sliced) {
                     // staging word of the bit-sliced index: distal hi plane, distal lo plane, then the
@@ -1011,11 +1011,19 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *block_sums, u
     }
 }
 
-__global__ void __launch_bounds__(1024) scan_fixup_kernel(uint32_t *data, uint32_t n, const uint32_t *block_sums) {
+// `cursor` (optional, n - 1 entries): the bucket starts without the padding bits -- the fill pass
+// takes slots from it with ONE returning atomic per entry instead of a load plus an atomic
+__global__ void __launch_bounds__(1024) scan_fixup_kernel(uint32_t *data, uint32_t n, const uint32_t *block_sums,
+                                                           uint32_t *cursor, uint32_t pad_mask) {
     const uint32_t base = blockIdx.x * 4096u + threadIdx.x * 4u;
     const uint32_t add = block_sums[blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < 4; i++) if (base + i < n) data[base + i] += add;
+    for (int i = 0; i < 4; i++)
+        if (base + i < n) {
+            const uint32_t v = data[base + i] + add;
+            data[base + i] = v;
+            if (cursor && base + i + 1 < n) cursor[base + i] = v & ~pad_mask;
+        }
 }
 
 static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
@@ -1172,7 +1180,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, pad - 1);
     // pads: c' = 15.  All slots up to the end of the last bucket are set (the bound is read on the
     // device: a partitioned index uses a fraction of the worst-case allocation); the fill then
     // overwrites the real entries.  (A per-bucket pad writer was measured slower.)
@@ -1282,7 +1290,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     // bucket starts; the entry behind the last bucket is the number of rows
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, 0);
     uint32_t total = 0;
     unsigned long long all_windows = 0;
     GUIDO_CUDA(cudaMemcpyAsync(&total, counts + n_buckets, sizeof total, cudaMemcpyDeviceToHost, stream));
