@@ -77,6 +77,8 @@ void device_release(guido_image *img) {
         if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
         for (auto &e : ds->ev) if (e) cudaEventDestroy(e);
         for (auto &p : ds->kev) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
+        for (auto &e : ds->ev_slice) if (e) cudaEventDestroy(e);
+        if (ds->build_stream) cudaStreamDestroy(ds->build_stream);
         if (ds->stream) cudaStreamDestroy(ds->stream);
     }
     delete ds;

@@ -61,6 +61,11 @@ struct DeviceState {
     // table was built with.
     int site_part_ix = 0, site_n_parts = 1;
     int site_tab_part_ix = 0, site_tab_n_parts = 1;
+    uint32_t site_row_off[33] = {};  // first table row of each 1/32 of the core-key space (+ the row count)
+    // second stream + events: the guide index is built slice by slice while the join already
+    // works on the slices that are ready (launch_ot_join)
+    cudaStream_t build_stream = nullptr;
+    cudaEvent_t ev_slice[34] = {};
 };
 
 int device_init(DeviceState *ds, int device);

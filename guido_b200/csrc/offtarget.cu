@@ -60,7 +60,7 @@ struct OtScanArgs {
     uint32_t *tab_a, *tab_b, *tab_q;   // hi plane (+ strand in bit 31), lo plane, global position
     uint2 *tab_kd;                     // {core key, distal bases as interleaved 2-bit codes (lo bit first)}
     uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts, fill cursors (build only)
-    uint32_t tab_n;
+    uint32_t tab_lo, tab_n;             // join: rows [tab_lo, tab_n) of the table
     uint32_t tab_key_lo, tab_key_span;  // table build: only core keys in [lo, lo + span) are tabled
 };
 
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
     __shared__ uint32_t sStart[2][kChunk], sLen[2][kChunk];
     if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
     __syncthreads();
-    const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
+    const uint32_t n_chunks = (a.tab_n - a.tab_lo + kChunk - 1) / kChunk;
     const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
     const uint32_t *__restrict__ planes = reinterpret_cast<const uint32_t *>(a.ix.planes);
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
     // (the table arrays are allocated with a chunk of slack, so the last chunk reads past tab_n
     // without a bounds check per row; such rows get an empty bucket range below)
     auto fetch = [&](uint32_t c, int buf) {  // this thread's table rows of chunk c -> shared memory
-        const uint2 *g = a.tab_kd + (size_t)c * kChunk + threadIdx.x;
+        const uint2 *g = a.tab_kd + a.tab_lo + (size_t)c * kChunk + threadIdx.x;
 #pragma unroll
         for (uint32_t k = 0; k < kJoinPerThread; k++) cp_async8(&sKD[buf][k * kThreads + threadIdx.x], g + k * kThreads);
         asm volatile("cp.async.commit_group;");
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
             const uint32_t idx = k * kThreads + threadIdx.x;
             const uint32_t start = v[k] & ~31u;
-            const uint32_t len = c * kChunk + idx < a.tab_n ? (w[k] & ~31u) - start - (v[k] & 31u) : 0u;
+            const uint32_t len = a.tab_lo + c * kChunk + idx < a.tab_n ? (w[k] & ~31u) - start - (v[k] & 31u) : 0u;
             sStart[buf][idx] = start; sLen[buf][idx] = len;
             if (len) {  // the first lines of the bucket's planes (one or two 176-byte blocks)
                 const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
@@ -710,9 +710,9 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
         }
     };
     auto process = [&](uint32_t c, int buf, uint32_t k) {
-        const uint32_t idx = k * kThreads + threadIdx.x, i = c * kChunk + idx;
+        const uint32_t idx = k * kThreads + threadIdx.x, i = a.tab_lo + c * kChunk + idx;
         const uint32_t len = sLen[buf][idx];
-        if (len == 0) return;  // empty bucket, or a row past the end of the table
+        if (len == 0) return;  // empty bucket, or a row past the end of the range
         const uint32_t D = sKD[buf][idx].y;
         visited += len;
         const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtSca
     __syncthreads();
     flush_queue(a, s_hits, true);
     if (threadIdx.x == 0 && a.site_count) {
-        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)a.tab_n);
+        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)(a.tab_n - a.tab_lo));
         atomicAdd(a.site_count + 1, s_hits.visited);
     }
 }
@@ -824,14 +824,14 @@ __global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a
     __syncthreads();
     // a CTA owns a contiguous stretch of the table, so consecutive chunks reuse the bucket in L1
     constexpr uint32_t kChunk = kJoinPerThread * kThreads;
-    const uint32_t n_chunks = (a.tab_n + kChunk - 1) / kChunk;
+    const uint32_t n_chunks = (a.tab_n - a.tab_lo + kChunk - 1) / kChunk;
     const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
     unsigned long long visited = 0;
     for (uint32_t c = c0; c < c1; c++) {
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
             BucketWalk w;
-            join_init(a, c * kChunk + k * kThreads + threadIdx.x, w, visited);
+            join_init(a, a.tab_lo + c * kChunk + k * kThreads + threadIdx.x, w, visited);
             while (w.off < w.len) walk_step<true>(a, a.tab_a, a.tab_b, a.tab_q, w, s_hits);
         }
         __syncthreads();
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a
     __syncthreads();
     flush_hits(a, s_hits, true);
     if (threadIdx.x == 0 && a.site_count) {
-        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)a.tab_n);
+        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)(a.tab_n - a.tab_lo));
         atomicAdd(a.site_count + 1, s_hits.visited);
     }
 }
@@ -1050,22 +1050,26 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 // ---- bit-sliced copy of the index (join over the site table, core 10 / distal 10 only) ----------
 //
 // The popc compare costs ~8 issue slots per key (XOR, shift, OR/AND, POPC, min/compare, register
-// rotation) and the join is bound by exactly that.  Transposing the keys removes most of it: per
-// block of 32 keys the index holds 24 words -- bit j of word w belongs to key j: 10 words of the
-// distal hi plane, 10 of the lo plane, 4 of c' = core mismatches + 7 - total_max -- and a window
-// thread evaluates all 32 keys at once: 20 LOP3 give the 10 per-base mismatch words, an 18-LOP3
-// carry-save tree tells where d + c' reaches 8 (= no hit).  ~50 issue slots per 32 keys, no POPC.
+// rotation) and the join is bound by exactly that.  Transposing the keys removes most of it.  Per
+// block of 32 keys the index holds 44 words in which bit k belongs to key k: for each of the 10
+// distal bases the four words "key k differs from letter c here" (c = A, C, G, T), then the 4 bit
+// planes of c' = core mismatches + 7 - total_max.  A window thread loads, per base, the word of its
+// own letter -- ten 4-byte loads are the ten mismatch words, no XOR/OR stage -- and an 18-LOP3
+// carry-save tree tells where d + c' reaches 8 (= no hit).  ~35 issue slots per 32 keys, no POPC.
 // Pad slots of a bucket's last block hold c' = 15 and never hit.
 
 // One warp per block of 32 staged keys: lane k loads key k, a 5-stage butterfly (shuffle + masked
-// merge, the recursive 2x2 block transpose of a 32x32 bit matrix) leaves lane j with word j -- bit
-// k of it is bit j of key k -- and lanes 0..23 store the block's 96 bytes.
-__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *slots_used, uint32_t *planes) {
+// merge, the recursive 2x2 block transpose of a 32x32 bit matrix) leaves lane j with bit plane j of
+// the 32 keys; lanes 0..9 pair their hi plane with the lo plane of lane j + 10 and write the four
+// per-letter words of base j, lanes 20..23 write the c' planes: 176 bytes per block.
+__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *offsets, uint32_t key_lo,
+                                                             uint32_t key_hi, uint32_t *planes) {
     constexpr int U = 4;  // blocks per warp iteration: independent loads in flight
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * 8u;
-    const uint32_t n_blocks = (__ldg(slots_used) & ~31u) >> 5;  // offsets[n_buckets]: end of the last bucket
-    for (uint32_t blk = (blockIdx.x * 8u + (threadIdx.x >> 5)) * U; blk < n_blocks; blk += warps * U) {
+    // the blocks of the buckets [key_lo, key_hi): bucket starts are multiples of 32 slots
+    const uint32_t blk_lo = (__ldg(&offsets[key_lo]) & ~31u) >> 5, n_blocks = (__ldg(&offsets[key_hi]) & ~31u) >> 5;
+    for (uint32_t blk = blk_lo + (blockIdx.x * 8u + (threadIdx.x >> 5)) * U; blk < n_blocks; blk += warps * U) {
         uint32_t x[U];
 #pragma unroll
         for (int u = 0; u < U; u++) x[u] = blk + u < n_blocks ? __ldg(&ent[(size_t)(blk + u) * 32 + lane]).x : 0u;
@@ -1107,10 +1111,11 @@ static bool ot_sliced_applicable(const OtParams &op, int64_t n_guides) {
     return (double)v.size() * (double)n_guides >= 16.0 * (double)(1u << (2 * op.core_len));
 }
 
-__global__ void __launch_bounds__(256) idx_pad_fill_kernel(uint4 *ent2, const uint32_t *slots_used) {
-    const uint32_t n = (__ldg(slots_used) & ~31u) / 2;  // two 8-byte entries per uint4
+__global__ void __launch_bounds__(256) idx_pad_fill_kernel(uint4 *ent2, const uint32_t *offsets, uint32_t key_lo, uint32_t key_hi) {
+    // the slots of the buckets [key_lo, key_hi), two 8-byte entries per uint4
+    const uint32_t lo = (__ldg(&offsets[key_lo]) & ~31u) / 2, n = (__ldg(&offsets[key_hi]) & ~31u) / 2;
     const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) ent2[i] = ff;
+    for (uint32_t i = lo + blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) ent2[i] = ff;
 }
 
 // builds the guide-side seed index of this search in ds->d_bucket / ds->d_index; with `sliced` the
@@ -1119,7 +1124,7 @@ __global__ void __launch_bounds__(256) idx_pad_fill_kernel(uint4 *ent2, const ui
 // share of the key space this handle's site table covers); 0 / 0 = everything
 static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
                              bool sliced, int part_bits, int part_ix, cudaStream_t stream, int *n_launches,
-                             OtIndex *out) {
+                             OtIndex *out, const std::function<int(uint32_t, uint32_t)> *after_slice = nullptr) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
         return GUIDO_ERR_ARG;
@@ -1181,29 +1186,27 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, pad - 1);
-    // pads: c' = 15.  All slots up to the end of the last bucket are set (the bound is read on the
-    // device: a partitioned index uses a fraction of the worst-case allocation); the fill then
-    // overwrites the real entries.  (A per-bucket pad writer was measured slower.)
-    if (sliced) idx_pad_fill_kernel<<<ds->sm_count * 8, 256, 0, stream>>>(reinterpret_cast<uint4 *>(keys), counts + n_buckets);
-    const uint32_t per_part = 1u << (slice_bits - part_bits);
-    for (uint32_t p = (uint32_t)part_ix * per_part; p < ((uint32_t)part_ix + 1) * per_part; p++) {
-        ia.slice = p;
-        idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
-    }
-    if (n_launches) *n_launches += (int)per_part + 4 + (sliced ? 1 : 0);
-    if (sliced) {
-        // blocks up to the end of the last bucket (read from the scanned offsets on the device)
-        const uint32_t n_blocks = (uint32_t)(n_slots / 32);
-        const int tgrid = (int)std::min<uint32_t>((n_blocks + 31) / 32, (uint32_t)ds->sm_count * 8);
-        idx_transpose_kernel<<<tgrid, 256, 0, stream>>>((const uint2 *)keys, counts + n_buckets, planes);
-        if (n_launches) *n_launches += 1;
-    }
-    GUIDO_CUDA(cudaGetLastError());
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
     const int wide = force ? atoi(force) : 2;
     *out = OtIndex{counts, keys, ids, cl, dl, field, wide, sliced ? (const uint4 *)planes : nullptr};
+    // Slice by slice: pads (c' = 15: all slots of the slice's buckets are set, the fill then
+    // overwrites the real entries -- a per-bucket pad writer was measured slower), fill, transpose.
+    // The slot ranges are read from the scanned offsets on the device.  After each slice the caller
+    // may start consuming it (`after_slice`: the join of the table rows of that key range).
+    const uint32_t per_part = 1u << (slice_bits - part_bits);
+    const int key_shift = 2 * cl - slice_bits;
+    for (uint32_t p = (uint32_t)part_ix * per_part; p < ((uint32_t)part_ix + 1) * per_part; p++) {
+        const uint32_t key_lo = p << key_shift, key_hi = (p + 1) << key_shift;
+        if (sliced) idx_pad_fill_kernel<<<ds->sm_count * 4, 256, 0, stream>>>(reinterpret_cast<uint4 *>(keys), counts, key_lo, key_hi);
+        ia.slice = p;
+        idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
+        if (sliced) idx_transpose_kernel<<<ds->sm_count * 4, 256, 0, stream>>>((const uint2 *)keys, counts, key_lo, key_hi, planes);
+        GUIDO_CUDA(cudaGetLastError());
+        if (after_slice && (rc = (*after_slice)(key_lo, key_hi))) return rc;
+    }
+    if (n_launches) *n_launches += 4 + (int)per_part * (sliced ? 3 : 1);
     return GUIDO_OK;
 }
 
@@ -1293,6 +1296,9 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, 0);
     uint32_t total = 0;
     unsigned long long all_windows = 0;
+    for (int k = 0; k <= 32; k++)  // first row of every 1/32 of the key space: the join's slice boundaries
+        GUIDO_CUDA(cudaMemcpyAsync(&ds->site_row_off[k], counts + (size_t)k * (n_buckets / 32), sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaMemcpyAsync(&total, counts + n_buckets, sizeof total, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaMemcpyAsync(&all_windows, ds->d_counts + 4, sizeof all_windows, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
@@ -1335,26 +1341,55 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (ds->site_n == 0) return GUIDO_OK;
     OtScanArgs a;
     const bool sliced = ot_sliced_applicable(op, n_guides);
-    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, stream, n_launches, &a.ix);
-    if (rc) return rc;
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
     a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
-    a.tab_counts = a.tab_fill = nullptr; a.tab_n = (uint32_t)ds->site_n;
+    a.tab_counts = a.tab_fill = nullptr;
     a.first_block = 0; a.n_tiles = 0;
     int per_sm = 0;
     if (sliced) GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_sliced_kernel, kThreads, 0));
     else GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
-    const uint32_t n_chunks = (a.tab_n + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
-    int grid = ds->sm_count * std::max(per_sm, 1) * 4;  // 4 waves' worth of CTAs evens out the tail
-    if ((uint32_t)grid > n_chunks) grid = (int)n_chunks;
-    kev_begin(ds, stream);
-    if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
-    else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
-    kev_end(ds, stream);
-    GUIDO_CUDA(cudaGetLastError());
-    if (n_launches) *n_launches += 1;
+    const int max_grid = ds->sm_count * std::max(per_sm, 1) * 4;  // 4 waves' worth of CTAs evens out the tail
+
+    // The index is built slice by slice (a slice = the buckets that share their top key bits) on a
+    // second, high-priority stream; the table rows are in key order, so as soon as a slice is ready
+    // the join of ITS rows starts on the caller's stream while the next slice is being filled: the
+    // scatter-bound build (atomics, little issue pressure) hides behind the issue-bound join.
+    if (!ds->build_stream) {
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        GUIDO_CUDA(cudaStreamCreateWithPriority(&ds->build_stream, cudaStreamNonBlocking, hi_prio));
+        for (auto &e : ds->ev_slice) GUIDO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t sb = ds->build_stream;
+    GUIDO_CUDA(cudaEventRecord(ds->ev_slice[33], stream));        // guides are on the device, previous search is done
+    GUIDO_CUDA(cudaStreamWaitEvent(sb, ds->ev_slice[33], 0));
+    const int cl = op.core_len;
+    int n_joins = 0;
+    const std::function<int(uint32_t, uint32_t)> join_slice = [&](uint32_t key_lo, uint32_t key_hi) -> int {
+        // rows of the keys [key_lo, key_hi): boundaries are multiples of 1/32 of the key space
+        const uint32_t unit = (1u << (2 * cl)) / 32;
+        a.tab_lo = ds->site_row_off[key_lo / unit];
+        a.tab_n = ds->site_row_off[key_hi / unit];
+        cudaEvent_t ready = ds->ev_slice[(key_lo / unit) & 31];
+        GUIDO_CUDA(cudaEventRecord(ready, sb));
+        GUIDO_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+        if (a.tab_n <= a.tab_lo) return GUIDO_OK;
+        const uint32_t n_chunks = (a.tab_n - a.tab_lo + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
+        const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
+        if (n_joins == 0) kev_begin(ds, stream);  // guido_kernel_times: first join launch .. last join done
+        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
+        else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+        GUIDO_CUDA(cudaGetLastError());
+        n_joins++;
+        return GUIDO_OK;
+    };
+    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, sb, n_launches,
+                               &a.ix, &join_slice);
+    if (rc) return rc;
+    if (n_joins) kev_end(ds, stream);
+    if (n_launches) *n_launches += n_joins;
     return GUIDO_OK;
 }
 
