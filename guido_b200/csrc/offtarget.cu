@@ -1356,6 +1356,25 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     // second, high-priority stream; the table rows are in key order, so as soon as a slice is ready
     // the join of ITS rows starts on the caller's stream while the next slice is being filled: the
     // scatter-bound build (atomics, little issue pressure) hides behind the issue-bound join.
+    // GUIDO_OT_OVERLAP=0 (measurement knob): everything on the caller's stream, ONE join launch over
+    // the whole table after the index is complete -- guido_kernel_times then reports the join
+    // kernel timed alone (bench.py's roofline pass); the results are the same either way.
+    const char *ov = getenv("GUIDO_OT_OVERLAP");
+    if (ov && atoi(ov) == 0) {
+        int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, stream,
+                                   n_launches, &a.ix);
+        if (rc) return rc;
+        a.tab_lo = 0; a.tab_n = (uint32_t)ds->site_n;
+        const uint32_t n_chunks = (a.tab_n + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
+        const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
+        kev_begin(ds, stream);
+        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
+        else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+        kev_end(ds, stream);
+        GUIDO_CUDA(cudaGetLastError());
+        if (n_launches) *n_launches += 1;
+        return GUIDO_OK;
+    }
     if (!ds->build_stream) {
         int lo_prio = 0, hi_prio = 0;
         cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
