@@ -79,6 +79,7 @@ void device_release(guido_image *img) {
         for (auto &p : ds->kev) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
         for (auto &e : ds->ev_slice) if (e) cudaEventDestroy(e);
         if (ds->build_stream) cudaStreamDestroy(ds->build_stream);
+        if (ds->join_stream) cudaStreamDestroy(ds->join_stream);
         if (ds->stream) cudaStreamDestroy(ds->stream);
     }
     delete ds;

@@ -64,7 +64,7 @@ struct DeviceState {
     uint32_t site_row_off[33] = {};  // first table row of each 1/32 of the core-key space (+ the row count)
     // second stream + events: the guide index is built slice by slice while the join already
     // works on the slices that are ready (launch_ot_join)
-    cudaStream_t build_stream = nullptr;
+    cudaStream_t build_stream = nullptr, join_stream = nullptr;
     cudaEvent_t ev_slice[34] = {};
 };
 

@@ -1379,11 +1379,15 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
         int lo_prio = 0, hi_prio = 0;
         cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
         GUIDO_CUDA(cudaStreamCreateWithPriority(&ds->build_stream, cudaStreamNonBlocking, hi_prio));
+        GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->join_stream, cudaStreamNonBlocking));
         for (auto &e : ds->ev_slice) GUIDO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    cudaStream_t sb = ds->build_stream;
+    // joins alternate between the caller's stream and a sibling, so the tail of one slice's join
+    // (its last, partly filled wave of CTAs) runs next to the head of the following one
+    cudaStream_t sb = ds->build_stream, sj = ds->join_stream;
     GUIDO_CUDA(cudaEventRecord(ds->ev_slice[33], stream));        // guides are on the device, previous search is done
     GUIDO_CUDA(cudaStreamWaitEvent(sb, ds->ev_slice[33], 0));
+    GUIDO_CUDA(cudaStreamWaitEvent(sj, ds->ev_slice[33], 0));
     const int cl = op.core_len;
     int n_joins = 0;
     const std::function<int(uint32_t, uint32_t)> join_slice = [&](uint32_t key_lo, uint32_t key_hi) -> int {
@@ -1391,21 +1395,27 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
         const uint32_t unit = (1u << (2 * cl)) / 32;
         a.tab_lo = ds->site_row_off[key_lo / unit];
         a.tab_n = ds->site_row_off[key_hi / unit];
-        cudaEvent_t ready = ds->ev_slice[(key_lo / unit) & 31];
+        cudaEvent_t ready = ds->ev_slice[(key_lo / unit) % 31];
         GUIDO_CUDA(cudaEventRecord(ready, sb));
-        GUIDO_CUDA(cudaStreamWaitEvent(stream, ready, 0));
         if (a.tab_n <= a.tab_lo) return GUIDO_OK;
+        cudaStream_t s = (n_joins & 1) ? sj : stream;
+        GUIDO_CUDA(cudaStreamWaitEvent(s, ready, 0));
         const uint32_t n_chunks = (a.tab_n - a.tab_lo + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
         const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
         if (n_joins == 0) kev_begin(ds, stream);  // guido_kernel_times: first join launch .. last join done
-        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
-        else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, s>>>(a);
+        else ot_join_kernel<<<grid, kThreads, 0, s>>>(a);
         GUIDO_CUDA(cudaGetLastError());
         n_joins++;
         return GUIDO_OK;
     };
     int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, sb, n_launches,
                                &a.ix, &join_slice);
+    // the caller's stream continues when both join streams (and with them the build stream) are done
+    GUIDO_CUDA(cudaEventRecord(ds->ev_slice[32], sj));
+    GUIDO_CUDA(cudaStreamWaitEvent(stream, ds->ev_slice[32], 0));
+    GUIDO_CUDA(cudaEventRecord(ds->ev_slice[31], sb));  // (slices without table rows are built but never joined)
+    GUIDO_CUDA(cudaStreamWaitEvent(stream, ds->ev_slice[31], 0));
     if (rc) return rc;
     if (n_joins) kev_end(ds, stream);
     if (n_launches) *n_launches += n_joins;
