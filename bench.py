@@ -344,29 +344,26 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
             del os.environ["GUIDO_OT_OVERLAP"]
     hits = int(R.allsum(float(d_count.item())))
 
+    # end to end through the public API, host buffers in and out.  One GPU: guido_offtarget_search
+    # (letters up, search, device sort, one copy into pinned host memory).  Several GPUs:
+    # parallel.DeviceMerge -- plane words up, search, NCCL all-gather of the hit lists, device sort,
+    # one copy of the merged list into pinned host memory on every rank.
+    merge = None
+    if R.world > 1:
+        from guido_b200.parallel import DeviceMerge
+        merge = DeviceMerge(img)
+
     def e2e():
+        if merge is not None:
+            # the merged list is needed on ONE host: rank 0 copies it down, the others keep it in HBM
+            h = merge.search(guides_u8, pam=PAM, algo=algo, to_host=R.rank == 0, **OT_KW)
+            return 20 * n_guides, 16 * len(h) + 8 * R.world + 8
         st = N.Stats()
-        h, _ = img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
-        if R.world > 1:
-            t = torch.from_numpy(h.view(np.int32).reshape(-1, 4)).to(R.dev, non_blocking=True)
-            cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=R.dev)
-            allc = torch.empty(R.world, dtype=torch.int64, device=R.dev)
-            dist.all_gather_into_tensor(allc, cnt)
-            m = max(int(allc.max().item()), 1)
-            pad = torch.zeros((m, 4), dtype=torch.int32, device=R.dev)
-            pad[:t.shape[0]] = t
-            merged = torch.empty((R.world * m, 4), dtype=torch.int32, device=R.dev)
-            dist.all_gather_into_tensor(merged, pad)
-            if R.rank == 0:  # the merged list lands in pinned host memory on rank 0
-                if e2e.host is None or e2e.host.shape[0] < merged.shape[0]:
-                    e2e.host = torch.empty((merged.shape[0] * 5 // 4, 4), dtype=torch.int32, pin_memory=True)
-                e2e.host[:merged.shape[0]].copy_(merged, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-        return st
+        img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
+        return int(st.bytes_h2d), int(st.bytes_d2h)
 
-    e2e.host = None
-
-    e2e_ms, st = R.wall(e2e, 3)
+    e2e_ms, (h2d, d2h) = R.wall(e2e, 3)
+    st = st0  # windows / index keys of this rank's search (same search as the timed steps)
     info = img.info
     span = info.shard_hi - info.shard_lo
     # algorithmic bytes of the search kernel on this rank: genome planes once, one 8-byte bucket
@@ -391,7 +388,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
             "kernel_ms": kernel_ms, "region_ms": region_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
             "alg_bytes_rank": alg_bytes_rank, "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
             "pairs_scan": float(st.n_pairs) if not use_index else None,
-            "e2e_ms": e2e_ms, "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
+            "e2e_ms": e2e_ms, "h2d": h2d, "d2h": d2h}
 
 
 def main():

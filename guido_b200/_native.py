@@ -71,6 +71,8 @@ _SIGNATURES = {
     "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
                                                   _i64, _vp, _vp]),
     "guido_offtarget_raw_flags": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _vp]),
+    "guido_hits_sort_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "guido_encode_guides_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
     "guido_site_table_free": (ctypes.c_int, [_vp]),
     "guido_site_table_partition": (ctypes.c_int, [_vp, _i32, _i32]),
@@ -399,6 +401,14 @@ class Image:
                                                core_mismatches, total_mismatches, algo, d_hits, cap,
                                                d_count, stream))
 
+    def encode_guides_dev(self, d_letters, n_guides, d_out, d_bad=None, stream=0):
+        """n x 20 letters in HBM -> n x {hi, lo} plane words in HBM; asynchronous"""
+        check(lib().guido_encode_guides_dev(self._h, d_letters, n_guides, d_out, d_bad, stream))
+
+    def sort_hits_dev(self, d_hits, n_hits, n_guides, stream=0):
+        """device-resident hit records -> (guide, gpos, strand) order, in place, asynchronous"""
+        check(lib().guido_hits_sort_dev(self._h, d_hits, n_hits, n_guides, stream))
+
 
 def pam_scan_seq(seq, pam, device=None, mode=SCAN_REGEX, stats=None):
     """(pams_fw, pams_rv): 0-based match starts in ``seq`` -- what the two re.finditer passes of
@@ -421,10 +431,15 @@ def pam_scan_seq(seq, pam, device=None, mode=SCAN_REGEX, stats=None):
 
 
 def encode_guides(protos):
-    """list of 20-nt strings -> (n,2) uint32 {hi, lo} plane words (guide position order)."""
-    protos = list(protos)
-    out = np.empty((len(protos), 2), np.uint32)
-    check(lib().guido_encode_guides("".join(protos).encode(), len(protos), out.ctypes.data))
+    """list of 20-nt strings (or an (n,20) uint8 array of letters) -> (n,2) uint32 {hi, lo} plane
+    words (guide position order)."""
+    if isinstance(protos, np.ndarray):
+        blob, n = np.ascontiguousarray(protos, dtype=np.uint8).tobytes(), protos.shape[0]
+    else:
+        protos = list(protos)
+        blob, n = "".join(protos).encode(), len(protos)
+    out = np.empty((n, 2), np.uint32)
+    check(lib().guido_encode_guides(blob, n, out.ctypes.data))
     return out
 
 

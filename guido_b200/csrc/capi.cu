@@ -455,6 +455,24 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
                           (uint64_t)cap, (unsigned long long *)d_count, nullptr, nullptr, st, nullptr);
 }
 
+int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_guides, void *d_out, void *d_bad,
+                            void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
+    DeviceState *ds = img->dev;
+    // without a report slot bad letters go unnoticed (the handle's own slot takes the atomics)
+    unsigned long long *bad = d_bad ? (unsigned long long *)d_bad : ds->d_counts + 6;
+    return encode_guides_device(ds, (const char *)d_letters, n_guides, (uint2 *)d_out, bad, (cudaStream_t)stream);
+}
+
+int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_hits < 0 || n_guides < 1) { set_error("bad hit or guide count"); return GUIDO_ERR_ARG; }
+    return sort_hits_device(img->dev, (guido_ot_hit *)d_hits, (uint64_t)n_hits, n_guides, (cudaStream_t)stream, nullptr);
+}
+
 // Key presence (off_targets.py:183-184) for the guides listed in `todo`: does the guide have ANY raw
 // bowtie alignment in this handle's stretch of the genome -- PAM mismatches allowed inside the seed
 // budget?  Brute force over every window (the PAM's fixed letters join the compare), flags[todo[i]].

@@ -51,6 +51,99 @@ def all_gather_hits(hits, group=None, device=None):
     return canonical_order(np.ascontiguousarray(merged).view(_native.OT_HIT_DTYPE).reshape(-1))
 
 
+class DeviceMerge:
+    """Off-target search of this rank's share + merge of all ranks' hits without leaving the GPUs
+    (NCCL process group): the guides' plane words go up once, the hits stay in HBM
+    (``guido_offtarget_search_dev``), the per-rank lists are all-gathered over NVLink, brought into
+    canonical (guide, gpos, strand) order on the device (``guido_hits_sort_dev``) and only then
+    copied to (pinned) host memory -- one device->host copy of the final list instead of a copy per
+    rank, an upload for the gather and a host sort.  Buffers are kept between calls."""
+
+    def __init__(self, image, group=None):
+        import torch
+        self.image, self.group = image, group
+        self.dev = torch.device("cuda", int(image.info.device))  # the device the image was uploaded to
+        self.cap = 0
+        self.d_hits = self.d_count = self.d_bad = self.host = None
+
+    def search(self, protos, pam="NGG", core_length=10, core_mismatches=2, total_mismatches=4,
+               algo=_native.OT_AUTO, to_host=True):
+        """-> merged hits (structured array in pinned host memory, or the (n,4) int32 device tensor
+        when ``to_host`` is false), identical on every rank"""
+        import torch
+        import torch.distributed as dist
+        import os
+        import sys
+        import time
+        world = dist.get_world_size(self.group)
+        trace = os.environ.get("GUIDO_TRACE") and dist.get_rank(self.group) == 0
+        t0 = time.perf_counter()
+
+        def lap(what):  # GUIDO_TRACE=1: wall clock of the phases on stderr (rank 0; synchronises)
+            if trace:
+                torch.cuda.synchronize(self.dev)
+                print(f"[guido merge] {what:18s} {(time.perf_counter() - t0) * 1e3:8.3f} ms", file=sys.stderr)
+
+        if isinstance(protos, np.ndarray):
+            letters = np.ascontiguousarray(protos, dtype=np.uint8).reshape(-1, 20)
+        else:
+            protos = list(protos)
+            for p in protos:
+                if len(p) != 20:
+                    raise ValueError(f"protospacer must be 20 nt, got {len(p)}: {p!r}")
+            letters = np.frombuffer("".join(protos).encode(), np.uint8).reshape(-1, 20)
+        n = letters.shape[0]
+        stream = torch.cuda.current_stream(self.dev)
+        with torch.cuda.device(self.dev):
+            # the letters go up as they are and are packed into plane words on the device
+            d_letters = torch.from_numpy(letters.copy() if not letters.flags.writeable else letters).to(self.dev, non_blocking=True)
+            d_guides = torch.empty((max(n, 1), 2), dtype=torch.int32, device=self.dev)
+            if self.d_count is None:
+                self.d_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+                self.d_bad = torch.empty(1, dtype=torch.int64, device=self.dev)
+            self.d_bad.fill_(-1)
+            self.image.encode_guides_dev(d_letters.data_ptr(), n, d_guides.data_ptr(), self.d_bad.data_ptr(),
+                                         stream.cuda_stream)
+            if self.cap == 0:
+                self.cap = max(1 << 16, 64 * n // world)
+            while True:
+                if self.d_hits is None or self.d_hits.shape[0] < self.cap:
+                    self.d_hits = torch.empty((self.cap, 4), dtype=torch.int32, device=self.dev)
+                self.image.offtarget_search_dev(d_guides.data_ptr(), n, pam, core_length, core_mismatches,
+                                                total_mismatches, algo, self.d_hits.data_ptr(), self.cap,
+                                                self.d_count.data_ptr(), stream.cuda_stream)
+                lap("search")
+                allc = torch.empty(world, dtype=torch.int64, device=self.dev)
+                dist.all_gather_into_tensor(allc, self.d_count, group=self.group)
+                counts = allc.tolist()
+                lap("counts")
+                bad = int(self.d_bad.item())
+                if bad != -1:
+                    raise ValueError(f"guide {bad // 32} holds a letter outside A/C/G/T at position {bad % 32 + 1}")
+                m = max(counts)
+                if m <= self.cap:
+                    break
+                self.cap = m + m // 8  # the exact need is known now: one more pass
+            m = max(m, 1)
+            gathered = torch.empty((world * m, 4), dtype=torch.int32, device=self.dev)
+            dist.all_gather_into_tensor(gathered, self.d_hits[:m], group=self.group)
+            merged = gathered if world == 1 else torch.cat([gathered[r * m:r * m + c] for r, c in enumerate(counts)])
+            total = sum(counts)
+            merged = merged[:total]
+            lap("gather")
+            if total > 1:
+                self.image.sort_hits_dev(merged.data_ptr(), total, n, stream.cuda_stream)
+            lap("sort")
+            if not to_host:
+                return merged
+            if self.host is None or self.host.shape[0] < total:
+                self.host = torch.empty((total + total // 8 + 16, 4), dtype=torch.int32, pin_memory=True)
+            self.host[:total].copy_(merged, non_blocking=True)
+            stream.synchronize()
+            lap("on the host")
+        return self.host[:total].numpy().view(_native.OT_HIT_DTYPE).reshape(-1)
+
+
 def all_gather_positions(positions, group=None, device=None):
     """Concatenate per-rank ascending position lists in rank order (= genome order)."""
     import torch
@@ -89,6 +182,7 @@ class ShardedGenome:
             raise ValueError(f"unknown partition {partition!r}")
         self.partition = partition
         self.image = image if isinstance(image, _native.Image) else _native.Image.load(image)
+        self._merge = None
         if partition == "key":
             self.image.upload(device=device)
             self.image.site_table_partition(self.rank, self.world)
@@ -113,9 +207,15 @@ class ShardedGenome:
         globally: ranks search without it, OR their "has a valid hit" flags, and only the guides
         that have none anywhere are checked, split over the ranks.
         """
+        import torch.distributed as dist
         protos = list(protos) if not isinstance(protos, np.ndarray) else [bytes(p).decode() for p in protos]
-        hits, _ = self.image.offtarget_search(protos, want_raw_flags=False, **kw)
-        merged = all_gather_hits(hits)
+        if dist.get_backend() == "nccl":  # search, merge and sort stay on the GPUs
+            if self._merge is None:
+                self._merge = DeviceMerge(self.image)
+            merged = self._merge.search(protos, **kw).copy()
+        else:
+            hits, _ = self.image.offtarget_search(protos, want_raw_flags=False, **kw)
+            merged = all_gather_hits(hits)
         if not want_raw_flags:
             return merged, None
         flags = np.zeros(len(protos), np.uint8)

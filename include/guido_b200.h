@@ -177,6 +177,17 @@ int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_gu
 int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides,
                                const char *pam, int32_t core_len, int32_t core_mm, int32_t total_mm,
                                int32_t algo, void *d_hits, int64_t cap, void *d_count, void *stream);
+/* device-side guido_encode_guides: d_letters = n_guides x 20 letters in HBM -> d_out = n_guides x
+ * {u32 hi, u32 lo}.  d_bad (device u64, may be NULL; set it to ~0 first) receives the smallest
+ * guide * 32 + position that holds a letter outside A/C/G/T.  Asynchronous on `stream`. */
+int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_guides, void *d_out, void *d_bad,
+                            void *stream);
+/* canonical order of a device-resident hit list (e.g. the NCCL-gathered lists of several GPUs):
+ * d_hits[0..n_hits) sorted in place by (guide, gpos, strand) -- the order guido_offtarget_search
+ * returns and the reference gets from sorting bowtie's rows (off_targets.py:174-225 walks them in
+ * file order; guido_b200 fixes the order so 1/2/4/8-GPU outputs are byte-identical).  n_guides
+ * bounds the guide field.  Asynchronous on `stream`; scratch memory belongs to the handle. */
+int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream);
 /* Genome-side index of the off-target search, the counterpart of the `bowtie-build` index files
  * (guido/genome.py:156-171): every PAM-valid window of the uploaded shard (both strands, guide
  * orientation) grouped by its core_len PAM-proximal bases, 20 bytes per window in HBM.  Guide
