@@ -302,7 +302,11 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     # kernels per search: one host-API call reports its launches; the device sort (split + radix
     # passes + merge) belongs to that call only
     st0 = N.Stats()
-    img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st0, pinned=True, **OT_KW)
+    os.environ["GUIDO_SORT"] = "radix"  # this one call: the general sort, whose launch count is known below
+    try:
+        img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st0, pinned=True, **OT_KW)
+    finally:
+        del os.environ["GUIDO_SORT"]
     guide_bits = max(1, int(np.ceil(np.log2(max(n_guides, 2)))))
     launches_per_search = int(st0.n_launches) - (2 + (33 + guide_bits + 7) // 8 if st0.bytes_d2h >= 16 + 2 * 16 else 0)
 

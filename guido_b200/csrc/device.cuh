@@ -110,6 +110,7 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
                    unsigned long long *d_count, uint8_t *d_flags, unsigned long long *d_site_count,
                    cudaStream_t stream, int *n_launches);
 
+int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *sums, uint32_t *cursor, cudaStream_t stream);
 int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t n_guides, cudaStream_t stream,
                      int *n_launches);
 int encode_guides_device(DeviceState *ds, const char *d_letters, int64_t n, uint2 *d_out, unsigned long long *d_bad,

@@ -1026,6 +1026,18 @@ __global__ void __launch_bounds__(1024) scan_fixup_kernel(uint32_t *data, uint32
         }
 }
 
+// in-place exclusive scan of data[0 .. n) on `stream` (sums: scratch of ceil(n / 4096) words; cursor,
+// optional, n - 1 entries: a second copy of the result for fill cursors) -- used by sort.cu as well
+int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *sums, uint32_t *cursor, cudaStream_t stream) {
+    if (n == 0) return GUIDO_OK;
+    const uint32_t n_blocks = (n + 4095) / 4096;
+    scan_blocks_kernel<<<n_blocks, 1024, 0, stream>>>(data, n, sums, 0);
+    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_blocks);
+    scan_fixup_kernel<<<n_blocks, 1024, 0, stream>>>(data, n, sums, cursor, 0);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
 static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
     // all (xh, xl) with popc(xh | xl) <= cm over cl positions; per chosen position 3 substitutions
     out->clear();

@@ -79,3 +79,42 @@ def test_device_merge_single_rank_group(native):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def _random_hits(rng, n, n_guides, heavy=None):
+    """n distinct (guide, gpos, strand) records in random order; `heavy` = (guide, count) gives one
+    guide a long list"""
+    g = rng.integers(0, n_guides, n).astype(np.uint32)
+    if heavy is not None:
+        g[:heavy[1]] = heavy[0]
+    gpos = rng.permutation(np.arange(n, dtype=np.uint32) * 7 + 3)  # distinct positions
+    strand = rng.integers(0, 2, n).astype(np.uint32)
+    hits = np.zeros(n, dtype=[("guide", "<u4"), ("gpos", "<u4"), ("hi", "<u4"), ("lo", "<u4")])
+    hits["guide"], hits["gpos"] = g, gpos
+    hits["hi"] = (strand << 31) | rng.integers(0, 1 << 23, n).astype(np.uint32)
+    hits["lo"] = rng.integers(0, 1 << 23, n).astype(np.uint32)
+    return hits[rng.permutation(n)]
+
+
+@pytest.mark.parametrize("n,n_guides,heavy", [
+    (2, 1, None), (1000, 1, None), (5000, 7, None), (200000, 1000, None), (300000, 100000, None),
+    (100000, 50, (3, 4096)),      # largest segment the rank sort takes (keys read through L1)
+    (100000, 50, (3, 4097)),      # one guide above it: general radix path
+    (50000, 1 << 20, None),       # far more guides than hits: mostly empty segments
+])
+def test_sort_hits_dev_matches_lexsort(native, monkeypatch, n, n_guides, heavy):
+    import torch
+    from guido_b200.parallel import canonical_order
+    rng = np.random.default_rng(n + n_guides)
+    hits = _random_hits(rng, n, n_guides, heavy)
+    want = canonical_order(hits)
+    img = native.Image.from_seqs([("c", "ACGT" * 64)]).upload()
+    dev = torch.device("cuda", int(img.info.device))
+    s = torch.cuda.current_stream(dev).cuda_stream
+    for mode in (None, "radix"):
+        if mode:
+            monkeypatch.setenv("GUIDO_SORT", mode)
+        d = torch.from_numpy(hits.view(np.int32).reshape(-1, 4).copy()).to(dev)
+        img.sort_hits_dev(d.data_ptr(), n, n_guides, s)
+        got = d.cpu().numpy().view(np.uint32).reshape(-1).view(want.dtype)
+        assert np.array_equal(got, want), mode
