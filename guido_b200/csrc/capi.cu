@@ -48,6 +48,7 @@ int device_init(DeviceState *ds, int device) {
     GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     for (auto &e : ds->ev) GUIDO_CUDA(cudaEventCreate(&e));
     GUIDO_CUDA(cudaMalloc(&ds->d_counts, 8 * sizeof(unsigned long long)));
+    GUIDO_CUDA(cudaMemset(ds->d_counts, 0, 8 * sizeof(unsigned long long)));  // [7]: look-back gave up (pam_scan.cu)
     GUIDO_CUDA(cudaMalloc(&ds->d_tile_counter, 4 * sizeof(unsigned int)));
     return GUIDO_OK;
 }
@@ -165,9 +166,15 @@ static int scan_to_host(guido_image *img, const PamSpec &pam, int mode, const Sc
                          (uint32_t *)ds->d_out[1], (uint64_t)dcap_r, ds->d_counts, ds->stream, &launches);
     if (rc) return rc;
     GUIDO_CUDA(cudaEventRecord(ds->ev[1], ds->stream));
-    unsigned long long counts[2];
+    unsigned long long counts[2], gave_up = 0;
     GUIDO_CUDA(cudaMemcpyAsync(counts, ds->d_counts, sizeof counts, cudaMemcpyDeviceToHost, ds->stream));
+    GUIDO_CUDA(cudaMemcpyAsync(&gave_up, ds->d_counts + 7, sizeof gave_up, cudaMemcpyDeviceToHost, ds->stream));
     GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
+    if (gave_up) {
+        cudaMemsetAsync(ds->d_counts + 7, 0, sizeof gave_up, ds->stream);
+        set_error("PAM scan: a tile never published its counts (look-back gave up)");
+        return GUIDO_ERR_CUDA;
+    }
     *n_fw = (int64_t)counts[0];
     *n_rv = (int64_t)counts[1];
     int64_t cf = std::min<int64_t>(*n_fw, dcap_f), cr = std::min<int64_t>(*n_rv, dcap_r);

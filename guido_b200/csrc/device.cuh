@@ -19,7 +19,7 @@ namespace guido {
 struct DeviceState {
     int device = -1;
     int sm_count = 0;
-    int scan_grid[2] = {0, 0};  // resident-CTA grids of the PAM count / fill kernels (cached)
+    int scan_grid[3] = {0, 0, 0};  // resident-CTA grids of the PAM count / fill / one-pass kernels (cached)
     int64_t blk_lo = 0;  // first resident block (global block index), includes the halo
     int64_t blk_n = 0;   // resident blocks (+1 spare at the end so `next` loads stay in bounds)
     ulonglong2 *d_planes = nullptr;

@@ -59,6 +59,7 @@ struct PamScanArgs {
     unsigned long long *counts;   // [0] n_fw, [1] n_rv
     unsigned long long *tiles;    // n_tiles: per-tile counts, fw | rv << 32
     int vec_ok;                   // both output arrays are 16-byte aligned: copy out as uint4
+    unsigned long long *err;      // one-pass kernel: set when a look-back gave up (never expected)
 };
 
 // planes of the thread's 4 blocks + the following block, as 32-bit words (10 per plane)
@@ -448,6 +449,206 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
     }
 }
 
+// ---- one pass: tile counts and output offsets in the same kernel (decoupled look-back) ----------
+//
+// The count kernel costs a quarter of the scan and reads the planes a second time.  Here a tile is
+// scanned once: its CTA publishes the tile's hit counts as soon as they are known, warp 0 walks
+// back over the descriptors of the preceding tiles until it meets an inclusive prefix -- WHILE the
+// other warps already stage the tile's hits in shared memory, which only needs tile-local ranks --
+// and the offsets are first needed for the copy-out.  Tiles are handed out by an atomic ticket at
+// the moment a CTA is ready to start one, so every predecessor of a running tile is running or
+// done (no deadlock, and nobody waits for a tile that is merely reserved).
+//
+// descriptor = status << 62 | fw hits << 31 | rv hits; status 0 = nothing yet, 1 = the tile's own
+// counts, 2 = inclusive prefix.  31 bits per strand: launch_pam_scan takes this path only for
+// ranges below 2^31 bases.  One aligned 64-bit word, relaxed loads / stores: the word IS the data.
+constexpr unsigned long long kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1;
+constexpr uint32_t kLookbackSpins = 1u << 19;  // polls before a look-back gives up (~a second; a bug, not a load effect)
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// whole warp: packed exclusive prefix (fw << 31 | rv) of `tile` from the descriptors before it.
+// A round reads 256 descriptors (8 per lane, independent loads, one L2 round trip): tiles are
+// started at ~40 per microsecond across the GPU, so a walk of 32 descriptors per round trip never
+// catches up with the tiles that have published their counts but not yet their prefix.
+constexpr int kLookPerLane = 8;
+__device__ __forceinline__ unsigned long long look_back(const PamScanArgs &a, uint32_t tile, int lane) {
+    unsigned long long excl = 0;
+    int64_t base = (int64_t)tile - 1;
+    uint32_t spins = 0;
+    if (ld_relaxed_u64(a.err)) return 0;  // an earlier look-back gave up: the launch is lost, do not wait again
+    while (base >= 0) {
+        unsigned long long d[kLookPerLane];
+#pragma unroll
+        for (int k = 0; k < kLookPerLane; k++) {  // distance lane + 32 k: k = 0, lane 0 is the nearest predecessor
+            const int64_t idx = base - lane - 32 * k;
+            d[k] = idx >= 0 ? ld_relaxed_u64(&a.tiles[idx]) : kDescPrefix;  // before tile 0: prefix 0
+        }
+        unsigned long long v = 0;
+        bool done = false, retry = false;
+#pragma unroll
+        for (int k = 0; k < kLookPerLane; k++) {
+            if (!done && !retry) {  // warp-uniform
+                const uint32_t st = (uint32_t)(d[k] >> 62);
+                const uint32_t pmask = __ballot_sync(kFull, st == 2), imask = __ballot_sync(kFull, st == 0);
+                // lanes up to and including the nearest inclusive prefix (all 32 when there is none)
+                const uint32_t upto = pmask ? ((2u << (__ffs((int)pmask) - 1)) - 1u) : 0xffffffffu;
+                if (imask & upto) retry = true;  // a predecessor has not published yet: poll again
+                else {
+                    if ((upto >> lane) & 1u) v += d[k] & kDescValue;
+                    done = pmask != 0;
+                }
+            }
+        }
+        if (retry) {
+            if (++spins > kLookbackSpins) { if (lane == 0) atomicExch(a.err, 1ull); break; }
+            continue;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        excl += v;
+        if (done) break;
+        base -= 32 * kLookPerLane;
+    }
+    return excl;
+}
+
+// staged hits s[0, n) -> g[0, n) (g = output + tile offset, any 4-byte phase): whole uint4 stores
+// where g is 16-byte aligned; the shared side is read as two aligned uint4s and shifted by the
+// (CTA-uniform) phase
+__device__ __forceinline__ void copy_out_shifted(const uint32_t *s, uint32_t n, uint32_t *g) {
+    const uint32_t d0 = (uint32_t)((0u - (uint32_t)(reinterpret_cast<uintptr_t>(g) >> 2)) & 3u);  // elements up to alignment
+    if (n < d0 + 4u) {
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) g[i] = s[i];
+        return;
+    }
+    const uint32_t nq = (n - d0) >> 2;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+    uint4 *g4 = reinterpret_cast<uint4 *>(g + d0);
+    if (d0 == 0) {
+        for (uint32_t q = threadIdx.x; q < nq; q += kThreads) g4[q] = s4[q];
+    } else if (d0 == 1) {
+        for (uint32_t q = threadIdx.x; q < nq; q += kThreads) { const uint4 x = s4[q], y = s4[q + 1]; g4[q] = make_uint4(x.y, x.z, x.w, y.x); }
+    } else if (d0 == 2) {
+        for (uint32_t q = threadIdx.x; q < nq; q += kThreads) { const uint4 x = s4[q], y = s4[q + 1]; g4[q] = make_uint4(x.z, x.w, y.x, y.y); }
+    } else {
+        for (uint32_t q = threadIdx.x; q < nq; q += kThreads) { const uint4 x = s4[q], y = s4[q + 1]; g4[q] = make_uint4(x.w, y.x, y.y, y.z); }
+    }
+    if (threadIdx.x < d0) g[threadIdx.x] = s[threadIdx.x];
+    const uint32_t t = d0 + 4u * nq + threadIdx.x;
+    if (t < n) g[t] = s[t];
+}
+
+__global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanArgs a) {
+    __shared__ unsigned long long s_warp[kThreads / 32];
+    __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_ticket;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    ulonglong2 *s_planes = reinterpret_cast<ulonglong2 *>(s_dyn);
+    uint32_t (*s_stage)[kStage + 8] = reinterpret_cast<uint32_t (*)[kStage + 8]>(s_dyn + kFillPlaneBytes);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sa_f = (uint32_t)__cvta_generic_to_shared(s_stage[0]);
+    const uint32_t sa_r = (uint32_t)__cvta_generic_to_shared(s_stage[1]);
+    unsigned long long *ticket = a.tiles + a.n_tiles;
+    if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(ticket, 1ull);
+    __syncthreads();
+    uint32_t tile = s_ticket;
+    while (tile < a.n_tiles) {
+        stage_issue(a.pv, tile_block0(a, tile), lane, s_planes);
+        {   // tickets run ahead of this tile by about one grid: pull that tile's planes into L2 (the next
+            // tile of THIS CTA is not known yet, so its planes cannot be requested into shared memory)
+            const int64_t i = tile_block0(a, tile + gridDim.x) - a.pv.blk_lo;
+            if (tile + gridDim.x < a.n_tiles && i >= 0 && i + kBpt <= a.pv.blk_n)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pv.planes + i));
+        }
+        ThreadRaw raw;
+        stage_read(s_planes, lane, raw);
+        uint32_t hf[kWpt], hr[kWpt];
+        tile_hit_words(a, tile, raw, hf, hr);
+        const unsigned long long mine = popc_words(hf, hr);  // fw | rv << 32
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();  // (1)
+        unsigned long long warp_prefix = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) {
+            const unsigned long long x = s_warp[w];
+            if (w < warp) warp_prefix += x;
+            total += x;
+        }
+        const uint32_t agg_f = (uint32_t)total, agg_r = (uint32_t)(total >> 32);
+        const unsigned long long agg = ((unsigned long long)agg_f << 31) | agg_r;
+        if (threadIdx.x == 0) st_relaxed_u64(&a.tiles[tile], (tile ? kDescAgg : kDescPrefix) | agg);
+        const unsigned long long excl = warp_prefix + inc - mine;
+        const int64_t block0 = (int64_t)(a.first_tile + tile) * kScanTileBlocks + threadIdx.x * kBpt;
+        const uint32_t base = (uint32_t)(block0 * 64) - a.r.out_base;
+        uint32_t of = (uint32_t)excl, orv = (uint32_t)(excl >> 32);
+        const bool stage_f = agg_f <= kStage, stage_r = agg_r <= kStage;
+        const bool direct = !(stage_f && stage_r);  // unusually dense tile: offsets are needed before the emission
+        auto resolve_prefix = [&]() {  // warp 0: exclusive prefix of this tile -> s_excl, inclusive prefix published
+            const unsigned long long ex = tile ? look_back(a, tile, lane) : 0ull;
+            if (lane == 0) {
+                if (tile) st_relaxed_u64(&a.tiles[tile], kDescPrefix | (ex + agg));
+                s_excl = ex;
+            }
+        };
+        // The look-back runs AFTER warp 0 has staged its own hits: by then the tiles just before
+        // this one -- started at almost the same moment -- have published their counts, so it
+        // walks instead of waiting, and the walk is all the other warps ever wait for.
+        if (direct) {
+            if (warp == 0) resolve_prefix();
+            __syncthreads();
+        }
+        if (stage_f) {
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) of = emit_word_staged(hf[w], base + 32 * w, sa_f, of);
+        }
+        if (stage_r) {
+#pragma unroll
+            for (int w = 0; w < kWpt; w++) orv = emit_word_staged(hr[w], base + 32 * w, sa_r, orv);
+        }
+        if (direct) {
+            const unsigned long long ex = s_excl;
+            const unsigned long long ef = ex >> 31, er = ex & 0x7fffffffull;
+            if (!stage_f && ef + agg_f <= a.cap_fw) {
+#pragma unroll
+                for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, a.out_fw + ef, of);
+            }
+            if (!stage_r && er + agg_r <= a.cap_rv) {
+#pragma unroll
+                for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, a.out_rv + er, orv);
+            }
+        }
+        if (!direct && warp == 0) resolve_prefix();
+        __syncthreads();  // (2) hits are staged, s_excl is there
+        const unsigned long long ex = s_excl;
+        const unsigned long long ef = ex >> 31, er = ex & 0x7fffffffull;
+        // the next ticket travels while this tile is copied out
+        if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(ticket, 1ull);
+        // capacity: a tile is written completely or not at all (the counts stay exact either way)
+        if (stage_f && ef + agg_f <= a.cap_fw) copy_out_shifted(s_stage[0], agg_f, a.out_fw + ef);
+        if (stage_r && er + agg_r <= a.cap_rv) copy_out_shifted(s_stage[1], agg_r, a.out_rv + er);
+        if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
+            a.counts[0] = ef + agg_f;
+            a.counts[1] = er + agg_r;
+        }
+        __syncthreads();  // (3) stage, s_warp, s_excl and the plane buffer are free again; the ticket is visible
+        tile = s_ticket;
+    }
+}
+
 static void make_coef(const PamSpec &pam, PamCoef *pc) {
     pc->len = pam.len;
     for (int strand = 0; strand < 2; strand++) {
@@ -485,7 +686,7 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
     a.out_fw = d_fw; a.out_rv = d_rv; a.cap_fw = cap_fw; a.cap_rv = cap_rv;
     a.counts = d_counts;
     a.vec_ok = ((reinterpret_cast<uintptr_t>(d_fw) | reinterpret_cast<uintptr_t>(d_rv)) & 15) == 0;
-    int64_t need = (int64_t)a.n_tiles;
+    int64_t need = (int64_t)a.n_tiles + 1;  // + the ticket counter of the one-pass kernel
     if (need > ds->desc_cap) {
         if (ds->d_desc) cudaFree(ds->d_desc);
         ds->d_desc = nullptr; ds->desc_cap = 0;
@@ -493,6 +694,7 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         ds->desc_cap = need;
     }
     a.tiles = ds->d_desc;
+    a.err = ds->d_counts + 7;
     if (ds->scan_grid[0] == 0) {
         int per_sm = 0;
         GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_count_kernel, kThreads, 0));
@@ -500,14 +702,27 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         GUIDO_CUDA(cudaFuncSetAttribute(pam_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFillSmemBytes));
         GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_fill_kernel, kThreads, kFillSmemBytes));
         ds->scan_grid[1] = ds->sm_count * std::max(per_sm, 1);
+        GUIDO_CUDA(cudaFuncSetAttribute(pam_onepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFillSmemBytes));
+        GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pam_onepass_kernel, kThreads, kFillSmemBytes));
+        ds->scan_grid[2] = ds->sm_count * std::max(per_sm, 1);
     }
-    GUIDO_CUDA(cudaMemsetAsync(a.tiles, 0, (size_t)a.n_tiles * sizeof(unsigned long long), stream));
+    GUIDO_CUDA(cudaMemsetAsync(a.tiles, 0, (size_t)(a.n_tiles + 1) * sizeof(unsigned long long), stream));
+    // One pass (look-back) when the descriptors' 31-bit counters cannot overflow and there are
+    // enough tiles to matter; count -> fill otherwise.  GUIDO_PAM_PASSES=1/2 forces either (tests).
+    const char *force = getenv("GUIDO_PAM_PASSES");
+    const bool small = (uint64_t)a.n_tiles * kScanTileBases < (1ull << 31);
+    const bool one_pass = force ? (atoi(force) == 1 && small) : small;
     kev_begin(ds, stream);
-    pam_count_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[0]), kThreads, 0, stream>>>(a);
-    pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, kFillSmemBytes, stream>>>(a);
+    if (one_pass) {
+        // every CTA of the grid must be resident: a tile only ever waits for tiles that are running
+        pam_onepass_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[2]), kThreads, kFillSmemBytes, stream>>>(a);
+    } else {
+        pam_count_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[0]), kThreads, 0, stream>>>(a);
+        pam_fill_kernel<<<(int)std::min<int64_t>(a.n_tiles, ds->scan_grid[1]), kThreads, kFillSmemBytes, stream>>>(a);
+    }
     kev_end(ds, stream);
     GUIDO_CUDA(cudaGetLastError());
-    if (n_launches) *n_launches += 2;
+    if (n_launches) *n_launches += one_pass ? 1 : 2;
     return GUIDO_OK;
 }
 

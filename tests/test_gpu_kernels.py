@@ -374,3 +374,27 @@ def test_offtarget_join_big_buckets(native, monkeypatch, sliced):
     merged = np.concatenate([c, d])
     merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
     assert np.array_equal(merged, a)
+
+
+@pytest.mark.parametrize("pam,mode", [("NGG", 0), ("NGG", 2), ("TTTV", 1), ("N", 0), ("NNGRRT", 2)])
+def test_pam_scan_one_pass_equals_two_pass(native, monkeypatch, pam, mode):
+    """The single-pass (look-back) kernel and the count -> fill pair must return the same lists:
+    ~700 tiles (several look-back rounds per tile), N runs across tile borders, and 'N' as the PAM
+    (every position a hit: the dense, unstaged write path of both kernels)."""
+    img = native.Image.synth([30_000_000, 12_345_678, 3_000_001, 70_000], seed=77, n_frac=0.01).upload()
+    monkeypatch.setenv("GUIDO_PAM_PASSES", "2")
+    fw2, rv2 = img.pam_scan_genome(pam, mode)
+    monkeypatch.setenv("GUIDO_PAM_PASSES", "1")
+    for _ in range(3):  # repeated: descriptors and the ticket are reset per launch
+        fw1, rv1 = img.pam_scan_genome(pam, mode)
+        assert np.array_equal(fw1, fw2) and np.array_equal(rv1, rv2)
+    assert len(fw2) > 100000 and np.all(np.diff(fw2.astype(np.int64)) > 0)
+    # capacity too small: exact counts come back, nothing is written past the caller's buffers
+    import ctypes
+    cap = len(fw2) // 2
+    fw, rv = np.full(cap + 8, 0xdeadbeef, np.uint32), np.full(cap + 8, 0xdeadbeef, np.uint32)
+    nf, nr = ctypes.c_int64(), ctypes.c_int64()
+    rc = native.lib().guido_pam_scan_genome(img._h, pam.encode(), mode, fw.ctypes.data, cap, ctypes.byref(nf),
+                                            rv.ctypes.data, cap, ctypes.byref(nr), None)
+    assert rc == native.ERR_CAPACITY and nf.value == len(fw2) and nr.value == len(rv2)
+    assert np.all(fw[cap:] == 0xdeadbeef) and np.all(rv[cap:] == 0xdeadbeef)
