@@ -546,6 +546,13 @@ __device__ __forceinline__ void copy_out_shifted(const uint32_t *s, uint32_t n, 
     if (t < n) g[t] = s[t];
 }
 
+// Software pipeline over the CTA's tiles: the COUNT of tile n+1 (load, hit words, scan, counts
+// published) runs before the look-back and copy-out of tile n, whose hits wait in the stage.  A
+// look-back therefore starts a whole phase after its own tile's counts went out, when the tiles
+// just before it -- started at almost the same moment, but with a long-tailed time to their counts
+// (N-run veto, DRAM latency) -- have long published theirs: it walks (1-2 rounds) and never polls.
+// Measured with %globaltimer stamps: ticket -> counts 3.5 us (p99 8.4), look-back right after the
+// tile's own staging 3.3 us, of which > 2 us was waiting for the slowest of ~300 predecessors.
 __global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanArgs a) {
     __shared__ unsigned long long s_warp[kThreads / 32];
     __shared__ unsigned long long s_excl;
@@ -560,56 +567,90 @@ __global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanA
     if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(ticket, 1ull);
     __syncthreads();
     uint32_t tile = s_ticket;
-    while (tile < a.n_tiles) {
-        stage_issue(a.pv, tile_block0(a, tile), lane, s_planes);
-        {   // tickets run ahead of this tile by about one grid: pull that tile's planes into L2 (the next
-            // tile of THIS CTA is not known yet, so its planes cannot be requested into shared memory)
-            const int64_t i = tile_block0(a, tile + gridDim.x) - a.pv.blk_lo;
-            if (tile + gridDim.x < a.n_tiles && i >= 0 && i + kBpt <= a.pv.blk_n)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pv.planes + i));
+    // the pending tile: staged (or, if dense, already written), waiting for its offsets and copy-out
+    bool pend = false, p_stage_f = false, p_stage_r = false, p_resolved = false;
+    uint32_t p_tile = 0, p_agg_f = 0, p_agg_r = 0;
+    unsigned long long p_ex = 0;
+
+    // warp 0: exclusive prefix of tile t (own counts `agg`) -> s_excl; inclusive prefix published
+    auto resolve_prefix = [&](uint32_t t, unsigned long long agg) {
+        const unsigned long long ex = t ? look_back(a, t, lane) : 0ull;
+        if (lane == 0) {
+            if (t) st_relaxed_u64(&a.tiles[t], kDescPrefix | (ex + agg));
+            s_excl = ex;
         }
-        ThreadRaw raw;
-        stage_read(s_planes, lane, raw);
+    };
+
+    for (;;) {
+        const bool have = tile < a.n_tiles;  // CTA-uniform
+        if (!have && !pend) break;
         uint32_t hf[kWpt], hr[kWpt];
-        tile_hit_words(a, tile, raw, hf, hr);
-        const unsigned long long mine = popc_words(hf, hr);  // fw | rv << 32
-        unsigned long long inc = mine;
+        unsigned long long mine = 0, inc = 0;
+        if (have) {
+            stage_issue(a.pv, tile_block0(a, tile), lane, s_planes);
+            {   // tickets run ahead of this tile by about one grid: pull that tile's planes into L2 (the
+                // next tile of THIS CTA is not known yet, so its planes cannot be requested into shared memory)
+                const int64_t i = tile_block0(a, tile + gridDim.x) - a.pv.blk_lo;
+                if (tile + gridDim.x < a.n_tiles && i >= 0 && i + kBpt <= a.pv.blk_n)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pv.planes + i));
+            }
+            ThreadRaw raw;
+            stage_read(s_planes, lane, raw);
+            tile_hit_words(a, tile, raw, hf, hr);
+            mine = popc_words(hf, hr);  // fw | rv << 32
+            inc = mine;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long t = __shfl_up_sync(kFull, inc, d);
-            if (lane >= d) inc += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long t = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += t;
+            }
+            if (lane == 31) s_warp[warp] = inc;
         }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();  // (1)
+        __syncthreads();  // (1) warp totals are there; every warp has finished staging the pending tile
         unsigned long long warp_prefix = 0, total = 0;
+        if (have) {
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; w++) {
-            const unsigned long long x = s_warp[w];
-            if (w < warp) warp_prefix += x;
-            total += x;
+            for (int w = 0; w < kThreads / 32; w++) {
+                const unsigned long long x = s_warp[w];
+                if (w < warp) warp_prefix += x;
+                total += x;
+            }
         }
         const uint32_t agg_f = (uint32_t)total, agg_r = (uint32_t)(total >> 32);
         const unsigned long long agg = ((unsigned long long)agg_f << 31) | agg_r;
-        if (threadIdx.x == 0) st_relaxed_u64(&a.tiles[tile], (tile ? kDescAgg : kDescPrefix) | agg);
+        if (have && threadIdx.x == 0) st_relaxed_u64(&a.tiles[tile], (tile ? kDescAgg : kDescPrefix) | agg);
+
+        if (pend) {  // offsets and copy-out of the tile staged one iteration ago
+            if (!p_resolved) {
+                if (warp == 0) resolve_prefix(p_tile, ((unsigned long long)p_agg_f << 31) | p_agg_r);
+                __syncthreads();  // (2)
+                p_ex = s_excl;
+            }
+            const unsigned long long ef = p_ex >> 31, er = p_ex & 0x7fffffffull;
+            // capacity: a tile is written completely or not at all (the counts stay exact either way)
+            if (p_stage_f && ef + p_agg_f <= a.cap_fw) copy_out_shifted(s_stage[0], p_agg_f, a.out_fw + ef);
+            if (p_stage_r && er + p_agg_r <= a.cap_rv) copy_out_shifted(s_stage[1], p_agg_r, a.out_rv + er);
+            if (p_tile == a.n_tiles - 1 && threadIdx.x == 0) {
+                a.counts[0] = ef + p_agg_f;
+                a.counts[1] = er + p_agg_r;
+            }
+            __syncthreads();  // (3) the stage is free again (and s_excl has been read)
+            pend = false;
+        }
+        if (!have) continue;  // (ends the loop: nothing pending any more)
+
+        // the next ticket travels while this tile's hits are staged
+        if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(ticket, 1ull);
         const unsigned long long excl = warp_prefix + inc - mine;
         const int64_t block0 = (int64_t)(a.first_tile + tile) * kScanTileBlocks + threadIdx.x * kBpt;
         const uint32_t base = (uint32_t)(block0 * 64) - a.r.out_base;
         uint32_t of = (uint32_t)excl, orv = (uint32_t)(excl >> 32);
         const bool stage_f = agg_f <= kStage, stage_r = agg_r <= kStage;
-        const bool direct = !(stage_f && stage_r);  // unusually dense tile: offsets are needed before the emission
-        auto resolve_prefix = [&]() {  // warp 0: exclusive prefix of this tile -> s_excl, inclusive prefix published
-            const unsigned long long ex = tile ? look_back(a, tile, lane) : 0ull;
-            if (lane == 0) {
-                if (tile) st_relaxed_u64(&a.tiles[tile], kDescPrefix | (ex + agg));
-                s_excl = ex;
-            }
-        };
-        // The look-back runs AFTER warp 0 has staged its own hits: by then the tiles just before
-        // this one -- started at almost the same moment -- have published their counts, so it
-        // walks instead of waiting, and the walk is all the other warps ever wait for.
-        if (direct) {
-            if (warp == 0) resolve_prefix();
+        const bool direct = !(stage_f && stage_r);  // unusually dense tile: written straight from registers,
+        if (direct) {                                // so its offsets are needed now
+            if (warp == 0) resolve_prefix(tile, agg);
             __syncthreads();
+            p_ex = s_excl;
         }
         if (stage_f) {
 #pragma unroll
@@ -620,8 +661,7 @@ __global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanA
             for (int w = 0; w < kWpt; w++) orv = emit_word_staged(hr[w], base + 32 * w, sa_r, orv);
         }
         if (direct) {
-            const unsigned long long ex = s_excl;
-            const unsigned long long ef = ex >> 31, er = ex & 0x7fffffffull;
+            const unsigned long long ef = p_ex >> 31, er = p_ex & 0x7fffffffull;
             if (!stage_f && ef + agg_f <= a.cap_fw) {
 #pragma unroll
                 for (int w = 0; w < kWpt; w++) of = emit_word(hf[w], base + 32 * w, a.out_fw + ef, of);
@@ -631,20 +671,9 @@ __global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanA
                 for (int w = 0; w < kWpt; w++) orv = emit_word(hr[w], base + 32 * w, a.out_rv + er, orv);
             }
         }
-        if (!direct && warp == 0) resolve_prefix();
-        __syncthreads();  // (2) hits are staged, s_excl is there
-        const unsigned long long ex = s_excl;
-        const unsigned long long ef = ex >> 31, er = ex & 0x7fffffffull;
-        // the next ticket travels while this tile is copied out
-        if (threadIdx.x == 0) s_ticket = (uint32_t)atomicAdd(ticket, 1ull);
-        // capacity: a tile is written completely or not at all (the counts stay exact either way)
-        if (stage_f && ef + agg_f <= a.cap_fw) copy_out_shifted(s_stage[0], agg_f, a.out_fw + ef);
-        if (stage_r && er + agg_r <= a.cap_rv) copy_out_shifted(s_stage[1], agg_r, a.out_rv + er);
-        if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
-            a.counts[0] = ef + agg_f;
-            a.counts[1] = er + agg_r;
-        }
-        __syncthreads();  // (3) stage, s_warp, s_excl and the plane buffer are free again; the ticket is visible
+        pend = true; p_tile = tile; p_agg_f = agg_f; p_agg_r = agg_r;
+        p_stage_f = stage_f; p_stage_r = stage_r; p_resolved = direct;
+        __syncthreads();  // (4) the ticket is visible (s_warp / the plane buffer are free as well)
         tile = s_ticket;
     }
 }
