@@ -3,15 +3,18 @@
 // Sits under Locus._find_guides_in_interval (reference guido/locus.py:178-183): the two
 // overlapping `re.finditer` passes become two streaming passes over the bit-plane image.
 //
-// Two launches, no inter-CTA waiting anywhere:
-//   pam_count_kernel  per tile (1024 blocks = 65536 bases): hit masks -> popcounts -> tile counts
+// One launch (pam_onepass_kernel, ranges below 2^31 bases): per tile (1024 blocks = 65536 bases) hit
+// masks -> popcounts -> tile counts published in a descriptor -> hits staged in shared memory ->
+// output offset from a decoupled look-back over the preceding tiles' descriptors -> coalesced
+// stores.  The loop is software pipelined so that a look-back walks instead of polling (see the
+// kernel).  Larger ranges use two launches without any inter-CTA waiting:
+//   pam_count_kernel  per tile: hit masks -> popcounts -> tile counts
 //   pam_fill_kernel   per tile: hit masks again (the planes come from L2 when the shard fits,
 //                     else from HBM); the tile's output offset is the running sum of the tile
 //                     counts (each CTA adds the counts of the tiles it strides over); CTA prefix
 //                     sum; hits staged in shared memory; coalesced 4-byte stores
-// A single-pass chained scan (decoupled look-back) was built first and rejected: with every
-// resident CTA on a tile of the same wave, the look-back polls hundreds of descriptors per tile
-// and the polling traffic alone saturated L2 (profiles/r1_pam_scan.md).
+// (History of the single-pass form -- a first version polled ~1200 descriptors per tile and lost
+// to count -> fill; what made it work is in profiles/r1_pam_scan.md, section F.)
 //
 // A thread owns 4 consecutive blocks (256 bases), handled as eight 32-bit words per plane:
 //   * two 256-bit loads (LDG.E.256) fetch its 64 bytes of {lo,hi} words; the next block (the
