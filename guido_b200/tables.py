@@ -221,6 +221,18 @@ class OffTargetTable:
             mean = np.where(n > 0, total / np.maximum(n, 1), np.nan)
         return mean, best, np.where(n > 0, total, np.nan)
 
+    def annotate(self, annotation, features=("CDS", "exon", "transcript", "gene")):
+        """Per-hit annotation (DataFrame: guide, chromosome, start, strand, feature, id): the most
+        specific feature of ``annotation`` -- a table from ``guido_b200.annotation.read_annotation``
+        or ``Genome.annotation`` -- that the 23-nt (20 + PAM) target overlaps, ``"intergenic"``
+        otherwise.  SURVEY §8(f) row 4; vectorised, see ``annotation.annotate_intervals``."""
+        import pandas as pd
+        from .annotation import annotate_intervals
+        lab = annotate_intervals(annotation, self.chromosome, self.start, self.start + self.width, features)
+        return pd.DataFrame({"guide": self.guide, "chromosome": self.chromosome, "start": self.start,
+                             "strand": np.where(self.strand_minus, "-", "+"),
+                             "feature": lab["feature"].to_numpy(), "id": lab["id"].to_numpy()})
+
     def records(self, ix):
         """the reference's list of off-target dicts for guide ``ix`` (no ``cfd_score``)"""
         P = len(self.pam)

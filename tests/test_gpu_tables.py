@@ -89,3 +89,18 @@ def test_offtarget_table_equals_run_bowtie(tmp_path):
             assert np.isclose(tot[ix], guides[ix].layers["ot_cfd_score_sum"], rtol=1e-12, atol=0)
         else:
             assert np.isnan(mean[ix]) and np.isnan(best[ix])
+    # hits against an annotation: the planted copy on chr2 lies in a "gene"
+    import pandas as pd
+    c2 = contigs[1][0]
+    ann = pd.DataFrame([dict(Chromosome=c2, Feature="gene", Start=4990, End=5810, ID="planted"),
+                        dict(Chromosome=c2, Feature="exon", Start=5100, End=5200, ID="planted")])
+    lab = t.annotate(ann)
+    assert len(lab) == len(t) and list(lab.columns) == ["guide", "chromosome", "start", "strand", "feature", "id"]
+    on2 = (t.chromosome == c2)
+    inside = on2 & (t.start < 5810) & (t.start + 23 > 4990)
+    in_exon = on2 & (t.start < 5200) & (t.start + 23 > 5100)
+    assert inside.sum() > 20 and in_exon.sum() > 0
+    assert np.array_equal(lab.feature.to_numpy() == "exon", in_exon)
+    assert np.array_equal(lab.feature.to_numpy() == "gene", inside & ~in_exon)
+    assert np.array_equal(lab.feature.to_numpy() == "intergenic", ~inside)
+    assert set(lab.id[inside]) == {"planted"} and set(lab.id[~inside]) <= {""}

@@ -234,3 +234,51 @@ def test_locus_factories(tmp_path, cpu_fakes):
     with pytest.raises(ValueError, match="not found"):
         guido.locus_from_gene(g, "NOPE")
     assert guido.locus_from_sequence("ACGT", "s").chromosome == "s"
+
+
+def test_annotate_intervals_matches_brute_force(tmp_path):
+    """hits labelled with the annotation they fall into; the vectorised lookup
+    against a plain per-hit filter over a GTF written to disk and read back (0-based Start)."""
+    from guido_b200.annotation import annotate_intervals, read_annotation, renamed
+    rng = np.random.default_rng(3)
+    lines = []
+    for c in ("chr1", "chr2"):
+        for g in range(30):
+            s = int(rng.integers(1, 60000))
+            e = s + int(rng.integers(500, 4000))
+            lines.append(f'{c}\tsyn\tgene\t{s}\t{e}\t.\t+\t.\tgene_id "{c}g{g}";')
+            for x in range(3):
+                a = s + int(rng.integers(0, e - s - 50))
+                b = min(e, a + int(rng.integers(30, 300)))
+                lines.append(f'{c}\tsyn\texon\t{a}\t{b}\t.\t+\t.\tgene_id "{c}g{g}"; exon_number "{x + 1}";')
+                if x == 0:
+                    lines.append(f'{c}\tsyn\tCDS\t{a + 3}\t{b - 3}\t.\t+\t0\tgene_id "{c}g{g}";')
+    path = tmp_path / "a.gtf"
+    path.write_text("\n".join(lines) + "\n")
+    for df in (read_annotation(path), renamed(read_annotation(path), path)):
+        idc = "ID" if "ID" in df.columns else "gene_id"
+        n = 500
+        ch = rng.choice(["chr1", "chr2", "chrX"], n)
+        st = rng.integers(0, 66000, n)
+        en = st + 23
+        out = annotate_intervals(df, ch, st, en)
+        assert len(out) == n
+        for i in range(n):
+            want = ("intergenic", "")
+            for ft in ("CDS", "exon", "transcript", "gene"):
+                sub = df[(df.Chromosome == ch[i]) & (df.Feature == ft) & (df.Start < en[i]) & (df.End > st[i])]
+                if len(sub):
+                    want = (ft, sub.sort_values("Start", kind="stable").iloc[0][idc])
+                    break
+            assert (out.feature[i], out.id[i]) == want, i
+        assert set(out.feature) == {"intergenic", "gene", "exon", "CDS"}
+    # edges: touching intervals do not overlap (End exclusive), empty inputs, empty annotation
+    df = read_annotation(path)
+    g0 = df[df.Feature == "gene"].iloc[0]
+    o = annotate_intervals(df, [g0.Chromosome] * 2, [g0.End, g0.Start - 23], [g0.End + 23, g0.Start], features=("gene",))
+    others = df[(df.Feature == "gene") & (df.Chromosome == g0.Chromosome)]
+    for k, (a, b) in enumerate([(g0.End, g0.End + 23), (g0.Start - 23, g0.Start)]):
+        expect = "gene" if ((others.Start < b) & (others.End > a)).any() else "intergenic"
+        assert o.feature[k] == expect
+    assert len(annotate_intervals(df, [], [], [])) == 0
+    assert list(annotate_intervals(df.iloc[:0], ["chr1"], [5], [28]).feature) == ["intergenic"]
