@@ -118,3 +118,22 @@ def test_sort_hits_dev_matches_lexsort(native, monkeypatch, n, n_guides, heavy):
         img.sort_hits_dev(d.data_ptr(), n, n_guides, s)
         got = d.cpu().numpy().view(np.uint32).reshape(-1).view(want.dtype)
         assert np.array_equal(got, want), mode
+
+
+@pytest.mark.parametrize("sliced", ["0", "1"])
+def test_join_schedules_agree(native, monkeypatch, sliced):
+    """The join launched slice by slice next to the index build (default) and as one launch after
+    the build (GUIDO_OT_OVERLAP=0, bench.py's roofline pass) return the same list; so do several
+    index slices (GUIDO_IDX_SLICE_MB=1, small enough to cut this index into the maximum of 32)."""
+    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    img, protos = _case(native, seed=31, n=400)
+    want, wf = img.offtarget_search(protos, algo=native.OT_SCAN)
+    for env in ({}, {"GUIDO_OT_OVERLAP": "0"}, {"GUIDO_IDX_SLICE_MB": "1"},
+                {"GUIDO_IDX_SLICE_MB": "1", "GUIDO_OT_OVERLAP": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for _ in range(2):  # back to back: events and streams are reused
+            got, gf = img.offtarget_search(protos, algo=native.OT_TABLE)
+            assert np.array_equal(got, want) and np.array_equal(gf, wf), env
+        for k in env:
+            monkeypatch.delenv(k)
