@@ -946,6 +946,71 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
     }
 }
 
+// ---- bucket sizes without 436 atomics per guide ---------------------------------------------------
+//
+// counts[key] = number of guides whose core is within <= core_mm substitutions of `key` = the exact
+// histogram of the guides' own cores convolved with a Hamming ball.  The histogram pass above does
+// that with one atomic per (guide, variant) -- 43.6 M L2 atomics, 0.19 ms that nothing else in the
+// search can overlap.  The convolution factorises over the core positions:
+//     g_j[key] = number of guides that differ from key in exactly j of the positions handled so far
+//     position p:  g_j[key] += sum over the 3 other letters c of g_{j-1}[key with position p := c]
+// (levels updated from the highest down, so g_{j-1} is still the previous step's).  Two kernels, the
+// low half of the positions and the high half: a CTA holds every key that differs from its tile only
+// in "its" positions -- 4^5 keys x (core_mm + 1) levels for a 10-base core -- in shared memory and
+// runs its positions there.  One atomic per guide (the exact histogram), ~40 MB of L2 traffic.
+constexpr int kDpMaxKeys = 1024;  // 4^5: cores up to 10 bases
+
+__global__ void __launch_bounds__(256) core_hist_kernel(const uint2 *guides, uint32_t n_guides, int cl, int dl, uint32_t *level0) {
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= n_guides) return;
+    const uint2 G = __ldg(&guides[g]);
+    const uint32_t cmask = (1u << cl) - 1;
+    atomicAdd(&level0[(((G.x >> dl) & cmask) << cl) | ((G.y >> dl) & cmask)], 1u);
+}
+
+// kHigh = false: positions [0, h) of the core, one tile per value of the other positions' bits;
+// levels[0] is read, levels[1 .. cm] are written.  kHigh = true: positions [h, cl); all levels are
+// read and their sum goes to counts[] (0 outside the handle's share of the key space).
+template <bool kHigh>
+__global__ void __launch_bounds__(256) ball_count_kernel(uint32_t *levels, uint32_t n_buckets, int cl, int h, int cm,
+                                                         uint32_t *counts, bool part_on, uint32_t part_shift, uint32_t part_ix) {
+    __shared__ uint32_t s[4][kDpMaxKeys];
+    const int w = kHigh ? cl - h : h;       // positions handled here
+    const int o = kHigh ? h : cl - h;       // positions fixed by the tile
+    const uint32_t n_local = 1u << (2 * w);
+    const uint32_t t_hi = blockIdx.x >> o, t_lo = blockIdx.x & ((1u << o) - 1u);
+    auto key_of = [&](uint32_t x) {
+        const uint32_t x_hi = x >> w, x_lo = x & ((1u << w) - 1u);
+        const uint32_t hi = kHigh ? ((x_hi << h) | t_hi) : ((t_hi << h) | x_hi);
+        const uint32_t lo = kHigh ? ((x_lo << h) | t_lo) : ((t_lo << h) | x_lo);
+        return (hi << cl) | lo;
+    };
+    for (uint32_t x = threadIdx.x; x < n_local; x += 256) {
+        const uint32_t key = key_of(x);
+        s[0][x] = levels[key];
+        for (int j = 1; j <= cm; j++) s[j][x] = kHigh ? levels[(size_t)j * n_buckets + key] : 0u;
+    }
+    for (int p = 0; p < w; p++) {
+        const uint32_t b_lo = 1u << p, b_hi = 1u << (w + p);
+        for (int j = cm; j >= 1; j--) {
+            __syncthreads();  // level j - 1 is complete for this step (and the loads above are done)
+            for (uint32_t x = threadIdx.x; x < n_local; x += 256)
+                s[j][x] += s[j - 1][x ^ b_lo] + s[j - 1][x ^ b_hi] + s[j - 1][x ^ b_lo ^ b_hi];
+        }
+    }
+    __syncthreads();
+    for (uint32_t x = threadIdx.x; x < n_local; x += 256) {
+        const uint32_t key = key_of(x);
+        if (kHigh) {
+            uint32_t c = 0;
+            for (int j = 0; j <= cm; j++) c += s[j][x];
+            counts[key] = (!part_on || (key >> part_shift) == part_ix) ? c : 0u;
+        } else {
+            for (int j = 1; j <= cm; j++) levels[(size_t)j * n_buckets + key] = s[j][x];
+        }
+    }
+}
+
 // in-place exclusive scan of n u32 values: 4096 per block, then the block sums, then the fix-up
 // With pad = 8 or 32 every value is rounded up to a multiple of pad before it is scanned (bucket
 // starts stay aligned for the 256-bit key loads / for whole 32-key blocks) and the padding
@@ -1148,7 +1213,12 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const uint64_t n_entries = (uint64_t)variants.size() * (uint64_t)n_guides;
     const uint32_t n_scan = n_buckets + 1, n_scan_blocks = (n_scan + 4095) / 4096;
     // d_bucket: [counts/offsets n_buckets+1][fill n_buckets][block sums][variants]
-    const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16;
+    // bucket sizes by the Hamming-ball convolution (ball_count_kernel) when a half core fits its
+    // shared-memory tile; GUIDO_IDX_HIST=atomic forces the histogram pass (tests, comparisons)
+    const char *hist_mode = getenv("GUIDO_IDX_HIST");
+    const bool dp_counts = cl <= 10 && op.core_max >= 1 && op.core_max <= 3 && !(hist_mode && hist_mode[0] == 'a');
+    const int64_t level_words = dp_counts ? (int64_t)(op.core_max + 1) * n_buckets : 0;
+    const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
     // every bucket is padded to a multiple of 8 slots (32 when sliced); worst case allocated
@@ -1194,7 +1264,19 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
     const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
-    idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
+    int n_count_launches = 1;
+    if (dp_counts) {
+        uint32_t *levels = d_var + ((variants.size() + 15) & ~(size_t)15);
+        const int h = cl / 2;
+        GUIDO_CUDA(cudaMemsetAsync(levels, 0, (size_t)n_buckets * 4, stream));
+        core_hist_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, levels);
+        ball_count_kernel<false><<<1u << (2 * (cl - h)), 256, 0, stream>>>(levels, n_buckets, cl, h, op.core_max, nullptr, false, 0, 0);
+        ball_count_kernel<true><<<1u << (2 * h), 256, 0, stream>>>(levels, n_buckets, cl, h, op.core_max, counts, ia.part_on,
+                                                                   ia.part_shift, ia.part_ix);
+        n_count_launches = 3;
+    } else {
+        idx_build_kernel<false><<<bgrid, 256, 0, stream>>>(ia);
+    }
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, pad - 1);
@@ -1218,7 +1300,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         GUIDO_CUDA(cudaGetLastError());
         if (after_slice && (rc = (*after_slice)(key_lo, key_hi))) return rc;
     }
-    if (n_launches) *n_launches += 4 + (int)per_part * (sliced ? 3 : 1);
+    if (n_launches) *n_launches += 3 + n_count_launches + (int)per_part * (sliced ? 3 : 1);
     return GUIDO_OK;
 }
 

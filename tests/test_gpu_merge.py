@@ -137,3 +137,34 @@ def test_join_schedules_agree(native, monkeypatch, sliced):
             assert np.array_equal(got, want) and np.array_equal(gf, wf), env
         for k in env:
             monkeypatch.delenv(k)
+
+
+@pytest.mark.parametrize("cl,cm,tm", [(10, 2, 4), (10, 1, 3), (10, 3, 4), (9, 2, 4), (7, 2, 3), (6, 1, 2), (10, 0, 2), (11, 2, 4)])
+def test_bucket_counts_by_convolution_equal_histogram(native, monkeypatch, cl, cm, tm):
+    """Bucket sizes of the guide index from the Hamming-ball convolution (default for cores up to 10
+    bases) and from the histogram pass (one atomic per guide and variant) give the same index:
+    identical hit lists for odd and even core lengths, every seed budget, key-range parts included.
+    (pam NGG has one N: core_mismatches + 1 <= 3.)"""
+    if cm + 1 > 3:
+        pytest.skip("bowtie's -n is at most 3")
+    img, protos = _case(native, seed=37 + cl, n=500)
+    protos = protos + protos[:50]  # repeated guides: buckets with several entries of the same key word
+    kw = dict(core_length=cl, core_mismatches=cm, total_mismatches=tm)
+    want, wf = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
+    for mode in (None, "atomic"):
+        if mode:
+            monkeypatch.setenv("GUIDO_IDX_HIST", mode)
+        for algo in (native.OT_TABLE, native.OT_INDEX):
+            got, gf = img.offtarget_search(protos, algo=algo, **kw)
+            assert np.array_equal(got, want) and np.array_equal(gf, wf), (mode, algo)
+    monkeypatch.delenv("GUIDO_IDX_HIST")
+    if cl == 10 and cm == 2:
+        n_all, _ = img.site_table_build("NGG", cl)
+        parts = []
+        for p in range(4):
+            img.site_table_partition(p, 4)
+            parts.append(img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False, **kw)[0])
+        img.site_table_partition(0, 1)
+        merged = np.concatenate(parts)
+        merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+        assert np.array_equal(merged, want)
