@@ -171,7 +171,6 @@ static int scan_to_host(guido_image *img, const PamSpec &pam, int mode, const Sc
     GUIDO_CUDA(cudaMemcpyAsync(&gave_up, ds->d_counts + 7, sizeof gave_up, cudaMemcpyDeviceToHost, ds->stream));
     GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
     if (gave_up) {
-        cudaMemsetAsync(ds->d_counts + 7, 0, sizeof gave_up, ds->stream);
         set_error("PAM scan: a tile never published its counts (look-back gave up)");
         return GUIDO_ERR_CUDA;
     }

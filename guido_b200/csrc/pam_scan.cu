@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 3) pam_fill_kernel(const PamScanArgs
 // counts, 2 = inclusive prefix.  31 bits per strand: launch_pam_scan takes this path only for
 // ranges below 2^31 bases.  One aligned 64-bit word, relaxed loads / stores: the word IS the data.
 constexpr unsigned long long kDescAgg = 1ull << 62, kDescPrefix = 2ull << 62, kDescValue = (1ull << 62) - 1;
-constexpr uint32_t kLookbackSpins = 1u << 19;  // polls before a look-back gives up (~a second; a bug, not a load effect)
+constexpr uint32_t kLookbackSpins = 1u << 24;  // polls before a look-back gives up (seconds: a bug, never a load effect)
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -739,6 +739,7 @@ int launch_pam_scan(DeviceState *ds, const PlanesView &pv, const PamSpec &pam, i
         ds->scan_grid[2] = ds->sm_count * std::max(per_sm, 1);
     }
     GUIDO_CUDA(cudaMemsetAsync(a.tiles, 0, (size_t)(a.n_tiles + 1) * sizeof(unsigned long long), stream));
+    GUIDO_CUDA(cudaMemsetAsync(a.err, 0, sizeof(unsigned long long), stream));  // per launch; the host calls read it back
     // One pass (look-back) when the descriptors' 31-bit counters cannot overflow and there are
     // enough tiles to matter; count -> fill otherwise.  GUIDO_PAM_PASSES=1/2 forces either (tests).
     const char *force = getenv("GUIDO_PAM_PASSES");
