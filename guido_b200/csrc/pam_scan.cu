@@ -348,6 +348,66 @@ __device__ __forceinline__ uint32_t emit_word_staged(uint32_t m, uint32_t base, 
     return next;
 }
 
+// Emission with a deferred tail (one-pass kernel).  A 32-base word holds Poisson(2) NGG hits, but a
+// warp pays for the MAXIMUM over its lanes -- 6.1 slots per word, four of them straight-line and
+// the rest in a loop that nearly every warp-word enters.  Here a word gets three straight-line
+// slots; a lane whose word holds more parks the remainder {bits, where its slots end, word index}
+// in a private queue and drains it once, after all sixteen words of the tile: the warp then pays
+// for the maximum of the lanes' TOTAL leftovers (~10 rounds) instead of sixteen per-word maxima.
+// The queue is the thread's own column of the plane buffer, free once the planes are in registers
+// (8 entries of 8 bytes; when it is full the word is finished in place).
+constexpr int kEmitQueue = 2 * kBpt;  // entries per thread: its kBpt 16-byte plane slots
+
+__device__ __forceinline__ uint32_t emit_word_deferred(uint32_t m, uint32_t base, uint32_t stage_addr, uint32_t off,
+                                                        uint32_t w, uint32_t q_addr, uint32_t &q_n) {
+    const uint32_t next = off + __popc(m);
+    uint32_t addr = stage_addr + 4u * next;  // shared-window byte address just past the word's last slot
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        asm volatile("{ .reg .pred q; .reg .u32 top, pos, bit;\n\t"
+                     "bfind.u32 top, %0;\n\t"
+                     "setp.ne.u32 q, %0, 0;\n\t"
+                     "add.u32 pos, %2, top;\n\t"
+                     "@q st.shared.u32 [%1], pos;\n\t"
+                     "shl.b32 bit, 1, top;\n\t"
+                     "xor.b32 %0, %0, bit; }"
+                     : "+r"(m) : "r"(addr - 4u * (k + 1)), "r"(base) : "memory");
+    }
+    if (m) {
+        addr -= 12;
+        if (q_n < (uint32_t)kEmitQueue) {  // entry e lives in plane slot e / 2 of this thread's column, half e % 2
+            const uint32_t e_addr = q_addr + (q_n >> 1) * (uint32_t)(kThreads * 16) + (q_n & 1u) * 8u;
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(e_addr), "r"(m), "r"(addr | (w << 24)) : "memory");
+            q_n++;
+        } else {
+            while (m) {
+                const uint32_t top = 31u - (uint32_t)__clz((int)m);
+                addr -= 4;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(base + top) : "memory");
+                m ^= 1u << top;
+            }
+        }
+    }
+    return next;
+}
+
+// thread_base = position of the thread's first base (the words' bases are thread_base + 32 w)
+__device__ __forceinline__ void emit_drain(uint32_t thread_base, uint32_t q_addr, uint32_t q_n) {
+    for (uint32_t e = 0; e < q_n; e++) {
+        uint32_t m, meta;
+        const uint32_t e_addr = q_addr + (e >> 1) * (uint32_t)(kThreads * 16) + (e & 1u) * 8u;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m), "=r"(meta) : "r"(e_addr) : "memory");
+        uint32_t addr = meta & 0xffffffu;
+        const uint32_t base = thread_base + 32u * (meta >> 24);
+        while (m) {
+            const uint32_t top = 31u - (uint32_t)__clz((int)m);
+            addr -= 4;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(base + top) : "memory");
+            m ^= 1u << top;
+        }
+    }
+}
+
 // staged hits [a0, a0+n) of s -> g[a0 .. a0+n); s and g agree modulo 16 bytes, so whole uint4s
 // move in the middle and at most 3 scalars at either end
 __device__ __forceinline__ void copy_out(const uint32_t *s, uint32_t a0, uint32_t n, uint32_t *g, int vec_ok) {
@@ -655,13 +715,20 @@ __global__ void __launch_bounds__(kThreads, 3) pam_onepass_kernel(const PamScanA
             __syncthreads();
             p_ex = s_excl;
         }
+        // (the plane buffer is free: stage_read moved this tile's planes to registers, the next tile's
+        // are requested at the top of the next iteration, by each thread into its own column)
+        const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(s_planes + threadIdx.x);
+        uint32_t q_n = 0;
         if (stage_f) {
 #pragma unroll
-            for (int w = 0; w < kWpt; w++) of = emit_word_staged(hf[w], base + 32 * w, sa_f, of);
+            for (int w = 0; w < kWpt; w++) of = emit_word_deferred(hf[w], base + 32 * w, sa_f, of, (uint32_t)w, q_addr, q_n);
+            emit_drain(base, q_addr, q_n);
+            q_n = 0;
         }
         if (stage_r) {
 #pragma unroll
-            for (int w = 0; w < kWpt; w++) orv = emit_word_staged(hr[w], base + 32 * w, sa_r, orv);
+            for (int w = 0; w < kWpt; w++) orv = emit_word_deferred(hr[w], base + 32 * w, sa_r, orv, (uint32_t)w, q_addr, q_n);
+            emit_drain(base, q_addr, q_n);
         }
         if (direct) {
             const unsigned long long ef = p_ex >> 31, er = p_ex & 0x7fffffffull;
