@@ -52,13 +52,13 @@ struct WarpSmem {
 };
 
 // greedy left-to-right non-overlapping starts out of a match bitmask (re.finditer semantics)
-__device__ __forceinline__ int greedy_select(const uint32_t *mask, int n_pos, int k, unsigned char *out, int lane) {
+__device__ __forceinline__ int greedy_select(const uint32_t *mask, int n_words, int n_pos, int k, unsigned char *out, int lane) {
     int count = 0, next = 0;
     while (next < n_pos) {
         int w = next >> 5;
         uint32_t m = mask[w] & (kFullMask << (next & 31));
-        while (!m && ++w < 8) m = mask[w];
-        if (!m || w >= 8) break;
+        while (!m && ++w < n_words) m = mask[w];
+        if (!m || w >= n_words) break;
         int x = (w << 5) + __ffs(m) - 1;
         if (x >= n_pos) break;
         if (lane == 0) out[count] = (unsigned char)x;
@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(kMmejWarps * 32) mmej_kernel(const MmejArgs a)
                 while (am) {
                     const int i0 = ibase + __ffs(am) - 1;
                     am &= am - 1;
-                    // occurrences of left[i0:i0+k] on both sides
-                    for (int w = 0; w < 8; w++) {
+                    // occurrences of left[i0:i0+k] on both sides (only the mask words either side can fill)
+                    const int n_words = (max(nl, nr) - k + 32) >> 5;
+                    for (int w = 0; w < n_words; w++) {
                         int x = (w << 5) + lane;
                         bool ml = false, mr = false;
                         if (x + k <= nl) {
@@ -139,8 +140,8 @@ __global__ void __launch_bounds__(kMmejWarps * 32) mmej_kernel(const MmejArgs a)
                         if (lane == 0) { s.ml[w] = bl; s.mr[w] = br; }
                     }
                     __syncwarp();
-                    const int cl = greedy_select(s.ml, nl - k + 1, k, s.lpos, lane);
-                    const int cr = greedy_select(s.mr, nr - k + 1, k, s.rpos, lane);
+                    const int cl = greedy_select(s.ml, n_words, nl - k + 1, k, s.lpos, lane);
+                    const int cr = greedy_select(s.mr, n_words, nr - k + 1, k, s.rpos, lane);
                     __syncwarp();
                     const int np = cl * cr;                       // itertools.product, left-major
                     for (int t = lane; t < np; t += 32) {
