@@ -303,7 +303,10 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     table = None
     if algo in (N.OT_AUTO, N.OT_TABLE):
         n_sites, build_ms = img.site_table_build(PAM, OT_KW["core_length"])
-        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 20 * n_sites, "build_ms": build_ms}
+        # 16 B per slot (position, planes, key: read for hits) + 5 B per slot of bit-sliced blocks (what
+        # the join streams); buckets are padded to whole blocks of 32 slots
+        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 21 * n_sites + 21 * 16 * (4 ** OT_KW["core_length"]) // R.world,
+                 "build_ms": build_ms}
     # kernels per search: one host-API call reports its launches; the device sort (split + radix
     # passes + merge) belongs to that call only
     st0 = N.Stats()
@@ -380,17 +383,20 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
     hits_rank = float(d_count.item())
     if table is not None:
-        # join over the site table: 8 B per window (core key + distal codes), the index once
-        # (re-reads are L1/L2 hits by construction: table order = bucket order) -- 176 B per 32-key
-        # block of the bit-sliced index (buckets padded to whole blocks: + 16 slots on average), or
-        # 4 B per key for the popc walk -- 4 B per bucket offset, and 36 B per hit (guide id,
-        # position and the two plane words read at flush time, 16-byte record written)
+        # join over the site table.  Block join (>= 8 keys per bucket): 5 B per table slot (the 160-byte
+        # blocks of 32 windows, buckets padded to whole blocks: + 16 slots per bucket on average), 8 B per
+        # index entry, 8 B of bucket offsets per bucket, and 40 B per hit (8-byte entry and 16-byte slot
+        # read at flush time, 16-byte record written).  Popc walk (small guide sets): 16 B per slot,
+        # 4 B per key, 4 B per bucket offset, 36 B per hit.
         from math import comb
         n_keys = float(n_guides) * sum(comb(OT_KW["core_length"], k) * 3 ** k for k in range(OT_KW["core_mismatches"] + 1))
         n_buckets = 4.0 ** OT_KW["core_length"]
-        index_bytes = (176.0 / 32.0) * (n_keys + 16.0 * n_buckets) if n_keys >= 16.0 * n_buckets else 4.0 * n_keys
         parts = R.world if getattr(R.a, "key_sharded", False) else 1  # key-sharded ranks build 1/N of the index
-        alg_bytes_rank = 8.0 * sites + (index_bytes + 4.0 * n_buckets) / parts + 36.0 * hits_rank
+        slots = sites + 16.0 * n_buckets / parts
+        if n_keys >= 8.0 * n_buckets and sites * parts >= 64.0 * n_buckets:
+            alg_bytes_rank = 5.0 * slots + (8.0 * n_keys + 8.0 * n_buckets) / parts + 40.0 * hits_rank
+        else:
+            alg_bytes_rank = 16.0 * slots + (4.0 * n_keys + 4.0 * n_buckets) / parts + 36.0 * hits_rank
     else:
         alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
     return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "table": table,
@@ -486,14 +492,15 @@ def main():
         use_index = algo != N.OT_SCAN
         use_table = r["table"] is not None
         # the join compares bit-sliced (32 keys per LOP3 lane) once buckets hold >= 16 keys on average
-        sliced = use_table and 436 * args.guides >= 16 * 4 ** OT_KW["core_length"]
-        kernel = ("ot_join_sliced_kernel" if sliced else "ot_join_kernel" if use_table else
+        sliced = use_table and 436 * args.guides >= 8 * 4 ** OT_KW["core_length"] and r["sites"] >= 64 * 4 ** OT_KW["core_length"]
+        kernel = ("ot_join_blocks_kernel" if sliced else "ot_join_kernel" if use_table else
                   "ot_kernel<index>" if use_index else "ot_kernel<scan>")
         algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
                      "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
-        alg_desc = ("per GPU: 8 B per window of the site table + the index once (176 B per 32-key block, or 4 B per "
-                    "key for the popc walk) + 4 B per bucket offset + 36 B per hit; the compare itself is "
-                    "integer-pipe bound, see int_pipe" if use_table else
+        alg_desc = ("per GPU: 5 B per slot of the bit-sliced site table (buckets padded to 32 slots) + 8 B per index "
+                    "entry + 8 B of offsets per bucket + 40 B per hit; the compare itself is ALU-pipe bound, see "
+                    "int_pipe" if sliced else
+                    "per GPU: 16 B per table slot + 4 B per index key + 4 B per bucket offset + 36 B per hit" if use_table else
                     "per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
                     "key compared + 16 B per hit" if use_index else
                     "per GPU: 0.25 B/base planes + 16 B per hit (the brute-force compare is "
@@ -530,15 +537,14 @@ def main():
             sm_mhz = (r["clocks"] or {}).get("sm_mhz") or 1965.0
             per_gpu = r["visited"] / world / (r["kernel_ms"] * 1e-3)
             if sliced:
-                # per block of 32 keys: 10 four-byte loads (the mismatch words of the window's own letters)
-                # + 18 LOP3 of carry-save counting on the ALU pipe (64 lanes/clk/SM = 2 warp-instr/clk/SM);
-                # blocks are counted from the true keys (the pad slots of each bucket's last block ride along)
-                out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "lop3_per_32_keys": 18, "loads_per_32_keys": 11,
+                # per (entry, block of 32 windows): 10 four-byte shared-memory loads (the mismatch words of
+                # the entry's own letters) + 18 LOP3 of carry-save counting on the ALU pipe (16 lanes/clk
+                # per SM sub-partition = 2 warp-instr/clk/SM); `visited` = entries x slots compared
+                out["int_pipe"] = {"pair_compares_per_s_per_gpu": per_gpu, "lop3_per_32_windows": 18, "loads_per_32_windows": 10,
                                    "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 18 / 32 / 148 / (sm_mhz * 1e6),
                                    "alu_peak_warp_instr_per_clk_per_sm": 2, "sm_mhz": sm_mhz,
                                    "note": "no XOR/OR stage and no POPC: per-letter mismatch words are loaded, an 18-LOP3 "
-                                           "carry-save tree counts them; ncu: ALU pipe ~60 %, issue slots ~67 % busy "
-                                           "overall incl. per-window set-up (profiles/r1_join_sliced_ncu.txt)"}
+                                           "carry-save tree counts them"}
             else:
                 # the popc kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
                 out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),

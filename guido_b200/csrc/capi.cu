@@ -75,6 +75,7 @@ void device_release(guido_image *img) {
         cudaFree(ds->d_out[0]); cudaFree(ds->d_out[1]); cudaFree(ds->d_guides); cudaFree(ds->d_flags);
         cudaFree(ds->d_index); cudaFree(ds->d_bucket);
         release_site_table(ds);
+        cudaFree(ds->d_site_off); cudaFree(ds->d_tickets);
         if (ds->h_pinned) cudaFreeHost(ds->h_pinned);
         for (auto &e : ds->ev) if (e) cudaEventDestroy(e);
         for (auto &p : ds->kev) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }

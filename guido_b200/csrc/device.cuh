@@ -48,10 +48,14 @@ struct DeviceState {
     // PAM-site table: every PAM-valid window of the resident shard (guide orientation), grouped by
     // core k-mer -- the genome-side index of the off-target search, built once per (PAM, core
     // length) and kept with the image like bowtie's index files (offtarget.cu)
-    uint32_t *d_site_a = nullptr, *d_site_b = nullptr, *d_site_q = nullptr;
-    uint2 *d_site_kd = nullptr;  // per row {core key, distal bases as interleaved 2-bit codes}: what the sliced join streams
-    int64_t site_cap = 0;       // entries allocated
-    int64_t site_n = -1;        // entries valid (-1: no table)
+    uint4 *d_site_slots = nullptr;     // per slot {global position, hi plane | strand << 31, lo plane, core key}; pad slots: x = ~0
+    uint32_t *d_site_blocks = nullptr; // bit-sliced form of the slots: 40 words per 32 slots (join_blocks.cu), or null
+    uint32_t *d_site_off = nullptr;    // n_buckets + 1: first slot of each bucket (multiple of 32) | pad count in the low 5 bits
+    uint32_t *d_tickets = nullptr;     // 64 work counters of the block join (one per launch in flight)
+    int64_t site_cap = 0;       // slots allocated
+    int64_t site_slots = 0;     // slots in use (buckets padded to whole blocks of 32)
+    int64_t site_n = -1;        // windows tabled (-1: no table)
+    int bj_grid = 0;            // resident-CTA grid of ot_join_blocks_kernel (cached)
     uint8_t site_fw[8] = {}, site_rv[8] = {};  // the PAM sets the table was built for
     int site_pam_len = 0, site_core_len = 0;
     float site_build_ms = 0;
@@ -61,7 +65,7 @@ struct DeviceState {
     // table was built with.
     int site_part_ix = 0, site_n_parts = 1;
     int site_tab_part_ix = 0, site_tab_n_parts = 1;
-    uint32_t site_row_off[33] = {};  // first table row of each 1/32 of the core-key space (+ the row count)
+    uint32_t site_row_off[33] = {};  // first table slot of each 1/32 of the core-key space (+ the slot count)
     // second stream + events: the guide index is built slice by slice while the join already
     // works on the slices that are ready (launch_ot_join)
     cudaStream_t build_stream = nullptr, join_stream = nullptr;

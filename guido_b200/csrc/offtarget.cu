@@ -23,12 +23,12 @@
 #include <vector>
 
 #include "scan_common.cuh"
+#include "join_blocks.cuh"
 
 namespace guido {
 
 constexpr int kSitesPerThread = 8;
-constexpr int kSiteRowBytes = 20;  // PAM-site table: hi plane, lo plane, position, {core key, distal codes}
-constexpr int kSliceWords = 44;  // words per 32-key block of the bit-sliced index (see idx_transpose_kernel)
+constexpr int kSiteSlotBytes = 16;  // PAM-site table: one uint4 {position, hi plane | strand, lo plane, core key} per slot
 
 // guide-side seed index (built per search call by the idx_* kernels below), structure of arrays:
 // the search streams `keys` only and touches `guides` on a hit
@@ -39,7 +39,6 @@ struct OtIndex {
     int cl, dl;               // core / distal length (cl + dl = 20)
     int field;                // bits per plane field of a key: dl + core_mm pseudo-positions
     int wide;                 // average bucket is large: walk buckets warp-wide
-    const uint4 *planes;      // bit-sliced copy of the keys (join over the site table), or null
 };
 
 struct OtScanArgs {
@@ -56,11 +55,10 @@ struct OtScanArgs {
     unsigned long long *count;
     uint8_t *flags;
     unsigned long long *site_count;
-    // PAM-site table (genome-side index): windows grouped by core key, structure of arrays
-    uint32_t *tab_a, *tab_b, *tab_q;   // hi plane (+ strand in bit 31), lo plane, global position
-    uint2 *tab_kd;                     // {core key, distal bases as interleaved 2-bit codes (lo bit first)}
-    uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts, fill cursors (build only)
-    uint32_t tab_lo, tab_n;             // join: rows [tab_lo, tab_n) of the table
+    // PAM-site table (genome-side index): windows grouped by core key, buckets padded to 32 slots
+    uint4 *tab_slots;                  // {global position, hi plane (+ strand in bit 31), lo plane, core key}; pads: x = ~0
+    uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts (| pad count), fill cursors (build only)
+    uint32_t tab_lo, tab_n;             // join: slots [tab_lo, tab_n) of the table
     uint32_t tab_key_lo, tab_key_span;  // table build: only core keys in [lo, lo + span) are tabled
 };
 
@@ -357,9 +355,9 @@ __device__ __forceinline__ void walk_init(const OtScanArgs &a, const uint32_t *s
 }
 
 // compare the 8 keys in registers (the next 8 are requested first); hits are parked
-template <bool kReuse>
-__device__ __forceinline__ void walk_step(const OtScanArgs &a, const uint32_t *sA, const uint32_t *sB,
-                                          const uint32_t *sQ, BucketWalk &w, HitBuf &hb) {
+// rec(idx) -> {position, hi plane, lo plane} of the window a hit belongs to
+template <bool kReuse, typename Rec>
+__device__ __forceinline__ void walk_step(const OtScanArgs &a, const Rec &rec, BucketWalk &w, HitBuf &hb) {
     const int F = a.ix.field;
     const uint32_t fmask = (1u << F) - 1;
     const int tot_max = a.op.total_max;
@@ -382,7 +380,8 @@ __device__ __forceinline__ void walk_step(const OtScanArgs &a, const uint32_t *s
             if (off + k < w.len && (int)__popc((x | (x >> F)) & fmask) <= tot_max) {
                 guido_ot_hit h;
                 h.guide = __ldg(&a.ix.guides[(w.p - a.ix.keys) + off + k]);
-                h.gpos = sQ[w.idx]; h.hi = sA[w.idx]; h.lo = sB[w.idx];
+                const uint3 win = rec(w.idx);
+                h.gpos = win.x; h.hi = win.y; h.lo = win.z;
                 push_hit(a, hb, h);
             }
         }
@@ -404,7 +403,8 @@ __device__ __forceinline__ void lookup_round_thread(const OtScanArgs &a, const u
     for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
         BucketWalk w;
         walk_init<RING>(a, sA, sB, head, j, n, w, visited);
-        while (w.off < w.len) walk_step<false>(a, sA, sB, sQ, w, hb);
+        const auto rec = [&](uint32_t idx) { return make_uint3(sQ[idx], sA[idx], sB[idx]); };
+        while (w.off < w.len) walk_step<false>(a, rec, w, hb);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
@@ -427,6 +427,7 @@ __device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t 
                                             const uint32_t *sQ, uint32_t head, uint32_t n) {
     const int cl = a.ix.cl, dl = a.ix.dl;
     const uint32_t cmask = (1u << cl) - 1;
+    uint32_t tabled = 0;
     for (uint32_t j = threadIdx.x; j < n; j += kThreads) {
         const uint32_t idx = (head + j) & (RING - 1);
         const uint32_t A = sA[idx], B = sB[idx];
@@ -434,11 +435,15 @@ __device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t 
         if (key - a.tab_key_lo >= a.tab_key_span) continue;  // another rank's share of the key space
         if constexpr (!kFill) {
             atomicAdd(&a.tab_counts[key], 1u);
+            tabled++;
         } else {
-            const uint32_t slot = a.tab_counts[key] + atomicAdd(&a.tab_fill[key], 1u);
-            a.tab_a[slot] = A; a.tab_b[slot] = B; a.tab_q[slot] = sQ[idx];
-            a.tab_kd[slot] = make_uint2(key, spread_bits(B & ((1u << dl) - 1u)) | (spread_bits(A & ((1u << dl) - 1u)) << 1));
+            const uint32_t slot = (a.tab_counts[key] & ~31u) + atomicAdd(&a.tab_fill[key], 1u);
+            a.tab_slots[slot] = make_uint4(sQ[idx], A, B, key);
         }
+    }
+    if constexpr (!kFill) {  // [1]: windows that fall into this handle's share of the key space
+        tabled = __reduce_add_sync(kFull, tabled);
+        if ((threadIdx.x & 31) == 0 && tabled && a.site_count) atomicAdd(a.site_count + 1, (unsigned long long)tabled);
     }
 }
 
@@ -568,211 +573,7 @@ __global__ void __launch_bounds__(kThreads, kMode == kModeScan ? 3 : 5) ot_kerne
     }
 }
 
-// ---- join against the bit-sliced index ----------------------------------------------------------
-
-__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
-__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
-__device__ __forceinline__ uint32_t lop3_nor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
-
 constexpr uint32_t kJoinPerThread = 4;  // windows per thread between two CTA barriers
-
-// Hits of the sliced join are parked as (table row, index slot) pairs -- two words, no loads in the
-// divergent hit path -- and turned into records (guide id, position, planes: four scattered
-// loads) by the whole CTA when the queue is flushed.
-constexpr int kHitQueue = 768;
-struct HitQueue {
-    uint32_t n;
-    unsigned long long base;
-    unsigned long long visited;
-    uint2 q[kHitQueue];
-};
-
-__device__ __forceinline__ guido_ot_hit resolve_hit(const OtScanArgs &a, uint32_t row, uint32_t slot) {
-    guido_ot_hit h;
-    h.guide = __ldg(&reinterpret_cast<const uint2 *>(a.ix.keys)[slot]).y;
-    h.gpos = __ldg(&a.tab_q[row]); h.hi = __ldg(&a.tab_a[row]); h.lo = __ldg(&a.tab_b[row]);
-    return h;
-}
-
-__device__ __forceinline__ void queue_hit(const OtScanArgs &a, HitQueue &hq, uint32_t row, uint32_t slot) {
-    const uint32_t i = atomicAdd(&hq.n, 1u);
-    if (i < kHitQueue) {
-        hq.q[i] = make_uint2(row, slot);
-    } else {  // queue full until the next flush: straight to the global list
-        unsigned long long dst = atomicAdd(a.count, 1ull);
-        if (dst < a.cap) a.hits[dst] = resolve_hit(a, row, slot);
-    }
-}
-
-// whole CTA, after a barrier that ends the queueing phase
-__device__ __forceinline__ void flush_queue(const OtScanArgs &a, HitQueue &hq, bool force) {
-    const uint32_t n = min(hq.n, (uint32_t)kHitQueue);
-    __syncthreads();  // everybody has looked at the fill level before anybody queues another hit
-    if (n == 0 || (!force && n < kHitQueue / 2)) return;
-    if (threadIdx.x == 0) hq.base = atomicAdd(a.count, (unsigned long long)n);
-    __syncthreads();
-    const unsigned long long base = hq.base;
-    for (uint32_t i = threadIdx.x; i < n; i += kThreads)
-        if (base + i < a.cap) a.hits[base + i] = resolve_hit(a, hq.q[i].x, hq.q[i].y);
-    __syncthreads();
-    if (threadIdx.x == 0) hq.n = 0;
-    __syncthreads();
-}
-
-__device__ __forceinline__ void cp_async8(const uint2 *smem_dst, const uint2 *gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
-}
-
-// One block of 32 keys against one window: bit k of the result is set when key k is a hit, i.e.
-// (distal mismatches + c') <= 7.  A block stores, per distal base j, the four words "key k differs
-// from letter c at base j" (c = 0..3) next to each other: the window picks, per base, the word of
-// its own letter -- ten 4-byte loads deliver the ten mismatch words, there is no XOR / OR stage,
-// and the lanes of a warp (same bucket, different letters) stay inside one 16-byte chunk per load.
-// p[j] = address of that word in the block at hand; cw = the block's four c' words.
-__device__ __forceinline__ uint32_t sliced_block_hits(const uint32_t *const (&p)[10], const uint4 *cw, uint32_t word_off) {
-    uint32_t m[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) m[j] = __ldg(p[j] + word_off + 4 * j);
-    const uint4 q5 = __ldg(cw + word_off / 4);
-    // carry-save count of m[0..9] + c' (q5.x..w = weights 1, 2, 4, 8); only "reaches 8" matters,
-    // so sums that feed nothing are never formed
-    // weight 1: eleven inputs -> five carries
-    const uint32_t s0 = lop3_xor3(m[0], m[1], m[2]), c0 = lop3_maj(m[0], m[1], m[2]);
-    const uint32_t s1 = lop3_xor3(m[3], m[4], m[5]), c1 = lop3_maj(m[3], m[4], m[5]);
-    const uint32_t s2 = lop3_xor3(m[6], m[7], m[8]), c2 = lop3_maj(m[6], m[7], m[8]);
-    const uint32_t s3 = lop3_xor3(s0, s1, s2), c3 = lop3_maj(s0, s1, s2);
-    const uint32_t c4 = lop3_maj(s3, m[9], q5.x);
-    // weight 2: five carries + c' bit 1 -> three carries
-    const uint32_t t0 = lop3_xor3(c0, c1, c2), d0 = lop3_maj(c0, c1, c2);
-    const uint32_t t1 = lop3_xor3(c3, c4, q5.y), d1 = lop3_maj(c3, c4, q5.y);
-    const uint32_t d2 = t0 & t1;
-    // weight 4: three carries + c' bit 2 -> two carries
-    const uint32_t u0 = lop3_xor3(d0, d1, d2), e0 = lop3_maj(d0, d1, d2);
-    const uint32_t e1 = u0 & q5.z;
-    // weight 8: any carry or c' bit 3 = more than 7
-    return lop3_nor3(e0, e1, q5.w);
-}
-
-// The join is a chain of dependent loads per window -- table row (DRAM, streamed), bucket offsets
-// (L2), key planes (DRAM the first time a bucket is touched) -- and with ~35 issue slots of work
-// per 32 keys the loads, not the compare, set the pace.  So the chain is pulled one chunk ahead:
-// while a CTA works on chunk c its threads' table rows of chunk c+1 arrive through cp.async,
-// half-way through the chunk their bucket ranges are looked up and the first plane blocks are
-// prefetched into L2; by the time chunk c+1 starts everything it needs is on chip.  A thread only
-// ever reads the shared-memory words it wrote itself, so the stages need no CTA barrier.
-__global__ void __launch_bounds__(kThreads, 4) ot_join_sliced_kernel(const OtScanArgs a) {
-    constexpr uint32_t kChunk = kJoinPerThread * kThreads;
-    __shared__ HitQueue s_hits;
-    __shared__ uint2 sKD[2][kChunk];                       // {core key, interleaved distal codes}
-    __shared__ uint32_t sStart[2][kChunk], sLen[2][kChunk];
-    if (threadIdx.x == 0) { s_hits.n = 0; s_hits.visited = 0; }
-    __syncthreads();
-    const uint32_t n_chunks = (a.tab_n - a.tab_lo + kChunk - 1) / kChunk;
-    const uint32_t per_cta = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const uint32_t c0 = min(blockIdx.x * per_cta, n_chunks), c1 = min(c0 + per_cta, n_chunks);
-    const uint32_t *__restrict__ planes = reinterpret_cast<const uint32_t *>(a.ix.planes);
-    unsigned long long visited = 0;
-
-    // (the table arrays are allocated with a chunk of slack, so the last chunk reads past tab_n
-    // without a bounds check per row; such rows get an empty bucket range below)
-    auto fetch = [&](uint32_t c, int buf) {  // this thread's table rows of chunk c -> shared memory
-        const uint2 *g = a.tab_kd + a.tab_lo + (size_t)c * kChunk + threadIdx.x;
-#pragma unroll
-        for (uint32_t k = 0; k < kJoinPerThread; k++) cp_async8(&sKD[buf][k * kThreads + threadIdx.x], g + k * kThreads);
-        asm volatile("cp.async.commit_group;");
-    };
-    auto resolve = [&](uint32_t c, int buf) {  // bucket ranges of those rows; planes towards L2
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        uint32_t v[kJoinPerThread], w[kJoinPerThread];
-#pragma unroll
-        for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t key = sKD[buf][k * kThreads + threadIdx.x].x & 0xfffffu;
-            v[k] = __ldg(&a.ix.offsets[key]); w[k] = __ldg(&a.ix.offsets[key + 1]);
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < kJoinPerThread; k++) {
-            const uint32_t idx = k * kThreads + threadIdx.x;
-            const uint32_t start = v[k] & ~31u;
-            const uint32_t len = a.tab_lo + c * kChunk + idx < a.tab_n ? (w[k] & ~31u) - start - (v[k] & 31u) : 0u;
-            sStart[buf][idx] = start; sLen[buf][idx] = len;
-            if (len) {  // the first lines of the bucket's planes (one or two 176-byte blocks)
-                const char *p = reinterpret_cast<const char *>(planes) + (size_t)(start >> 5) * (kSliceWords * 4);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256));
-            }
-        }
-    };
-    auto process = [&](uint32_t c, int buf, uint32_t k) {
-        const uint32_t idx = k * kThreads + threadIdx.x, i = a.tab_lo + c * kChunk + idx;
-        const uint32_t len = sLen[buf][idx];
-        if (len == 0) return;  // empty bucket, or a row past the end of the range
-        const uint32_t D = sKD[buf][idx].y;
-        visited += len;
-        const uint32_t blk0 = sStart[buf][idx] >> 5, n_blk = (len + 31) >> 5;
-        const uint32_t *base = planes + (size_t)blk0 * kSliceWords;
-        // per distal base: the word of the window's own letter (code = 2 bits of D) in block 0.
-        // p[j] = base + 4 * code bytes as ONE 64-bit multiply-add on the FMA pipe (the ALU pipe is
-        // the busy one); the base's own offset 16 * j rides in the loads' immediate field.
-        const uint32_t *p[10];
-#pragma unroll
-        for (int j = 0; j < 10; j++) {
-            const uint32_t code4 = j ? ((D >> (2 * j - 2)) & 12u) : ((D << 2) & 12u);  // 4 * letter code
-            unsigned long long addr;
-            asm volatile("mad.wide.u32 %0, %1, 1, %2;" : "=l"(addr) : "r"(code4), "l"(base));
-            p[j] = reinterpret_cast<const uint32_t *>(addr);
-        }
-        const uint4 *cw = reinterpret_cast<const uint4 *>(base + 40);
-        auto report = [&](uint32_t r, uint32_t blk) {  // rare: 1.4 % of (window, block) pairs
-            while (r) {
-                const int kk = __ffs((int)r) - 1;
-                r &= r - 1;
-                queue_hit(a, s_hits, i, blk * 32 + (uint32_t)kk);
-            }
-        };
-        // two blocks per round at compile-time offsets from the ten pointers (a bucket of the
-        // 100 k-guide index has 1.9 blocks on average); the pointers move only for a third block
-        for (uint32_t b = 0;;) {
-            report(sliced_block_hits(p, cw, 0), blk0 + b);
-            if (b + 1 < n_blk) report(sliced_block_hits(p, cw, kSliceWords), blk0 + b + 1);
-            b += 2;
-            if (b >= n_blk) break;
-#pragma unroll
-            for (int j = 0; j < 10; j++) p[j] += 2 * kSliceWords;
-            cw += 2 * kSliceWords / 4;
-        }
-    };
-
-    if (c0 < c1) { fetch(c0, 0); resolve(c0, 0); }
-    for (uint32_t c = c0; c < c1; c++) {
-        const int buf = (int)((c - c0) & 1u);
-        const bool more = c + 1 < c1;
-        if (more) fetch(c + 1, buf ^ 1);
-        process(c, buf, 0);
-        process(c, buf, 1);
-        if (more) resolve(c + 1, buf ^ 1);
-        process(c, buf, 2);
-        process(c, buf, 3);
-        __syncthreads();
-        flush_queue(a, s_hits, false);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) visited += __shfl_xor_sync(kFull, visited, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_hits.visited, visited);
-    __syncthreads();
-    flush_queue(a, s_hits, true);
-    if (threadIdx.x == 0 && a.site_count) {
-        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)(a.tab_n - a.tab_lo));
-        atomicAdd(a.site_count + 1, s_hits.visited);
-    }
-}
-static_assert(kJoinPerThread == 4, "the stage schedule of ot_join_sliced_kernel is written for 4 windows per thread");
 
 template <int kMode>
 static int launch_ot_kernel(DeviceState *ds, OtScanArgs &a, cudaStream_t stream) {
@@ -807,7 +608,9 @@ __device__ __forceinline__ void join_init(const OtScanArgs &a, uint32_t i, Bucke
     w.len = 0; w.off = 0; w.p = a.ix.keys; w.dist = 0; w.idx = i;
     w.n0 = w.n1 = w.n2 = w.n3 = 0;
     if (i >= a.tab_n) return;
-    const uint32_t A = __ldg(&a.tab_a[i]), B = __ldg(&a.tab_b[i]);
+    const uint4 slot = __ldg(&a.tab_slots[i]);
+    if (slot.x == 0xffffffffu) return;  // pad slot at the end of a bucket
+    const uint32_t A = slot.y, B = slot.z;
     const uint32_t key = (((A >> dl) & cmask) << cl) | ((B >> dl) & cmask);
     uint32_t start;
     bucket_range(a.ix, key, start, w.len);
@@ -832,7 +635,8 @@ __global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a
         for (uint32_t k = 0; k < kJoinPerThread; k++) {
             BucketWalk w;
             join_init(a, a.tab_lo + c * kChunk + k * kThreads + threadIdx.x, w, visited);
-            while (w.off < w.len) walk_step<true>(a, a.tab_a, a.tab_b, a.tab_q, w, s_hits);
+            const auto rec = [&](uint32_t idx) { const uint4 t = __ldg(&a.tab_slots[idx]); return make_uint3(t.x, t.y, t.z); };
+            while (w.off < w.len) walk_step<true>(a, rec, w, s_hits);
         }
         __syncthreads();
         flush_hits(a, s_hits, false);
@@ -843,7 +647,6 @@ __global__ void __launch_bounds__(kThreads, 5) ot_join_kernel(const OtScanArgs a
     __syncthreads();
     flush_hits(a, s_hits, true);
     if (threadIdx.x == 0 && a.site_count) {
-        if (blockIdx.x == 0) atomicAdd(a.site_count, (unsigned long long)(a.tab_n - a.tab_lo));
         atomicAdd(a.site_count + 1, s_hits.visited);
     }
 }
@@ -855,10 +658,10 @@ int launch_ot_scan(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
+    a.ix = OtIndex{nullptr, nullptr, nullptr, 0, 0, 0, 0};
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = d_flags; a.site_count = d_site_count;
-    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_kd = nullptr; a.tab_n = 0;
+    a.tab_slots = nullptr; a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
     int rc = launch_ot_kernel<kModeScan>(ds, a, stream);
     if (rc) return rc;
     if (n_launches) *n_launches += 1;
@@ -887,9 +690,9 @@ struct IdxArgs {
     uint16_t group_off[33];      // variants sorted by the top slice_bits of their hi-plane mask
     uint32_t part_shift, part_ix; // histogram pass: only keys with key >> part_shift == part_ix (when part_on)
     bool part_on;
-    uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7 or 31)
-    int sliced;                // 1: row-major staging format of the bit-sliced index (see below)
-    uint32_t cbias;            // sliced: 7 - total_max, added to the variant's core mismatch count
+    uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7, or 0: no padding)
+    int entries;               // 1: one {letters | bias, guide} entry per key, the format of the block join (join_blocks.cu)
+    uint32_t cbias;            // entries: 7 - total_max, added to the variant's core mismatch count
 };
 
 // One warp per guide: the guide is read once, the lanes walk the variant list (staged in shared
@@ -905,11 +708,13 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
     __syncthreads();
     const uint32_t cmask = (1u << a.cl) - 1, dmask = (1u << a.dl) - 1;
     const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * 8u;
-    uint2 *ent = reinterpret_cast<uint2 *>(a.keys);  // sliced staging: {key word, guide} per slot
+    uint2 *ent = reinterpret_cast<uint2 *>(a.keys);  // entry format: {letters | bias, guide} per key
     for (uint32_t g = blockIdx.x * 8u + (threadIdx.x >> 5); g < a.n_guides; g += warps) {
         const uint2 G = __ldg(&a.guides[g]);
         const uint32_t ch = (G.x >> a.dl) & cmask, cl_ = (G.y >> a.dl) & cmask;
         const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
+        // entry format: the distal bases as 2-bit letter codes, base j at bits 2j (= 2 * hi + lo)
+        const uint32_t letters = kFill && a.entries ? (spread_bits(dlo) | (spread_bits(dh) << 1)) : 0u;
         // A fill pass writes the buckets whose top `slice_bits` key bits equal `slice`; the variants
         // are grouped by the same bits of their hi-plane mask, so the group (top bits of the
         // guide's core ^ slice) holds exactly this pass's variants: every lane of every iteration
@@ -929,11 +734,10 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
                 // fill[] starts out as the bucket starts (scan_fixup_kernel): the atomic IS the slot
                 const uint32_t pos = atomicAdd(&a.fill[key], 1u);
                 const uint32_t cmm = (uint32_t)__popc(xh | xl);
-                if (a.sliced) {
-                    // staging word of the bit-sliced index: distal hi plane, distal lo plane, then the
-                    // biased core mismatch count c' = c + 7 - total_max (a hit is d + c' <= 7);
-                    // one 8-byte store per entry
-                    ent[pos] = make_uint2(dh | (dlo << a.dl) | ((cmm + a.cbias) << (2 * a.dl)), g);
+                if (a.entries) {
+                    // the guide's distal letters and the biased core mismatch count of this variant,
+                    // c' = c + 7 - total_max (a hit is d + c' <= 7); one 8-byte store per entry
+                    ent[pos] = make_uint2(letters | (min(cmm + a.cbias, 15u) << 20), g);
                 } else {
                     // key = distal planes in two fields of `field` bits; the core mismatches of this
                     // variant are appended to the hi field as that many 1-bits, which the window's
@@ -1124,83 +928,13 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
     return (double)v.size() * (double)n_guides < 1.5e9;  // entries are addressed with 32 bits (12 GB)
 }
 
-// ---- bit-sliced copy of the index (join over the site table, core 10 / distal 10 only) ----------
-//
-// The popc compare costs ~8 issue slots per key (XOR, shift, OR/AND, POPC, min/compare, register
-// rotation) and the join is bound by exactly that.  Transposing the keys removes most of it.  Per
-// block of 32 keys the index holds 44 words in which bit k belongs to key k: for each of the 10
-// distal bases the four words "key k differs from letter c here" (c = A, C, G, T), then the 4 bit
-// planes of c' = core mismatches + 7 - total_max.  A window thread loads, per base, the word of its
-// own letter -- ten 4-byte loads are the ten mismatch words, no XOR/OR stage -- and an 18-LOP3
-// carry-save tree tells where d + c' reaches 8 (= no hit).  ~35 issue slots per 32 keys, no POPC.
-// Pad slots of a bucket's last block hold c' = 15 and never hit.
-
-// One warp per block of 32 staged keys: lane k loads key k, a 5-stage butterfly (shuffle + masked
-// merge, the recursive 2x2 block transpose of a 32x32 bit matrix) leaves lane j with bit plane j of
-// the 32 keys; lanes 0..9 pair their hi plane with the lo plane of lane j + 10 and write the four
-// per-letter words of base j, lanes 20..23 write the c' planes: 176 bytes per block.
-__global__ void __launch_bounds__(256) idx_transpose_kernel(const uint2 *ent, const uint32_t *offsets, uint32_t key_lo,
-                                                             uint32_t key_hi, uint32_t *planes) {
-    constexpr int U = 4;  // blocks per warp iteration: independent loads in flight
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * 8u;
-    // the blocks of the buckets [key_lo, key_hi): bucket starts are multiples of 32 slots
-    const uint32_t blk_lo = (__ldg(&offsets[key_lo]) & ~31u) >> 5, n_blocks = (__ldg(&offsets[key_hi]) & ~31u) >> 5;
-    for (uint32_t blk = blk_lo + (blockIdx.x * 8u + (threadIdx.x >> 5)) * U; blk < n_blocks; blk += warps * U) {
-        uint32_t x[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) x[u] = blk + u < n_blocks ? __ldg(&ent[(size_t)(blk + u) * 32 + lane]).x : 0u;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint32_t m = 0x0000ffffu;
-#pragma unroll
-            for (int j = 16; j; j >>= 1) {
-                const uint32_t y = __shfl_xor_sync(kFull, x[u], j);
-                // rows without bit j keep their low columns and take the partner's low columns as
-                // their high ones; rows with bit j do the opposite
-                x[u] = (lane & j) ? ((x[u] & ~m) | ((y & ~m) >> j)) : ((x[u] & m) | ((y & m) << j));
-                m ^= m << (j >> 1);
-            }
-            // lane j < 10 holds the hi-plane word of base j and fetches the lo-plane word from lane
-            // j + 10; it writes the four "differs from letter c" words, c = 2 * hi + lo
-            const uint32_t kl = __shfl_down_sync(kFull, x[u], 10);
-            if (blk + u < n_blocks) {
-                uint32_t *blockp = planes + (size_t)(blk + u) * kSliceWords;
-                if (lane < 10) {
-                    const uint32_t kh = x[u];
-                    reinterpret_cast<uint4 *>(blockp)[lane] = make_uint4(kh | kl, kh | ~kl, ~kh | kl, ~kh | ~kl);
-                } else if (lane >= 20 && lane < 24) {
-                    blockp[40 + (lane - 20)] = x[u];
-                }
-            }
-        }
-    }
-}
-
-// Worth it when buckets hold at least half a block on average: below that the padding to whole
-// 32-key blocks (memset, transpose, compare) costs more than the popc walk over 8-key sectors.
-// GUIDO_OT_SLICED=0/1 forces the choice (tests, tuning).
-static bool ot_sliced_applicable(const OtParams &op, int64_t n_guides) {
-    if (op.core_len != 10 || op.total_max < 0 || op.total_max > 7 || op.core_max > 3) return false;
-    if (const char *f = getenv("GUIDO_OT_SLICED")) return atoi(f) != 0;
-    std::vector<uint32_t> v;
-    enumerate_variants(op.core_len, op.core_max, &v);
-    return (double)v.size() * (double)n_guides >= 16.0 * (double)(1u << (2 * op.core_len));
-}
-
-__global__ void __launch_bounds__(256) idx_pad_fill_kernel(uint4 *ent2, const uint32_t *offsets, uint32_t key_lo, uint32_t key_hi) {
-    // the slots of the buckets [key_lo, key_hi), two 8-byte entries per uint4
-    const uint32_t lo = (__ldg(&offsets[key_lo]) & ~31u) / 2, n = (__ldg(&offsets[key_hi]) & ~31u) / 2;
-    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    for (uint32_t i = lo + blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) ent2[i] = ff;
-}
-
-// builds the guide-side seed index of this search in ds->d_bucket / ds->d_index; with `sliced` the
-// keys are additionally transposed into 32-key bit-plane blocks (buckets padded to whole blocks)
+// builds the guide-side seed index of this search in ds->d_bucket / ds->d_index.  `entries`: one
+// 8-byte {letters | bias, guide} entry per key, buckets unpadded (the block join); otherwise the
+// key / guide-id arrays of the popc kernels with buckets padded to 8 keys.
 // `part_bits` / `part_ix`: only the buckets whose top part_bits key bits equal part_ix are built (the
 // share of the key space this handle's site table covers); 0 / 0 = everything
 static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
-                             bool sliced, int part_bits, int part_ix, cudaStream_t stream, int *n_launches,
+                             bool entries, int part_bits, int part_ix, cudaStream_t stream, int *n_launches,
                              OtIndex *out, const std::function<int(uint32_t, uint32_t)> *after_slice = nullptr) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
@@ -1221,20 +955,19 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
-    // every bucket is padded to a multiple of 8 slots (32 when sliced); worst case allocated
-    const uint32_t pad = sliced ? 32u : 8u;
-    const uint64_t n_slots = (n_entries + (uint64_t)(pad - 1) * n_buckets + 31) & ~(uint64_t)31;
+    // popc format: every bucket is padded to a multiple of 8 slots; worst case allocated
+    const uint32_t pad = entries ? 0u : 8u;
+    const uint64_t n_slots = (n_entries + (uint64_t)(pad ? pad - 1 : 0) * n_buckets + 31) & ~(uint64_t)31;
     if (n_slots >= (1ull << 32)) { set_error("seed index too large"); return GUIDO_ERR_ARG; }
-    // d_index: [keys n_slots][ids n_slots][planes n_slots / 32 * 24 (sliced)]
-    const int64_t index_bytes = (int64_t)n_slots * 8 + (sliced ? (int64_t)(n_slots / 32) * kSliceWords * 4 : 0);
-    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, index_bytes))) return rc;
+    // d_index: [keys n_slots][ids n_slots], or n_slots 8-byte entries
+    if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_slots * 8))) return rc;
     uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
              *d_var = sums + n_scan_blocks;
-    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots, *planes = ids + n_slots;
+    uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots;
     const int field = dl + op.core_max;  // <= 16, checked by ot_index_applicable
     GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
-    // The fill scatters 8-byte entries all over a ~0.5 GB index: done in one go every store dirties
-    // its own 32-byte sector in DRAM (8x write amplification).  Filling one slice of the bucket
+    // The fill scatters 8-byte entries all over a ~0.35 GB index: done in one go every store dirties
+    // its own 32-byte sector in DRAM (4x write amplification).  Filling one slice of the bucket
     // range at a time -- the buckets that share their top slice_bits key bits -- keeps the slice
     // L2-resident, so DRAM sees whole lines.  Expected slots actually used (uniform keys: half a
     // pad unit per bucket) size the slices.
@@ -1262,7 +995,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     ia.slice_bits = (uint32_t)slice_bits; ia.slice = 0;
     ia.part_shift = (uint32_t)(2 * cl - part_bits); ia.part_ix = (uint32_t)part_ix; ia.part_on = part_bits > 0;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
-    ia.pad_mask = pad - 1; ia.sliced = sliced ? 1 : 0; ia.cbias = sliced ? (uint32_t)(7 - op.total_max) : 0u;
+    ia.pad_mask = pad ? pad - 1 : 0; ia.entries = entries ? 1 : 0; ia.cbias = entries ? (uint32_t)(7 - op.total_max) : 0u;
     const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
     int n_count_launches = 1;
     if (dp_counts) {
@@ -1279,28 +1012,24 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     }
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, pad - 1);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, ia.pad_mask);
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
     const int wide = force ? atoi(force) : 2;
-    *out = OtIndex{counts, keys, ids, cl, dl, field, wide, sliced ? (const uint4 *)planes : nullptr};
-    // Slice by slice: pads (c' = 15: all slots of the slice's buckets are set, the fill then
-    // overwrites the real entries -- a per-bucket pad writer was measured slower), fill, transpose.
-    // The slot ranges are read from the scanned offsets on the device.  After each slice the caller
-    // may start consuming it (`after_slice`: the join of the table rows of that key range).
+    *out = OtIndex{counts, keys, ids, cl, dl, field, wide};
+    // Slice by slice; the slot ranges are read from the scanned offsets on the device.  After each
+    // slice the caller may start consuming it (`after_slice`: the join of that key range).
     const uint32_t per_part = 1u << (slice_bits - part_bits);
     const int key_shift = 2 * cl - slice_bits;
     for (uint32_t p = (uint32_t)part_ix * per_part; p < ((uint32_t)part_ix + 1) * per_part; p++) {
         const uint32_t key_lo = p << key_shift, key_hi = (p + 1) << key_shift;
-        if (sliced) idx_pad_fill_kernel<<<ds->sm_count * 4, 256, 0, stream>>>(reinterpret_cast<uint4 *>(keys), counts, key_lo, key_hi);
         ia.slice = p;
         idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
-        if (sliced) idx_transpose_kernel<<<ds->sm_count * 4, 256, 0, stream>>>((const uint2 *)keys, counts, key_lo, key_hi, planes);
         GUIDO_CUDA(cudaGetLastError());
         if (after_slice && (rc = (*after_slice)(key_lo, key_hi))) return rc;
     }
-    if (n_launches) *n_launches += 3 + n_count_launches + (int)per_part * (sliced ? 3 : 1);
+    if (n_launches) *n_launches += 3 + n_count_launches + (int)per_part;
     return GUIDO_OK;
 }
 
@@ -1315,7 +1044,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
-    a.tab_a = a.tab_b = a.tab_q = a.tab_counts = a.tab_fill = nullptr; a.tab_kd = nullptr; a.tab_n = 0;
+    a.tab_slots = nullptr; a.tab_counts = a.tab_fill = nullptr; a.tab_n = 0;
     rc = launch_ot_kernel<kModeIndex>(ds, a, stream);
     if (rc) return rc;
     if (n_launches) *n_launches += 1;
@@ -1326,19 +1055,20 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
 //
 // Genome-side index: the PAM-valid windows of the resident shard in guide orientation, grouped by
 // core key (counting sort: histogram pass, scan, scatter pass -- both passes are the search front
-// end with a different consumer).  20 bytes per window (7.7 GB for NGG on 3.1 Gb), built once per
-// (PAM sets, core length) and kept until the image is released or other parameters are asked for.
-// It plays the role of the reference's bowtie index files (genome.py:157-168): guide-independent,
-// part of the built genome.
+// end with a different consumer).  Every bucket is padded to whole blocks of 32 slots.  Per slot 16
+// bytes {position, hi plane | strand, lo plane, core key} -- read for hits, and by the popc join --
+// plus, for 10-base cores, 5 bytes of the bit-sliced block form the block join streams
+// (join_blocks.cu): ~8.4 GB for NGG on 3.1 Gb.  Built once per (PAM sets, core length) and kept
+// until the image is released or other parameters are asked for.  It plays the role of the
+// reference's bowtie index files (genome.py:157-168): guide-independent, part of the built genome.
 
 void release_site_table(DeviceState *ds) {
-    if (ds->d_site_a) cudaFree(ds->d_site_a);
-    if (ds->d_site_b) cudaFree(ds->d_site_b);
-    if (ds->d_site_q) cudaFree(ds->d_site_q);
-    if (ds->d_site_kd) cudaFree(ds->d_site_kd);
-    ds->d_site_a = ds->d_site_b = ds->d_site_q = nullptr;
-    ds->d_site_kd = nullptr;
+    if (ds->d_site_slots) cudaFree(ds->d_site_slots);
+    if (ds->d_site_blocks) cudaFree(ds->d_site_blocks);
+    ds->d_site_slots = nullptr;
+    ds->d_site_blocks = nullptr;
     ds->site_cap = 0;
+    ds->site_slots = 0;
     ds->site_n = -1;
 }
 
@@ -1369,61 +1099,87 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     const uint32_t n_buckets = 1u << (2 * cl);
     const uint32_t n_scan = n_buckets + 1, n_scan_blocks = (n_scan + 4095) / 4096;
     int rc;
-    if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, ((int64_t)n_scan + n_buckets + n_scan_blocks + 16) * 4))) return rc;
-    uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets;
-    GUIDO_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_scan + n_buckets) * 4, stream));
+    if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, ((int64_t)n_buckets + n_scan_blocks + 16) * 4))) return rc;
+    // the bucket offsets belong to the table (the joins read them), the fill cursors are scratch
+    if (ds->d_site_off) { cudaFree(ds->d_site_off); ds->d_site_off = nullptr; }
+    GUIDO_CUDA(cudaMalloc(&ds->d_site_off, (size_t)n_scan * 4));
+    if (!ds->d_tickets) GUIDO_CUDA(cudaMalloc(&ds->d_tickets, 64 * sizeof(uint32_t)));
+    uint32_t *counts = ds->d_site_off, *fill = (uint32_t *)ds->d_bucket, *sums = fill + n_buckets;
+    GUIDO_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_scan * 4, stream));
+    GUIDO_CUDA(cudaMemsetAsync(fill, 0, (size_t)n_buckets * 4, stream));
     GUIDO_CUDA(cudaMemsetAsync(ds->d_counts + 4, 0, 2 * sizeof(unsigned long long), stream));
     GUIDO_CUDA(cudaEventRecord(ds->ev[1], stream));
     OtScanArgs a;
     a.pv = pv; a.op = op; a.r = r;
-    a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0, nullptr};
+    a.ix = OtIndex{nullptr, nullptr, nullptr, cl, dl, 0, 0};
     a.guides = nullptr; a.n_guides = 0;
     a.hits = nullptr; a.cap = 0; a.count = nullptr; a.flags = nullptr;
     a.site_count = ds->d_counts + 4;  // every PAM-valid window of the shard, 64-bit: guards the 32-bit scan
-    a.tab_a = a.tab_b = a.tab_q = nullptr; a.tab_kd = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
+    a.tab_slots = nullptr; a.tab_counts = counts; a.tab_fill = fill; a.tab_n = 0;
     a.tab_key_span = n_buckets >> part_bits_of(ds);
     a.tab_key_lo = a.tab_key_span * (uint32_t)ds->site_part_ix;
     if ((rc = launch_ot_kernel<kModeTabCount>(ds, a, stream))) return rc;
-    // bucket starts; the entry behind the last bucket is the number of rows
-    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 0);
+    // A 32-bit scan of the padded counts: refuse before it can wrap (every bucket gains < 32 slots)
+    unsigned long long seen[2] = {0, 0};  // windows of the shard, windows in this handle's key range
+    GUIDO_CUDA(cudaMemcpyAsync(seen, ds->d_counts + 4, sizeof seen, cudaMemcpyDeviceToHost, stream));
+    GUIDO_CUDA(cudaStreamSynchronize(stream));
+    const unsigned long long all_windows = seen[1];
+    if (seen[0] >= (1ull << 31)) return GUIDO_ERR_CAPACITY;  // 32-bit slot numbers (and the scan) end here
+    // bucket starts, every bucket rounded up to whole blocks of 32 slots (the pad count rides in the
+    // low 5 bits); the entry behind the last bucket is the number of slots
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 32);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, 0);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, 31);
     uint32_t total = 0;
-    unsigned long long all_windows = 0;
-    for (int k = 0; k <= 32; k++)  // first row of every 1/32 of the key space: the join's slice boundaries
+    for (int k = 0; k <= 32; k++)  // first slot of every 1/32 of the key space: the join's slice boundaries
         GUIDO_CUDA(cudaMemcpyAsync(&ds->site_row_off[k], counts + (size_t)k * (n_buckets / 32), sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaMemcpyAsync(&total, counts + n_buckets, sizeof total, cudaMemcpyDeviceToHost, stream));
-    GUIDO_CUDA(cudaMemcpyAsync(&all_windows, ds->d_counts + 4, sizeof all_windows, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
-    if (all_windows >= (1ull << 31)) return GUIDO_ERR_CAPACITY;  // 32-bit row numbers (and the scan) end here
-    if ((int64_t)total > ds->site_cap) {
+    for (int k = 0; k <= 32; k++) ds->site_row_off[k] &= ~31u;
+    total &= ~31u;
+    const bool want_blocks = dl == 10;  // the block join is written for ten distal bases
+    if ((int64_t)total > ds->site_cap || (want_blocks && !ds->d_site_blocks)) {
         release_site_table(ds);
         size_t free_b = 0, total_b = 0;
         GUIDO_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const int64_t cap = (int64_t)total + 1024;
-        if ((uint64_t)cap * kSiteRowBytes + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
+        const uint64_t bytes = (uint64_t)cap * kSiteSlotBytes + (want_blocks ? (uint64_t)(cap / 32) * kSiteBlockWords * 4 : 0);
+        if (bytes + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
         // GUIDO_SITE_TABLE_MAX_MB: cap on the table size (tests of the streaming fallback, shared GPUs)
         if (const char *lim = getenv("GUIDO_SITE_TABLE_MAX_MB"))
-            if ((uint64_t)cap * kSiteRowBytes > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
-        GUIDO_CUDA(cudaMalloc(&ds->d_site_a, (size_t)cap * 4));
-        GUIDO_CUDA(cudaMalloc(&ds->d_site_b, (size_t)cap * 4));
-        GUIDO_CUDA(cudaMalloc(&ds->d_site_q, (size_t)cap * 4));
-        GUIDO_CUDA(cudaMalloc(&ds->d_site_kd, (size_t)cap * 8));
+            if (bytes > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
+        GUIDO_CUDA(cudaMalloc(&ds->d_site_slots, (size_t)cap * kSiteSlotBytes));
+        if (want_blocks) GUIDO_CUDA(cudaMalloc(&ds->d_site_blocks, (size_t)(cap / 32) * kSiteBlockWords * 4));
         ds->site_cap = cap;
     }
-    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
+    // pad slots keep position ~0 (never a window: the image ends below 2^32 - 23)
+    GUIDO_CUDA(cudaMemsetAsync(ds->d_site_slots, 0xff, (size_t)total * kSiteSlotBytes, stream));
+    a.tab_slots = ds->d_site_slots;
     a.site_count = nullptr;
     if ((rc = launch_ot_kernel<kModeTabFill>(ds, a, stream))) return rc;
+    if (want_blocks && (rc = launch_site_blocks(ds, ds->d_site_slots, total / 32, dl, ds->d_site_blocks, stream))) return rc;
     GUIDO_CUDA(cudaEventRecord(ds->ev[2], stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
     cudaEventElapsedTime(&ds->site_build_ms, ds->ev[1], ds->ev[2]);
-    ds->site_n = (int64_t)total;
+    ds->site_n = (int64_t)all_windows;
+    ds->site_slots = (int64_t)total;
     ds->site_core_len = cl; ds->site_pam_len = op.pam.len;
     ds->site_tab_part_ix = ds->site_part_ix; ds->site_tab_n_parts = ds->site_n_parts;
     for (int k = 0; k < kMaxPam; k++) { ds->site_fw[k] = op.pam.fw[k]; ds->site_rv[k] = op.pam.rv[k]; }
     if (built) *built = true;
     return GUIDO_OK;
+}
+
+// The block join pays per (32 entries x 32 slots); it wins once buckets hold enough of both.
+// GUIDO_OT_BLOCKS=0/1 forces the choice (tests, tuning).
+static bool ot_blocks_applicable(const DeviceState *ds, const OtParams &op, int64_t n_guides) {
+    if (!ds->d_site_blocks || op.core_len != 10 || op.total_max < 0 || op.total_max > 7 || op.core_max > 3) return false;
+    if (const char *f = getenv("GUIDO_OT_BLOCKS")) return atoi(f) != 0;
+    std::vector<uint32_t> v;
+    enumerate_variants(op.core_len, op.core_max, &v);
+    const double n_buckets = (double)(1u << (2 * op.core_len)) / ds->site_tab_n_parts;
+    return (double)v.size() * (double)n_guides / ds->site_tab_n_parts >= 8.0 * n_buckets && (double)ds->site_n >= 64.0 * n_buckets;
 }
 
 int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
@@ -1434,39 +1190,68 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     if (!site_table_matches(ds, op)) { set_error("PAM-site table was not built for these parameters"); return GUIDO_ERR_ARG; }
     if (ds->site_n == 0) return GUIDO_OK;
     OtScanArgs a;
-    const bool sliced = ot_sliced_applicable(op, n_guides);
+    const bool blocks = ot_blocks_applicable(ds, op, n_guides);
     a.pv = pv; a.op = op; a.r = r;
     a.guides = d_guides; a.n_guides = (uint32_t)n_guides;
     a.hits = d_hits; a.cap = cap; a.count = d_count; a.flags = nullptr; a.site_count = d_site_count;
-    a.tab_a = ds->d_site_a; a.tab_b = ds->d_site_b; a.tab_q = ds->d_site_q; a.tab_kd = ds->d_site_kd;
+    a.tab_slots = ds->d_site_slots;
     a.tab_counts = a.tab_fill = nullptr;
     a.first_block = 0; a.n_tiles = 0;
     int per_sm = 0;
-    if (sliced) GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_sliced_kernel, kThreads, 0));
-    else GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
+    GUIDO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ot_join_kernel, kThreads, 0));
     const int max_grid = ds->sm_count * std::max(per_sm, 1) * 4;  // 4 waves' worth of CTAs evens out the tail
+    if (d_site_count) {  // statistics: windows of the table (the kernels add the entries they compare)
+        const unsigned long long n_windows = (unsigned long long)ds->site_n;
+        GUIDO_CUDA(cudaMemcpyAsync(d_site_count, &n_windows, sizeof n_windows, cudaMemcpyHostToDevice, stream));
+    }
+    BjArgs bj;
+    bj.blocks = ds->d_site_blocks; bj.blk_off = ds->d_site_off; bj.slots = ds->d_site_slots;
+    bj.ent = nullptr; bj.ent_off = nullptr; bj.key_lo = bj.key_hi = 0; bj.group = bj.n_groups = 0;
+    bj.ticket = ds->d_tickets; bj.hits = d_hits; bj.cap = cap; bj.count = d_count; bj.site_count = d_site_count;
+    const int cl = op.core_len;
+    const int part_bits = part_bits_of(ds);
+    const uint32_t part_keys = (1u << (2 * cl)) >> part_bits;
+    const uint32_t part_lo = part_keys * (uint32_t)ds->site_part_ix;
+    if (blocks) GUIDO_CUDA(cudaMemsetAsync(ds->d_tickets, 0, 64 * sizeof(uint32_t), stream));
 
-    // The index is built slice by slice (a slice = the buckets that share their top key bits) on a
-    // second, high-priority stream; the table rows are in key order, so as soon as a slice is ready
-    // the join of ITS rows starts on the caller's stream while the next slice is being filled: the
-    // scatter-bound build (atomics, little issue pressure) hides behind the issue-bound join.
+    // one join launch over the keys [key_lo, key_hi) on stream s
+    int n_joins = 0;
+    auto join_keys = [&](uint32_t key_lo, uint32_t key_hi, cudaStream_t s) -> int {
+        const uint32_t unit = (1u << (2 * cl)) / 32;
+        if (blocks) {
+            bj.ent = reinterpret_cast<const uint2 *>(a.ix.keys); bj.ent_off = a.ix.offsets;
+            bj.key_lo = key_lo; bj.key_hi = key_hi; bj.ticket = ds->d_tickets + (n_joins % 64);
+            int rc = launch_join_blocks(ds, bj, s);
+            if (rc) return rc;
+        } else {
+            a.tab_lo = ds->site_row_off[key_lo / unit];
+            a.tab_n = ds->site_row_off[key_hi / unit];
+            if (a.tab_n <= a.tab_lo) return GUIDO_OK;
+            const uint32_t n_chunks = (a.tab_n - a.tab_lo + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
+            const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
+            ot_join_kernel<<<grid, kThreads, 0, s>>>(a);
+            GUIDO_CUDA(cudaGetLastError());
+        }
+        n_joins++;
+        return GUIDO_OK;
+    };
+
+    // The index is built slice by slice (a slice = the buckets that share their top key bits); the
+    // table is in key order, so as soon as a slice is ready the join of ITS buckets can start on
+    // the caller's stream while the next slice is being filled on a second, high-priority stream:
+    // the scatter-bound build (atomics, little issue pressure) hides behind the ALU-bound join.
     // GUIDO_OT_OVERLAP=0 (measurement knob): everything on the caller's stream, ONE join launch over
     // the whole table after the index is complete -- guido_kernel_times then reports the join
     // kernel timed alone (bench.py's roofline pass); the results are the same either way.
     const char *ov = getenv("GUIDO_OT_OVERLAP");
     if (ov && atoi(ov) == 0) {
-        int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, stream,
-                                   n_launches, &a.ix);
+        int rc = build_guide_index(ds, op, d_guides, n_guides, blocks, part_bits, ds->site_part_ix, stream, n_launches, &a.ix);
         if (rc) return rc;
-        a.tab_lo = 0; a.tab_n = (uint32_t)ds->site_n;
-        const uint32_t n_chunks = (a.tab_n + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
-        const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
         kev_begin(ds, stream);
-        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, stream>>>(a);
-        else ot_join_kernel<<<grid, kThreads, 0, stream>>>(a);
+        rc = join_keys(part_lo, part_lo + part_keys, stream);
         kev_end(ds, stream);
-        GUIDO_CUDA(cudaGetLastError());
-        if (n_launches) *n_launches += 1;
+        if (rc) return rc;
+        if (n_launches) *n_launches += n_joins;
         return GUIDO_OK;
     }
     if (!ds->build_stream) {
@@ -1482,28 +1267,16 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     GUIDO_CUDA(cudaEventRecord(ds->ev_slice[33], stream));        // guides are on the device, previous search is done
     GUIDO_CUDA(cudaStreamWaitEvent(sb, ds->ev_slice[33], 0));
     GUIDO_CUDA(cudaStreamWaitEvent(sj, ds->ev_slice[33], 0));
-    const int cl = op.core_len;
-    int n_joins = 0;
     const std::function<int(uint32_t, uint32_t)> join_slice = [&](uint32_t key_lo, uint32_t key_hi) -> int {
-        // rows of the keys [key_lo, key_hi): boundaries are multiples of 1/32 of the key space
         const uint32_t unit = (1u << (2 * cl)) / 32;
-        a.tab_lo = ds->site_row_off[key_lo / unit];
-        a.tab_n = ds->site_row_off[key_hi / unit];
         cudaEvent_t ready = ds->ev_slice[(key_lo / unit) % 31];
         GUIDO_CUDA(cudaEventRecord(ready, sb));
-        if (a.tab_n <= a.tab_lo) return GUIDO_OK;
         cudaStream_t s = (n_joins & 1) ? sj : stream;
         GUIDO_CUDA(cudaStreamWaitEvent(s, ready, 0));
-        const uint32_t n_chunks = (a.tab_n - a.tab_lo + kJoinPerThread * kThreads - 1) / (kJoinPerThread * kThreads);
-        const int grid = (int)std::min<uint32_t>((uint32_t)max_grid, n_chunks);
         if (n_joins == 0) kev_begin(ds, stream);  // guido_kernel_times: first join launch .. last join done
-        if (sliced) ot_join_sliced_kernel<<<grid, kThreads, 0, s>>>(a);
-        else ot_join_kernel<<<grid, kThreads, 0, s>>>(a);
-        GUIDO_CUDA(cudaGetLastError());
-        n_joins++;
-        return GUIDO_OK;
+        return join_keys(key_lo, key_hi, s);
     };
-    int rc = build_guide_index(ds, op, d_guides, n_guides, sliced, part_bits_of(ds), ds->site_part_ix, sb, n_launches,
+    int rc = build_guide_index(ds, op, d_guides, n_guides, blocks, part_bits, ds->site_part_ix, sb, n_launches,
                                &a.ix, &join_slice);
     // the caller's stream continues when both join streams (and with them the build stream) are done
     GUIDO_CUDA(cudaEventRecord(ds->ev_slice[32], sj));

@@ -130,16 +130,16 @@ def _protos_from_genome(rng, contigs, n, mutate=3):
     ("NRG", dict(core_mismatches=1)),
     ("TGG", dict(core_mismatches=3, total_mismatches=4)),
 ])
-@pytest.mark.parametrize("algo", ["scan", "index", "table", "table-sliced"])
+@pytest.mark.parametrize("algo", ["scan", "index", "table", "table-blocks"])
 def test_offtarget_scan_matches_oracle(native, oracle, monkeypatch, pam, kw, algo):
-    if algo == "table-sliced":  # bit-sliced compare of the join (only taken for core length 10)
-        monkeypatch.setenv("GUIDO_OT_SLICED", "1")
+    if algo == "table-blocks":  # bit-sliced compare of the join (only taken for core length 10)
+        monkeypatch.setenv("GUIDO_OT_BLOCKS", "1")
     contigs = util.synthetic_contigs(21, [60000, 25000, 300], n_runs=4, iupac=5)
     rng = np.random.default_rng(3)
     protos = _protos_from_genome(rng, contigs, 60)
     img = native.Image.from_seqs(contigs).upload()
     hits, flags = img.offtarget_search(protos, pam=pam, algo={"scan": native.OT_SCAN, "index": native.OT_INDEX, "table": native.OT_TABLE,
-                                             "table-sliced": native.OT_TABLE}[algo], **kw)
+                                             "table-blocks": native.OT_TABLE}[algo], **kw)
     valid, keys = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
     assert util.gpu_hit_set(img, hits) == valid
     assert len(hits) == len(valid)
@@ -274,7 +274,7 @@ def test_offtarget_guides_are_packed_on_the_device(native):
 def test_offtarget_join_variants(native, monkeypatch, total, sliced):
     """the table join has a bit-sliced compare (core 10, total <= 7) and a popc compare: both must
     give the brute-force hit list, whatever the mismatch budget"""
-    monkeypatch.setenv("GUIDO_OT_SLICED", "1" if sliced else "0")   # small guide sets default to popc
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", "1" if sliced else "0")   # small guide sets default to popc
     contigs = util.synthetic_contigs(28, [180000, 20000], n_runs=3)
     rng = np.random.default_rng(9)
     protos = _protos_from_genome(rng, contigs, 400, mutate=5)
@@ -309,7 +309,7 @@ def test_site_table_capacity_fallback(native, monkeypatch):
 def test_site_table_partition_union(native, monkeypatch, sliced):
     """key-range partition of the site table (the multi-GPU mode without replicated index builds):
     the parts' hit lists are disjoint and their union is the whole image's hit list"""
-    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", sliced)
     contigs = util.synthetic_contigs(30, [250000, 60000], n_runs=3)
     rng = np.random.default_rng(11)
     protos = _protos_from_genome(rng, contigs, 300, mutate=4)
@@ -356,7 +356,7 @@ def test_offtarget_raw_flags_entry_point(native, oracle):
 def test_offtarget_join_big_buckets(native, monkeypatch, sliced):
     """many copies of the same guides: buckets of several hundred keys, i.e. more than the two
     32-key blocks the sliced join evaluates per round (pointer-advance path), and long popc walks"""
-    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", sliced)
     contigs = util.synthetic_contigs(32, [200000], n_runs=2)
     rng = np.random.default_rng(13)
     img = native.Image.from_seqs(contigs).upload()

@@ -125,7 +125,7 @@ def test_join_schedules_agree(native, monkeypatch, sliced):
     """The join launched slice by slice next to the index build (default) and as one launch after
     the build (GUIDO_OT_OVERLAP=0, bench.py's roofline pass) return the same list; so do several
     index slices (GUIDO_IDX_SLICE_MB=1, small enough to cut this index into the maximum of 32)."""
-    monkeypatch.setenv("GUIDO_OT_SLICED", sliced)
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", sliced)
     img, protos = _case(native, seed=31, n=400)
     want, wf = img.offtarget_search(protos, algo=native.OT_SCAN)
     for env in ({}, {"GUIDO_OT_OVERLAP": "0"}, {"GUIDO_IDX_SLICE_MB": "1"},
