@@ -304,8 +304,8 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     if algo in (N.OT_AUTO, N.OT_TABLE):
         n_sites, build_ms = img.site_table_build(PAM, OT_KW["core_length"])
         # 16 B per slot (position, planes, key: read for hits) + 5 B per slot of bit-sliced blocks (what
-        # the join streams); buckets are padded to whole blocks of 32 slots
-        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 21 * n_sites + 21 * 16 * (4 ** OT_KW["core_length"]) // R.world,
+        # the join streams); buckets are padded to whole blocks of 64 slots
+        table = {"sites_per_gpu": n_sites, "bytes_per_gpu": 21 * n_sites + 21 * 32 * (4 ** OT_KW["core_length"]) // R.world,
                  "build_ms": build_ms}
     # kernels per search: one host-API call reports its launches; the device sort (split + radix
     # passes + merge) belongs to that call only
@@ -383,8 +383,8 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
     hits_rank = float(d_count.item())
     if table is not None:
-        # join over the site table.  Block join (>= 8 keys per bucket): 5 B per table slot (the 160-byte
-        # blocks of 32 windows, buckets padded to whole blocks: + 16 slots per bucket on average), 8 B per
+        # join over the site table.  Block join (>= 8 keys per bucket): 5 B per table slot (the 320-byte
+        # blocks of 64 windows, buckets padded to whole blocks: + 32 slots per bucket on average), 8 B per
         # index entry, 8 B of bucket offsets per bucket, and 40 B per hit (8-byte entry and 16-byte slot
         # read at flush time, 16-byte record written).  Popc walk (small guide sets): 16 B per slot,
         # 4 B per key, 4 B per bucket offset, 36 B per hit.
@@ -392,7 +392,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
         n_keys = float(n_guides) * sum(comb(OT_KW["core_length"], k) * 3 ** k for k in range(OT_KW["core_mismatches"] + 1))
         n_buckets = 4.0 ** OT_KW["core_length"]
         parts = R.world if getattr(R.a, "key_sharded", False) else 1  # key-sharded ranks build 1/N of the index
-        slots = sites + 16.0 * n_buckets / parts
+        slots = sites + 32.0 * n_buckets / parts
         if n_keys >= 8.0 * n_buckets and sites * parts >= 64.0 * n_buckets:
             alg_bytes_rank = 5.0 * slots + (8.0 * n_keys + 8.0 * n_buckets) / parts + 40.0 * hits_rank
         else:
@@ -497,7 +497,7 @@ def main():
                   "ot_kernel<index>" if use_index else "ot_kernel<scan>")
         algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
                      "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
-        alg_desc = ("per GPU: 5 B per slot of the bit-sliced site table (buckets padded to 32 slots) + 8 B per index "
+        alg_desc = ("per GPU: 5 B per slot of the bit-sliced site table (buckets padded to 64 slots) + 8 B per index "
                     "entry + 8 B of offsets per bucket + 40 B per hit; the compare itself is ALU-pipe bound, see "
                     "int_pipe" if sliced else
                     "per GPU: 16 B per table slot + 4 B per index key + 4 B per bucket offset + 36 B per hit" if use_table else

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libguido_b200.so")
+# GUIDO_B200_LIB: another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("GUIDO_B200_LIB") or os.path.join(_HERE, "lib", "libguido_b200.so")
 
 OK, ERR_ARG, ERR_IO, ERR_CUDA, ERR_CAPACITY, ERR_PAM, ERR_NOMEM = range(7)
 SCAN_REGEX, SCAN_GUIDE, SCAN_STRICT = 0, 1, 2

@@ -1,5 +1,5 @@
 // join_blocks.cu -- the off-target join for large guide sets: guide-side seed index (entries in
-// bucket order) x genome-side PAM-site table in BIT-SLICED BLOCKS OF 32 WINDOWS.
+// bucket order) x genome-side PAM-site table in BIT-SLICED BLOCKS OF 64 WINDOWS.
 //
 // Sits under run_bowtie (reference guido/off_targets.py:89-227), like offtarget.cu.
 //
@@ -7,24 +7,27 @@
 // PAM-valid windows with that core, the same bucket of the seed index the guides whose core is
 // within the seed budget of it.  What is left per bucket is W windows x K entries distal compares
 // (human genome, 100 k guides: W ~ 366, K ~ 42).  The table is guide independent, so IT is the side
-// that is bit-sliced, once, when it is built: a block of 32 windows stores, per distal base j and
-// letter c, the word "window i differs from c at base j" (bit i) -- 40 words, 160 bytes, 5 bytes
-// per window.  Buckets are padded to whole blocks (366 -> 384: 5 % pad slots instead of the 35 % of
-// the round-1 layout that sliced the ~42 keys of a bucket into 64 slots).
+// that is bit-sliced, once, when it is built: a block of 64 windows stores, per distal base j and
+// letter c, the 64-bit word "window i differs from c at base j" (bit i) -- 40 words, 320 bytes,
+// 5 bytes per window.  Buckets are padded to whole blocks (366 -> 384: 5 % pad slots instead of the
+// 35 % of the round-1 layout that sliced the ~42 keys of a bucket into 64 slots).
 //
 // One LANE owns one index entry (a guide filed under this core): its ten letters select ten words
-// of a block -- ten 4-byte shared-memory loads at per-lane addresses fixed for the whole bucket --
-// and an 18-LOP3 carry-save tree says for which of the 32 windows (distal mismatches + bias)
+// of a block -- ten 8-byte shared-memory loads at per-lane addresses fixed for the whole bucket --
+// and a carry-save tree of LOP3s says for which of the 64 windows (distal mismatches + bias)
 // reaches 8, bias = core mismatches of the entry + 7 - total_max: no XOR/OR stage, no POPC, no
-// per-window set-up.  Entries beyond a multiple of 32 do not get a whole pass of their own: 16 or
-// fewer left-over entries share the lanes 2 or 4 ways and each copy takes every 2nd / 4th block.
+// per-window set-up.  18 LOP3 per 32 windows in general; 14 when every lane of the pass has bias 5
+// ("at most 2 of 10", the dominant class: the index files those entries first in every bucket).
+// Entries beyond a multiple of 32 do not get a whole pass of their own: 16 or fewer left-over
+// entries share the lanes 2 or 4 ways and each copy takes every 2nd / 4th block.
 //
-// Data movement: a WARP streams its buckets by itself.  Lane 0 fetches the blocks of the next
-// bucket with ONE bulk-TMA copy (cp.async.bulk -> UBLKCP, <= 2560 bytes, completion on the warp's
-// own mbarrier) into the other half of a double buffer while the warp compares the current one; no
+// Data movement: a WARP streams its buckets by itself.  Lane 0 fetches the blocks and the entries
+// of the next bucket with two bulk-TMA copies (cp.async.bulk -> UBLKCP, completion on the warp's own
+// mbarrier) into the other half of a double buffer while the warp compares the current one; no
 // CTA barrier anywhere in the loop.  Buckets are handed out in groups by an atomic ticket.
-// Non-empty result words are queued per warp as (word, entry, block) and turned into hit records
-// by all 32 lanes, 32 at a time (one atomic on the global cursor per flush).
+// Non-empty result words are queued per warp (one shared-memory atomic and one 16-byte store by
+// the lane that has one) and turned into hit records by all 32 lanes, 32 at a time: one atomic on
+// the global cursor per round, the gathers (guide id, window slot) go out behind it.
 #include "scan_common.cuh"
 #include "join_blocks.cuh"
 
@@ -32,15 +35,32 @@ namespace guido {
 
 namespace {
 
-constexpr int kBjWarps = 8;                      // warps per CTA (they do not interact)
-constexpr int kBjCapBlocks = 16;                 // blocks per stage buffer (larger buckets go in pieces)
-constexpr int kBjBlockWords = kSiteBlockWords;   // 40
-constexpr int kBjQueue = 96;                     // result words parked per warp (flushed from 64 on)
+#ifndef BJ_WARPS
+#define BJ_WARPS 8
+#endif
+#ifndef BJ_MIN_CTAS
+#define BJ_MIN_CTAS 3
+#endif
+constexpr int kBjWarps = BJ_WARPS;               // warps per CTA (they do not interact)
+constexpr int kBjCapBlocks = 7;                  // 64-window blocks per stage buffer (larger buckets go in pieces)
+constexpr int kBjCapEnt = 64;                    // entries per stage buffer (the rest of a bucket is read from global memory)
+constexpr int kBjBlockWords = kSiteBlockWords;   // 80 32-bit words = 40 x 64 bits
+constexpr int kBjQueue = 64;                     // result words parked per warp
+constexpr int kBjGroupMax = 16;                  // buckets per ticket, at most
+constexpr uint32_t kBjBiasAtMost2 = 5;           // bias of "at most 2 distal mismatches"
+
+struct __align__(16) BjStage {
+    uint2 blk[kBjCapBlocks * kBjBlockWords / 2]; // 2240 bytes, filled by a bulk copy
+    uint2 ent[kBjCapEnt];                        // 512 bytes, filled by a bulk copy
+};
 
 struct __align__(16) BjWarpSmem {
-    uint32_t blk[2][kBjCapBlocks * kBjBlockWords];  // 2 x 2560 bytes, filled by bulk copies
-    unsigned long long bar[2];                      // mbarriers: "buffer s is full"
-    uint32_t q_r[kBjQueue], q_e[kBjQueue], q_b[kBjQueue];
+    BjStage st[2];
+    uint4 meta[kBjGroupMax];                     // per bucket of the ticket: {first block, blocks, first entry, entries}
+    uint4 q[kBjQueue];                           // parked results: {hit bits of windows 0..31, 32..63, entry, block}
+    unsigned long long bar[2];                   // mbarriers: "stage s is full"
+    uint32_t qn;                                 // entries asked for in q (may run past kBjQueue: those went out directly)
+    uint32_t pad_[3];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,30 +83,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     } while (!ok);
 }
 
-__device__ __forceinline__ uint32_t lop_xor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
-__device__ __forceinline__ uint32_t lop_maj(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
-__device__ __forceinline__ uint32_t lop_nor3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x01;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
-}
+#define BJ_LOP3(name, lut)                                                                         \
+    __device__ __forceinline__ uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                 \
+        uint32_t r; asm("lop3.b32 %0, %1, %2, %3, " #lut ";" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; \
+    }
+BJ_LOP3(lop_xor3, 0x96)      // a ^ b ^ c
+BJ_LOP3(lop_maj, 0xe8)       // at least two of three
+BJ_LOP3(lop_nor3, 0x01)      // ~(a | b | c)
+BJ_LOP3(lop_or3, 0xfe)       // a | b | c
+BJ_LOP3(lop_and3, 0x80)      // a & b & c
+BJ_LOP3(lop_a_and_borc, 0xe0)  // a & (b | c)
+BJ_LOP3(lop_ab_or_c, 0xea)     // (a & b) | c
+#undef BJ_LOP3
 
 // what one lane keeps for the whole bucket: the ten word addresses of ITS letters in block 0 of the
 // stage buffer and the four bias words (bit planes of the entry's bias, 0 or ~0)
 struct LaneKey {
-    const uint32_t *p[10];
+    const uint2 *p[10];
     uint32_t q1, q2, q4, q8;
 };
 
-// bit i set <=> window i of the block `word_off` words further on is a hit for this lane's entry:
-// carry-save count of the ten mismatch words plus the bias; only "reaches 8" matters, so sums that
-// feed nothing are never formed (18 LOP3)
-__device__ __forceinline__ uint32_t block_hits(const LaneKey &k, int word_off) {
-    uint32_t m[10];
-#pragma unroll
-    for (int j = 0; j < 10; j++) m[j] = k.p[j][word_off + 4 * j];
+// bit i set <=> window i is a hit for this lane's entry: carry-save count of the ten mismatch words
+// plus the bias; only "reaches 8" matters, so sums that feed nothing are never formed (18 LOP3)
+__device__ __forceinline__ uint32_t tree_any(const uint32_t (&m)[10], const LaneKey &k) {
     // weight 1: eleven inputs -> five carries
     const uint32_t s0 = lop_xor3(m[0], m[1], m[2]), c0 = lop_maj(m[0], m[1], m[2]);
     const uint32_t s1 = lop_xor3(m[3], m[4], m[5]), c1 = lop_maj(m[3], m[4], m[5]);
@@ -104,97 +123,166 @@ __device__ __forceinline__ uint32_t block_hits(const LaneKey &k, int word_off) {
     return lop_nor3(e0, e1, k.q8);
 }
 
-// queued result words -> hit records.  Lane i takes queue entry i: the guide id comes from the
-// index entry, position and planes of each hit window from its slot of the table.
-__device__ __noinline__ void bj_flush(const BjArgs &a, BjWarpSmem &ws, uint32_t qn) {
+// the same for bias 5, i.e. "at most two of the ten words are set": with A = s0 + s1 + s2 + m9 and
+// C = c0 + c1 + c2 the count is A + 2 C, and it reaches 3 when C >= 2, or C = 1 and A >= 1, or
+// A >= 3 (14 LOP3)
+__device__ __forceinline__ uint32_t tree_at_most2(const uint32_t (&m)[10]) {
+    const uint32_t s0 = lop_xor3(m[0], m[1], m[2]), c0 = lop_maj(m[0], m[1], m[2]);
+    const uint32_t s1 = lop_xor3(m[3], m[4], m[5]), c1 = lop_maj(m[3], m[4], m[5]);
+    const uint32_t s2 = lop_xor3(m[6], m[7], m[8]), c2 = lop_maj(m[6], m[7], m[8]);
+    const uint32_t c_ge2 = lop_maj(c0, c1, c2), c_ge1 = lop_or3(c0, c1, c2);
+    const uint32_t s_any = lop_or3(s0, s1, s2), s_ge2 = lop_maj(s0, s1, s2), s_all = lop_and3(s0, s1, s2);
+    const uint32_t x = lop_a_and_borc(c_ge1, s_any, m[9]);   // C >= 1 and A >= 1
+    const uint32_t y = lop_ab_or_c(s_ge2, m[9], s_all);      // A >= 3
+    return lop_nor3(c_ge2, x, y);
+}
+
+// hit bits of one parked result -> records: the guide id comes from the index entry, position and
+// planes of each hit window from its slot of the table
+__device__ __forceinline__ void bj_write_hits(const BjArgs &a, uint32_t r, uint32_t guide, size_t slot0, unsigned long long &dst) {
+    while (r) {
+        const uint32_t bit = (uint32_t)__ffs((int)r) - 1u;
+        r &= r - 1u;
+        const uint4 s = __ldg(&a.slots[slot0 + bit]);
+        if (dst < a.cap) reinterpret_cast<uint4 *>(a.hits)[dst] = make_uint4(guide, s.x, s.y, s.z);
+        dst++;
+    }
+}
+
+// a lane whose result found the queue full takes it to the global list by itself (rare: more than
+// 33 non-empty results inside one pass, e.g. many copies of a guide against a repeat)
+__device__ __noinline__ void bj_emit_direct(const BjArgs &a, uint4 v) {
+    unsigned long long dst = atomicAdd(a.count, (unsigned long long)(__popc(v.x) + __popc(v.y)));
+    const uint32_t guide = __ldg(&a.ent[v.z]).y;
+    bj_write_hits(a, v.x, guide, (size_t)v.w * 64u, dst);
+    bj_write_hits(a, v.y, guide, (size_t)v.w * 64u + 32u, dst);
+}
+
+// parked results -> hit records, lane i takes entry i; only whole rounds of 32 unless `all`.  The
+// cursor is moved first and the gathers go out behind it, so a round costs one memory round trip.
+// Whatever stays is moved to the front of the queue.
+__device__ __noinline__ void bj_flush(const BjArgs &a, BjWarpSmem &ws, bool all) {
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t b0 = 0; b0 < qn; b0 += 32) {
-        const uint32_t i = b0 + lane;
-        uint32_t r = i < qn ? ws.q_r[i] : 0u;
-        const uint32_t e = i < qn ? ws.q_e[i] : 0u, gb = i < qn ? ws.q_b[i] : 0u;
-        const uint32_t n = (uint32_t)__popc(r);
+    const uint32_t qn = min(ws.qn, (uint32_t)kBjQueue);
+    uint32_t done = 0;
+    while (done + 32u <= qn || (all && done < qn)) {
+        const uint32_t i = done + lane;
+        const uint4 v = i < qn ? ws.q[i] : make_uint4(0, 0, 0, 0);
+        const uint32_t n = (uint32_t)(__popc(v.x) + __popc(v.y));
+        const uint32_t total = __reduce_add_sync(kFull, n);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.count, (unsigned long long)total);
+        uint32_t guide = 0;
+        uint4 s0 = make_uint4(0, 0, 0, 0);
+        uint32_t r0 = v.x, r1 = v.y;
+        if (n) {  // the common case is one hit in the result
+            guide = __ldg(&a.ent[v.z]).y;
+            const uint32_t first = r0 ? (uint32_t)__ffs((int)r0) - 1u : 32u + (uint32_t)__ffs((int)r1) - 1u;
+            s0 = __ldg(&a.slots[(size_t)v.w * 64u + first]);
+            if (r0) r0 &= r0 - 1u; else r1 &= r1 - 1u;
+        }
         uint32_t inc = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(kFull, inc, d);
             if (lane >= (uint32_t)d) inc += t;
         }
-        const uint32_t total = __shfl_sync(kFull, inc, 31);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.count, (unsigned long long)total);
         base = __shfl_sync(kFull, base, 0);
         unsigned long long dst = base + (inc - n);
-        if (r) {
-            const uint32_t guide = __ldg(&a.ent[e]).y;
-            while (r) {
-                const uint32_t bit = (uint32_t)__ffs((int)r) - 1u;
-                r &= r - 1u;
-                const uint4 s = __ldg(&a.slots[(size_t)gb * 32u + bit]);
-                if (dst < a.cap) reinterpret_cast<uint4 *>(a.hits)[dst] = make_uint4(guide, s.x, s.y, s.z);
-                dst++;
-            }
+        if (n) {
+            if (dst < a.cap) reinterpret_cast<uint4 *>(a.hits)[dst] = make_uint4(guide, s0.x, s0.y, s0.z);
+            dst++;
+            bj_write_hits(a, r0, guide, (size_t)v.w * 64u, dst);
+            bj_write_hits(a, r1, guide, (size_t)v.w * 64u + 32u, dst);
         }
+        done += 32u;
     }
+    const uint32_t left = done < qn ? qn - done : 0u;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (lane < left) v = ws.q[done + lane];
+    __syncwarp();
+    if (lane < left) ws.q[lane] = v;
+    if (lane == 0) ws.qn = left;
     __syncwarp();
 }
 
 // one pass of <= 32 entries (R of them valid) over the nblk blocks of the stage buffer; with
 // S = 2 / 4 the lanes hold S copies of <= 16 / 8 entries and copy s takes blocks s, s + S, ...
+// `e_first`: global index of the pass's first entry, `e_rel` its index inside the bucket.
 template <int S>
-__device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const uint32_t *buf, uint32_t nblk,
-                                        uint32_t gblk0, uint32_t e_first, uint32_t R, uint32_t &qn) {
+__device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const BjStage &st, uint32_t nblk,
+                                        uint32_t gblk0, uint32_t e_first, uint32_t e_rel, uint32_t R) {
     constexpr uint32_t kPer = 32 / S;
+    constexpr int kIters = (kBjCapBlocks + S - 1) / S;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r_ix = lane & (kPer - 1), s_ix = lane / kPer;
     const bool valid = r_ix < R;
     const uint32_t e = e_first + (valid ? r_ix : 0u);
-    const uint32_t w = valid ? __ldg(&a.ent[e]).x : (15u << 20);  // bias 15 never hits
+    uint32_t w = 15u << 20;  // bias 15 never hits
+    if (valid) w = e_rel + r_ix < (uint32_t)kBjCapEnt ? st.ent[e_rel + r_ix].x : __ldg(&a.ent[e]).x;
     LaneKey k;
 #pragma unroll
-    for (int j = 0; j < 10; j++) k.p[j] = buf + s_ix * kBjBlockWords + ((w >> (2 * j)) & 3u);
+    for (int j = 0; j < 10; j++) k.p[j] = st.blk + s_ix * (kBjBlockWords / 2) + ((w >> (2 * j)) & 3u);
     k.q1 = 0u - ((w >> 20) & 1u); k.q2 = 0u - ((w >> 21) & 1u); k.q4 = 0u - ((w >> 22) & 1u); k.q8 = 0u - ((w >> 23) & 1u);
-    const uint32_t lt = (1u << lane) - 1u;
+    // the short tree needs bias 5 in every lane (idle lanes carry 15 and must stay silent: they
+    // take the general tree's path too)
+    const bool at_most2 = S == 1 && __all_sync(kFull, ((w >> 20) & 15u) == kBjBiasAtMost2);
+    auto step = [&](const int it, const bool short_tree) {
+        uint32_t mx[10], my[10];
 #pragma unroll
-    for (int it = 0; it < kBjCapBlocks / S; it++) {
-        if ((uint32_t)(it * S) >= nblk) break;
-        uint32_t r = block_hits(k, it * S * kBjBlockWords);
-        if (S > 1 && it * S + s_ix >= nblk) r = 0;  // this copy's block is beyond the bucket
-        const uint32_t any = __ballot_sync(kFull, r != 0);
-        if (any) {
-            if (r) {
-                const uint32_t pos = qn + (uint32_t)__popc(any & lt);
-                ws.q_r[pos] = r; ws.q_e[pos] = e; ws.q_b[pos] = gblk0 + it * S + s_ix;
-            }
-            qn += (uint32_t)__popc(any);
-            if (qn > kBjQueue - 32) {
-                __syncwarp();
-                bj_flush(a, ws, qn);
-                qn = 0;
-            }
+        for (int j = 0; j < 10; j++) {
+            const uint2 m = k.p[j][it * S * (kBjBlockWords / 2) + 4 * j];
+            mx[j] = m.x; my[j] = m.y;
+        }
+        uint32_t rx = short_tree ? tree_at_most2(mx) : tree_any(mx, k);
+        uint32_t ry = short_tree ? tree_at_most2(my) : tree_any(my, k);
+        if (S > 1 && it * S + s_ix >= nblk) rx = ry = 0;  // this copy's block is beyond the piece
+        if (rx | ry) {
+            const uint4 v = make_uint4(rx, ry, e, gblk0 + it * S + s_ix);
+            const uint32_t pos = atomicAdd(&ws.qn, 1u);
+            if (pos < (uint32_t)kBjQueue) ws.q[pos] = v;
+            else bj_emit_direct(a, v);
+        }
+    };
+    if (at_most2) {
+#pragma unroll
+        for (int it = 0; it < kIters; it++) {
+            if ((uint32_t)(it * S) >= nblk) break;
+            step(it, true);
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < kIters; it++) {
+            if ((uint32_t)(it * S) >= nblk) break;
+            step(it, false);
         }
     }
+    __syncwarp();
+    if (ws.qn >= 32u) bj_flush(a, ws, false);
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(kBjWarps * 32, 4) ot_join_blocks_kernel(const BjArgs a) {
+__global__ void __launch_bounds__(kBjWarps * 32, BJ_MIN_CTAS) ot_join_blocks_kernel(const BjArgs a) {
     extern __shared__ __align__(128) unsigned char bj_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     BjWarpSmem &ws = reinterpret_cast<BjWarpSmem *>(bj_smem)[warp];
-    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); }
+    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); ws.qn = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t parity = 0;  // bit s: phase of bar[s] the next wait on it looks for
-    uint32_t qn = 0;      // queued result words (warp-uniform)
-    unsigned long long compared = 0;  // statistics: entries x slots compared (lane 0)
+    unsigned long long compared = 0;  // statistics: entries x slots compared (per lane, summed at the end)
     const uint32_t G = a.group;
+    constexpr uint32_t kBlockBytes = kBjBlockWords * 4u;
 
-    // a unit = one piece (<= kBjCapBlocks blocks) of one bucket
-    auto issue = [&](uint32_t gblk, uint32_t nblk, int s) {
+    // first piece of a bucket: its blocks and its entries (16-byte aligned: buckets start at even entries)
+    auto issue_first = [&](const uint4 m, int s) {
         if (lane == 0) {
-            const uint32_t bytes = nblk * (kBjBlockWords * 4u);
-            mbar_expect_tx(&ws.bar[s], bytes);
-            bulk_g2s(ws.blk[s], a.blocks + (size_t)gblk * kBjBlockWords, bytes, &ws.bar[s]);
+            const uint32_t bytes_b = min(m.y, (uint32_t)kBjCapBlocks) * kBlockBytes;
+            const uint32_t bytes_e = ((min(m.w, (uint32_t)kBjCapEnt) + 1u) >> 1) * 16u;
+            mbar_expect_tx(&ws.bar[s], bytes_b + bytes_e);
+            bulk_g2s(ws.st[s].blk, a.blocks + (size_t)m.x * kBjBlockWords, bytes_b, &ws.bar[s]);
+            bulk_g2s(ws.st[s].ent, a.ent + m.z, bytes_e, &ws.bar[s]);
         }
     };
 
@@ -205,76 +293,83 @@ __global__ void __launch_bounds__(kBjWarps * 32, 4) ot_join_blocks_kernel(const 
         if (t >= a.n_groups) break;
         const uint32_t k0 = a.key_lo + t * G;
         const uint32_t nb = min(G, a.key_hi - k0);
-        // bucket bounds of the group: lane i holds bucket k0 + i
-        uint32_t b_lo = 0, b_hi = 0, e_lo = 0, e_hi = 0;
+        // bucket bounds of the group: lane i describes bucket k0 + i
+        uint4 mine = make_uint4(0, 0, 0, 0);
         if (lane < nb) {
-            b_lo = __ldg(&a.blk_off[k0 + lane]) >> 5; b_hi = __ldg(&a.blk_off[k0 + lane + 1]) >> 5;
-            e_lo = __ldg(&a.ent_off[k0 + lane]); e_hi = __ldg(&a.ent_off[k0 + lane + 1]);
+            const uint32_t b0 = __ldg(&a.blk_off[k0 + lane]) >> 6, b1 = __ldg(&a.blk_off[k0 + lane + 1]) >> 6;
+            const uint32_t v0 = __ldg(&a.ent_off[k0 + lane]), v1 = __ldg(&a.ent_off[k0 + lane + 1]);
+            mine = make_uint4(b0, b1 - b0, v0 & ~1u, (v1 & ~1u) - (v0 & ~1u) - (v0 & 1u));
+            compared += (unsigned long long)mine.y * 64u * mine.w;
         }
         // buckets without entries or without windows have nothing to join
-        const uint32_t live = __ballot_sync(kFull, lane < nb && b_hi > b_lo && e_hi > e_lo);
-        if (!live) continue;
-        // unit cursor: bucket `ub` (lane index), blocks from `ublk`
-        uint32_t rest = live;
-        int ub = __ffs((int)rest) - 1;
-        uint32_t cur_blk = __shfl_sync(kFull, b_lo, ub), cur_end = __shfl_sync(kFull, b_hi, ub);
+        uint32_t rest = __ballot_sync(kFull, mine.y != 0 && mine.w != 0);
+        if (!rest) continue;
+        if (lane < (uint32_t)kBjGroupMax) ws.meta[lane] = mine;
+        __syncwarp();
         int s = 0;
-        issue(cur_blk, min(cur_end - cur_blk, (uint32_t)kBjCapBlocks), 0);
-        while (true) {
-            const uint32_t nblk = min(cur_end - cur_blk, (uint32_t)kBjCapBlocks);
-            // the unit after this one: next piece of the bucket, or the next live bucket of the group
-            int nub = ub;
-            uint32_t nxt_blk = cur_blk + nblk, nxt_end = cur_end, nrest = rest;
-            if (nxt_blk >= cur_end) {
-                nrest = rest & (rest - 1u);
-                nub = nrest ? __ffs((int)nrest) - 1 : -1;
-                if (nub >= 0) { nxt_blk = __shfl_sync(kFull, b_lo, nub); nxt_end = __shfl_sync(kFull, b_hi, nub); }
+        issue_first(ws.meta[__ffs((int)rest) - 1], 0);
+        while (rest) {
+            const uint4 m = ws.meta[__ffs((int)rest) - 1];
+            rest &= rest - 1u;
+            if (rest) issue_first(ws.meta[__ffs((int)rest) - 1], s ^ 1);
+            const uint32_t K = m.w;
+            for (uint32_t piece = 0; piece < m.y; piece += kBjCapBlocks) {
+                const uint32_t nblk = min(m.y - piece, (uint32_t)kBjCapBlocks);
+                if (piece) {  // a bucket larger than the stage: the further pieces are fetched in place
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_expect_tx(&ws.bar[s], nblk * kBlockBytes);
+                        bulk_g2s(ws.st[s].blk, a.blocks + (size_t)(m.x + piece) * kBjBlockWords, nblk * kBlockBytes, &ws.bar[s]);
+                    }
+                }
+                mbar_wait(&ws.bar[s], (parity >> s) & 1u);
+                parity ^= 1u << s;
+                for (uint32_t g0 = 0; g0 < K; g0 += 32) {
+                    const uint32_t R = min(K - g0, 32u);
+                    if (R > 16 || nblk == 1) bj_pass<1>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
+                    else if (R > 8 || nblk == 2) bj_pass<2>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
+                    else bj_pass<4>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
+                }
             }
-            if (nub >= 0) issue(nxt_blk, min(nxt_end - nxt_blk, (uint32_t)kBjCapBlocks), s ^ 1);
-            const uint32_t e0 = __shfl_sync(kFull, e_lo, ub), K = __shfl_sync(kFull, e_hi, ub) - e0;
-            mbar_wait(&ws.bar[s], (parity >> s) & 1u);
-            parity ^= 1u << s;
-            const uint32_t *buf = ws.blk[s];
-            if (lane == 0) compared += (unsigned long long)K * nblk * 32u;
-            for (uint32_t g0 = 0; g0 < K; g0 += 32) {
-                const uint32_t R = min(K - g0, 32u);
-                if (R > 16 || nblk == 1) bj_pass<1>(a, ws, buf, nblk, cur_blk, e0 + g0, R, qn);
-                else if (R > 8 || nblk == 2) bj_pass<2>(a, ws, buf, nblk, cur_blk, e0 + g0, R, qn);
-                else bj_pass<4>(a, ws, buf, nblk, cur_blk, e0 + g0, R, qn);
-            }
-            __syncwarp();  // every lane is done with buffer s before it is refilled
-            if (nub < 0) break;
-            ub = nub; rest = nrest; cur_blk = nxt_blk; cur_end = nxt_end; s ^= 1;
+            __syncwarp();  // every lane is done with stage s before it is refilled
+            s ^= 1;
         }
     }
-    if (qn) bj_flush(a, ws, qn);
-    if (a.site_count && lane == 0 && compared) atomicAdd(a.site_count + 1, compared);
+    __syncwarp();
+    if (ws.qn) bj_flush(a, ws, true);
+    if (a.site_count) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) compared += __shfl_xor_sync(kFull, compared, o);
+        if (lane == 0 && compared) atomicAdd(a.site_count + 1, compared);
+    }
 }
 
 // ---- table side: slots -> bit-sliced blocks -------------------------------------------------------
 //
-// One warp per block of 32 slots: lane i reads slot i (pad slots carry gpos = 0xffffffff and differ
-// from every letter, so they never hit), forty ballots give the forty words.
+// One warp per block of 64 slots: lane i reads slots i and 32 + i (pad slots carry gpos = 0xffffffff
+// and differ from every letter, so they never hit), forty ballot pairs give the forty 64-bit words.
 __global__ void __launch_bounds__(256) site_blocks_kernel(const uint4 *slots, uint32_t n_blocks, int dl, uint32_t *blocks) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t b = blockIdx.x * 8u + (threadIdx.x >> 5); b < n_blocks; b += gridDim.x * 8u) {
-        const uint4 s = slots[(size_t)b * 32u + lane];
-        const bool pad = s.x == 0xffffffffu;
-        uint32_t w0 = 0, w1 = 0;  // lane l keeps words l and 32 + l
+        const uint4 sa = slots[(size_t)b * 64u + lane], sb = slots[(size_t)b * 64u + 32u + lane];
+        const bool pad_a = sa.x == 0xffffffffu, pad_b = sb.x == 0xffffffffu;
+        uint2 w0 = make_uint2(0, 0), w1 = make_uint2(0, 0);  // lane l keeps words l and 32 + l
 #pragma unroll
         for (int j = 0; j < 10; j++) {
-            const uint32_t code = j < dl ? ((((s.y >> j) & 1u) << 1) | ((s.z >> j) & 1u)) : 0u;
+            const uint32_t code_a = j < dl ? ((((sa.y >> j) & 1u) << 1) | ((sa.z >> j) & 1u)) : 0u;
+            const uint32_t code_b = j < dl ? ((((sb.y >> j) & 1u) << 1) | ((sb.z >> j) & 1u)) : 0u;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const uint32_t word = __ballot_sync(kFull, pad || code != (uint32_t)c);
+                const uint2 word = make_uint2(__ballot_sync(kFull, pad_a || code_a != (uint32_t)c),
+                                              __ballot_sync(kFull, pad_b || code_b != (uint32_t)c));
                 const int ix = 4 * j + c;
                 if (ix < 32) { if (lane == (uint32_t)ix) w0 = word; }
                 else if (lane == (uint32_t)(ix - 32)) w1 = word;
             }
         }
-        uint32_t *out = blocks + (size_t)b * kSiteBlockWords;
+        uint2 *out = reinterpret_cast<uint2 *>(blocks + (size_t)b * kSiteBlockWords);
         out[lane] = w0;
-        if (lane < kSiteBlockWords - 32) out[32 + lane] = w1;
+        if (lane < kSiteBlockWords / 2 - 32) out[32 + lane] = w1;
     }
 }
 
@@ -307,7 +402,7 @@ int launch_join_blocks(DeviceState *ds, BjArgs a, cudaStream_t stream) {
     // least 4 buckets per ticket so the atomic and the bound loads stay off the critical path
     const uint32_t n_keys = a.key_hi - a.key_lo;
     const uint32_t warps = (uint32_t)grid * kBjWarps;
-    uint32_t G = 32;
+    uint32_t G = 16;
     while (G > 4 && n_keys / G < warps * 16u) G >>= 1;
     a.group = G;
     a.n_groups = (n_keys + G - 1) / G;

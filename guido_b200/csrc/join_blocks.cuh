@@ -4,14 +4,16 @@
 
 namespace guido {
 
-constexpr int kSiteBlockWords = 40;  // 32 windows x 10 distal bases x 4 letters, one bit each
+constexpr int kSiteBlockSlots = 64;  // windows per bit-sliced block
+constexpr int kSiteBlockWords = 80;  // 32-bit words per block: 10 distal bases x 4 letters x 64 windows, one bit each
 
 struct BjArgs {
-    const uint32_t *blocks;   // site table: kSiteBlockWords words per block of 32 slots
-    const uint32_t *blk_off;  // n_buckets + 1: first SLOT of each bucket (multiple of 32) | pad count in the low 5 bits
+    const uint32_t *blocks;   // site table: kSiteBlockWords words per block of 64 slots
+    const uint32_t *blk_off;  // n_buckets + 1: first SLOT of each bucket (multiple of 64) | pad count in the low 6 bits
     const uint4 *slots;       // per slot {global position, hi plane | strand << 31, lo plane, core key}; pads: x = ~0
-    const uint2 *ent;         // seed index entries {distal letters (2 bits each) | bias << 20, guide}, bucket order
-    const uint32_t *ent_off;  // n_buckets + 1: first entry of each bucket
+    const uint2 *ent;         // seed index entries {distal letters (2 bits each) | bias << 20, guide}, bucket order;
+                              // inside a bucket the entries of the largest bias class come first
+    const uint32_t *ent_off;  // n_buckets + 1: first entry of each bucket (even) | 1 if an unused pad entry follows the bucket
     uint32_t key_lo, key_hi;  // buckets joined by this launch
     uint32_t group, n_groups; // buckets per ticket, tickets (set by launch_join_blocks)
     uint32_t *ticket;         // zero at launch

@@ -55,7 +55,7 @@ struct OtScanArgs {
     unsigned long long *count;
     uint8_t *flags;
     unsigned long long *site_count;
-    // PAM-site table (genome-side index): windows grouped by core key, buckets padded to 32 slots
+    // PAM-site table (genome-side index): windows grouped by core key, buckets padded to 64 slots
     uint4 *tab_slots;                  // {global position, hi plane (+ strand in bit 31), lo plane, core key}; pads: x = ~0
     uint32_t *tab_counts, *tab_fill;   // per-bucket histogram -> starts (| pad count), fill cursors (build only)
     uint32_t tab_lo, tab_n;             // join: slots [tab_lo, tab_n) of the table
@@ -437,7 +437,7 @@ __device__ __forceinline__ void table_round(const OtScanArgs &a, const uint32_t 
             atomicAdd(&a.tab_counts[key], 1u);
             tabled++;
         } else {
-            const uint32_t slot = (a.tab_counts[key] & ~31u) + atomicAdd(&a.tab_fill[key], 1u);
+            const uint32_t slot = (a.tab_counts[key] & ~63u) + atomicAdd(&a.tab_fill[key], 1u);
             a.tab_slots[slot] = make_uint4(sQ[idx], A, B, key);
         }
     }
@@ -693,6 +693,8 @@ struct IdxArgs {
     uint32_t pad_mask;         // bucket starts are multiples of pad_mask + 1 (7, or 0: no padding)
     int entries;               // 1: one {letters | bias, guide} entry per key, the format of the block join (join_blocks.cu)
     uint32_t cbias;            // entries: 7 - total_max, added to the variant's core mismatch count
+    uint32_t core_max;         // entries: variants with this many core mismatches go to the front of a bucket
+    uint32_t *back;            // entries: n_buckets cursors that start at the bucket ends
 };
 
 // One warp per guide: the guide is read once, the lanes walk the variant list (staged in shared
@@ -731,9 +733,12 @@ __global__ void __launch_bounds__(256) idx_build_kernel(const IdxArgs a) {
             if constexpr (!kFill) {
                 if (!a.part_on || (key >> a.part_shift) == a.part_ix) atomicAdd(&a.counts[key], 1u);
             } else {
-                // fill[] starts out as the bucket starts (scan_fixup_kernel): the atomic IS the slot
-                const uint32_t pos = atomicAdd(&a.fill[key], 1u);
+                // fill[] starts out as the bucket starts (scan_fixup_kernel): the atomic IS the slot.
+                // Entry format: the variants with the most core mismatches (the bulk: 405 of 436 for
+                // 10 / 2) fill a bucket from the front, the others from the back, so whole passes of
+                // the block join see one bias and may take the short compare tree.
                 const uint32_t cmm = (uint32_t)__popc(xh | xl);
+                const uint32_t pos = a.entries && cmm != a.core_max ? atomicSub(&a.back[key], 1u) - 1u : atomicAdd(&a.fill[key], 1u);
                 if (a.entries) {
                     // the guide's distal letters and the biased core mismatch count of this variant,
                     // c' = c + 7 - total_max (a hit is d + c' <= 7); one 8-byte store per entry
@@ -907,6 +912,13 @@ int exclusive_scan_u32(uint32_t *data, uint32_t n, uint32_t *sums, uint32_t *cur
     return GUIDO_OK;
 }
 
+// back[key] = end of bucket key's entries (offsets carry the pad count of a bucket in their low bits)
+__global__ void __launch_bounds__(256) idx_back_cursor_kernel(const uint32_t *offsets, uint32_t n_buckets, uint32_t pad_mask,
+                                                               uint32_t *back) {
+    const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    if (k < n_buckets) back[k] = (offsets[k + 1] & ~pad_mask) - (offsets[k] & pad_mask);
+}
+
 static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
     // all (xh, xl) with popc(xh | xl) <= cm over cl positions; per chosen position 3 substitutions
     out->clear();
@@ -929,7 +941,7 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 }
 
 // builds the guide-side seed index of this search in ds->d_bucket / ds->d_index.  `entries`: one
-// 8-byte {letters | bias, guide} entry per key, buckets unpadded (the block join); otherwise the
+// 8-byte {letters | bias, guide} entry per key, buckets padded to even sizes (the block join); otherwise the
 // key / guide-id arrays of the popc kernels with buckets padded to 8 keys.
 // `part_bits` / `part_ix`: only the buckets whose top part_bits key bits equal part_ix are built (the
 // share of the key space this handle's site table covers); 0 / 0 = everything
@@ -946,22 +958,22 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const uint32_t n_buckets = 1u << (2 * cl);
     const uint64_t n_entries = (uint64_t)variants.size() * (uint64_t)n_guides;
     const uint32_t n_scan = n_buckets + 1, n_scan_blocks = (n_scan + 4095) / 4096;
-    // d_bucket: [counts/offsets n_buckets+1][fill n_buckets][block sums][variants]
+    // d_bucket: [counts/offsets n_buckets+1][fill n_buckets][back n_buckets][block sums][variants][levels]
     // bucket sizes by the Hamming-ball convolution (ball_count_kernel) when a half core fits its
     // shared-memory tile; GUIDO_IDX_HIST=atomic forces the histogram pass (tests, comparisons)
     const char *hist_mode = getenv("GUIDO_IDX_HIST");
     const bool dp_counts = cl <= 10 && op.core_max >= 1 && op.core_max <= 3 && !(hist_mode && hist_mode[0] == 'a');
     const int64_t level_words = dp_counts ? (int64_t)(op.core_max + 1) * n_buckets : 0;
-    const int64_t bucket_words = (int64_t)n_scan + n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words;
+    const int64_t bucket_words = (int64_t)n_scan + 2 * (int64_t)n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
     // popc format: every bucket is padded to a multiple of 8 slots; worst case allocated
-    const uint32_t pad = entries ? 0u : 8u;
+    const uint32_t pad = entries ? 2u : 8u;  // entries: buckets start 16-byte aligned (bulk copies)
     const uint64_t n_slots = (n_entries + (uint64_t)(pad ? pad - 1 : 0) * n_buckets + 31) & ~(uint64_t)31;
     if (n_slots >= (1ull << 32)) { set_error("seed index too large"); return GUIDO_ERR_ARG; }
     // d_index: [keys n_slots][ids n_slots], or n_slots 8-byte entries
     if ((rc = ensure_bytes(&ds->d_index, &ds->index_cap, (int64_t)n_slots * 8))) return rc;
-    uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *sums = fill + n_buckets,
+    uint32_t *counts = (uint32_t *)ds->d_bucket, *fill = counts + n_scan, *back = fill + n_buckets, *sums = back + n_buckets,
              *d_var = sums + n_scan_blocks;
     uint32_t *keys = (uint32_t *)ds->d_index, *ids = keys + n_slots;
     const int field = dl + op.core_max;  // <= 16, checked by ot_index_applicable
@@ -996,6 +1008,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     ia.part_shift = (uint32_t)(2 * cl - part_bits); ia.part_ix = (uint32_t)part_ix; ia.part_on = part_bits > 0;
     ia.cl = cl; ia.dl = dl; ia.field = field; ia.counts = counts; ia.fill = fill; ia.keys = keys; ia.ids = ids;
     ia.pad_mask = pad ? pad - 1 : 0; ia.entries = entries ? 1 : 0; ia.cbias = entries ? (uint32_t)(7 - op.total_max) : 0u;
+    ia.core_max = (uint32_t)op.core_max; ia.back = back;
     const int bgrid = (int)std::min<uint64_t>(((uint64_t)n_guides + 7) / 8, (uint64_t)ds->sm_count * 8);
     int n_count_launches = 1;
     if (dp_counts) {
@@ -1013,6 +1026,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, ia.pad_mask);
+    if (entries) idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
@@ -1029,7 +1043,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         GUIDO_CUDA(cudaGetLastError());
         if (after_slice && (rc = (*after_slice)(key_lo, key_hi))) return rc;
     }
-    if (n_launches) *n_launches += 3 + n_count_launches + (int)per_part;
+    if (n_launches) *n_launches += 3 + (entries ? 1 : 0) + n_count_launches + (int)per_part;
     return GUIDO_OK;
 }
 
@@ -1055,7 +1069,7 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
 //
 // Genome-side index: the PAM-valid windows of the resident shard in guide orientation, grouped by
 // core key (counting sort: histogram pass, scan, scatter pass -- both passes are the search front
-// end with a different consumer).  Every bucket is padded to whole blocks of 32 slots.  Per slot 16
+// end with a different consumer).  Every bucket is padded to whole blocks of 64 slots.  Per slot 16
 // bytes {position, hi plane | strand, lo plane, core key} -- read for hits, and by the popc join --
 // plus, for 10-base cores, 5 bytes of the bit-sliced block form the block join streams
 // (join_blocks.cu): ~8.4 GB for NGG on 3.1 Gb.  Built once per (PAM sets, core length) and kept
@@ -1119,38 +1133,38 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     a.tab_key_span = n_buckets >> part_bits_of(ds);
     a.tab_key_lo = a.tab_key_span * (uint32_t)ds->site_part_ix;
     if ((rc = launch_ot_kernel<kModeTabCount>(ds, a, stream))) return rc;
-    // A 32-bit scan of the padded counts: refuse before it can wrap (every bucket gains < 32 slots)
+    // A 32-bit scan of the padded counts: refuse before it can wrap (every bucket gains < 64 slots)
     unsigned long long seen[2] = {0, 0};  // windows of the shard, windows in this handle's key range
     GUIDO_CUDA(cudaMemcpyAsync(seen, ds->d_counts + 4, sizeof seen, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
     const unsigned long long all_windows = seen[1];
     if (seen[0] >= (1ull << 31)) return GUIDO_ERR_CAPACITY;  // 32-bit slot numbers (and the scan) end here
-    // bucket starts, every bucket rounded up to whole blocks of 32 slots (the pad count rides in the
-    // low 5 bits); the entry behind the last bucket is the number of slots
-    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, 32);
+    // bucket starts, every bucket rounded up to whole blocks of 64 slots (the pad count rides in the
+    // low 6 bits); the entry behind the last bucket is the number of slots
+    scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, kSiteBlockSlots);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, 31);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, nullptr, kSiteBlockSlots - 1);
     uint32_t total = 0;
     for (int k = 0; k <= 32; k++)  // first slot of every 1/32 of the key space: the join's slice boundaries
         GUIDO_CUDA(cudaMemcpyAsync(&ds->site_row_off[k], counts + (size_t)k * (n_buckets / 32), sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaMemcpyAsync(&total, counts + n_buckets, sizeof total, cudaMemcpyDeviceToHost, stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
-    for (int k = 0; k <= 32; k++) ds->site_row_off[k] &= ~31u;
-    total &= ~31u;
+    for (int k = 0; k <= 32; k++) ds->site_row_off[k] &= ~(uint32_t)(kSiteBlockSlots - 1);
+    total &= ~(uint32_t)(kSiteBlockSlots - 1);
     const bool want_blocks = dl == 10;  // the block join is written for ten distal bases
     if ((int64_t)total > ds->site_cap || (want_blocks && !ds->d_site_blocks)) {
         release_site_table(ds);
         size_t free_b = 0, total_b = 0;
         GUIDO_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const int64_t cap = (int64_t)total + 1024;
-        const uint64_t bytes = (uint64_t)cap * kSiteSlotBytes + (want_blocks ? (uint64_t)(cap / 32) * kSiteBlockWords * 4 : 0);
+        const uint64_t bytes = (uint64_t)cap * kSiteSlotBytes + (want_blocks ? (uint64_t)(cap / kSiteBlockSlots) * kSiteBlockWords * 4 : 0);
         if (bytes + (4ull << 30) > free_b) return GUIDO_ERR_CAPACITY;
         // GUIDO_SITE_TABLE_MAX_MB: cap on the table size (tests of the streaming fallback, shared GPUs)
         if (const char *lim = getenv("GUIDO_SITE_TABLE_MAX_MB"))
             if (bytes > ((uint64_t)std::max(0, atoi(lim)) << 20)) return GUIDO_ERR_CAPACITY;
         GUIDO_CUDA(cudaMalloc(&ds->d_site_slots, (size_t)cap * kSiteSlotBytes));
-        if (want_blocks) GUIDO_CUDA(cudaMalloc(&ds->d_site_blocks, (size_t)(cap / 32) * kSiteBlockWords * 4));
+        if (want_blocks) GUIDO_CUDA(cudaMalloc(&ds->d_site_blocks, (size_t)(cap / kSiteBlockSlots) * kSiteBlockWords * 4));
         ds->site_cap = cap;
     }
     // pad slots keep position ~0 (never a window: the image ends below 2^32 - 23)
@@ -1158,7 +1172,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     a.tab_slots = ds->d_site_slots;
     a.site_count = nullptr;
     if ((rc = launch_ot_kernel<kModeTabFill>(ds, a, stream))) return rc;
-    if (want_blocks && (rc = launch_site_blocks(ds, ds->d_site_slots, total / 32, dl, ds->d_site_blocks, stream))) return rc;
+    if (want_blocks && (rc = launch_site_blocks(ds, ds->d_site_slots, total / kSiteBlockSlots, dl, ds->d_site_blocks, stream))) return rc;
     GUIDO_CUDA(cudaEventRecord(ds->ev[2], stream));
     GUIDO_CUDA(cudaStreamSynchronize(stream));
     cudaEventElapsedTime(&ds->site_build_ms, ds->ev[1], ds->ev[2]);
@@ -1171,7 +1185,7 @@ int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op,
     return GUIDO_OK;
 }
 
-// The block join pays per (32 entries x 32 slots); it wins once buckets hold enough of both.
+// The block join pays per (32 entries x 64 slots); it wins once buckets hold enough of both.
 // GUIDO_OT_BLOCKS=0/1 forces the choice (tests, tuning).
 static bool ot_blocks_applicable(const DeviceState *ds, const OtParams &op, int64_t n_guides) {
     if (!ds->d_site_blocks || op.core_len != 10 || op.total_max < 0 || op.total_max > 7 || op.core_max > 3) return false;

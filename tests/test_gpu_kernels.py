@@ -376,6 +376,38 @@ def test_offtarget_join_big_buckets(native, monkeypatch, sliced):
     assert np.array_equal(merged, a)
 
 
+@pytest.mark.parametrize("total", [3, 4, 5])
+def test_offtarget_block_join_full_passes(native, oracle, monkeypatch, total):
+    """dense buckets on both sides (2 000 guides x 40 copies, a 24 Mb image): the block join runs
+    whole 32-entry passes -- the short "at most 2 of 10" tree when every lane carries that bias
+    (total 4), the general tree otherwise -- plus shared remainder passes; the result must equal
+    the popc join's, and the oracle's on a sample of the guides"""
+    img = native.Image.synth([15_000_000, 9_000_000], seed=91, n_frac=0.004).upload()
+    rng = np.random.default_rng(17)
+    fw, _ = img.pam_scan_genome("NGG", native.SCAN_STRICT)
+    pos = rng.choice(fw, size=2000, replace=False).astype(np.int64)
+    base = img.fetch_windows(pos - 20, 20)
+    mut = rng.integers(0, 20, size=len(base))
+    base[np.arange(len(base)), mut] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=len(base))]
+    protos = np.ascontiguousarray(np.tile(base, (40, 1)))
+    kw = dict(core_length=10, core_mismatches=2, total_mismatches=total, want_raw_flags=False)
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", "0")
+    a, _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", "1")
+    b, _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)
+    assert len(a) > 40 * 2000 and np.array_equal(a, b)
+    # every copy of a guide owns the same hits
+    first = b[b["guide"] < 2000]
+    for c in (1, 17, 39):
+        cp = b[(b["guide"] >= 2000 * c) & (b["guide"] < 2000 * (c + 1))]
+        assert np.array_equal(cp["gpos"], first["gpos"]) and np.array_equal(cp["hi"], first["hi"])
+    # oracle on a few guides against the part of the genome that holds their hits is too slow at
+    # 24 Mb; brute force on the device is the independent check here
+    sub = np.ascontiguousarray(base[:64])
+    c, _ = img.offtarget_search(sub, algo=native.OT_SCAN, **kw)
+    assert np.array_equal(c, first[first["guide"] < 64])
+
+
 @pytest.mark.parametrize("pam,mode", [("NGG", 0), ("NGG", 2), ("TTTV", 1), ("N", 0), ("NNGRRT", 2)])
 def test_pam_scan_one_pass_equals_two_pass(native, monkeypatch, pam, mode):
     """The single-pass (look-back) kernel and the count -> fill pair must return the same lists:
