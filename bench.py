@@ -2,8 +2,8 @@
 """bench.py -- guido hot path on B200: off-target guides/sec and PAM-scan GB/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload offtarget|pam] [--genome human|agam|<Mb>] [--guides G] [--algo auto|scan|index|table]
-                    [--shard key|position]
+                    [--workload offtarget|pam|mmej|locus] [--genome human|agam|<Mb>] [--guides G]
+                    [--algo auto|scan|index|table] [--shard key|position]
 
 One "step" = one pass of the hot path over one batch:
   offtarget  (default) 100 000 SpCas9 guides, <=4 mismatches (core 10 / 2), against a synthetic
@@ -14,17 +14,27 @@ One "step" = one pass of the hot path over one batch:
              `--algo index` streams the genome instead and needs no table).
   pam        whole-genome NGG scan, both strands, synthetic 273 Mb genome -- configs[1].
              The default run also measures this one and reports it under "pam_scan".
+  mmej       configs[4]: Cas12a TTTV scan of a synthetic 100 Mb genome, guides kept inside the
+             exons of 5 000 genes, MMEJ enumeration for every guide (one step = scan + batch kernel).
+  locus      configs[0] (the reference's own CPU-runnable case): find_guides + off-targets <=3 mm
+             for a 100 kb locus of a 10 Mb genome, through the drop-in Python API.
 Multi-GPU: one process per GPU (torchrun).  Off-target search: every rank holds the whole image and
 1/N of the PAM-site table, split by core k-mer range, and builds the guide index for that range
 only (`--shard key`, default); or the genome is sharded in contiguous, tile-aligned chunks with a
 256-base halo and the guides are replicated (`--shard position`; always for the PAM scan).  The
-per-rank hit lists are merged with an NCCL all-gather inside the step.  Total work is fixed as N
-grows ("strong").
+per-rank hit lists are merged with ONE padded NCCL all-gather inside the step (header record =
+count; no host round trip).  Total work is fixed as N grows ("strong").
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with inputs resident in HBM;
-`e2e` goes through the host-buffer C-ABI call (guides H2D, hits sorted on the device, D2H into
-pinned host memory inside the region).  `--impl reference` times the CPU oracle port (bowtie is
-not in this image) on the host cores, on a bounded sample scaled to the whole workload.
+`e2e` goes through the host-buffer C-ABI call (guide letters H2D, search, device sort, raw-hit flags,
+8-byte hit records D2H into pinned host memory -- all inside the region).
+
+`--impl reference` (and `cpu_baseline`): the CPU arm.  The reference's off-target path is the
+external bowtie 1.3.1 binary, which is not in this image; what runs is the oracle's SEED-INDEXED C
+restatement of the same search (index built once = bowtie-build, not timed; every step searches a
+bounded sample of the guides against the WHOLE genome on all host threads), labelled kind "port".
+PAM scan / guide construction / MMEJ are timed on the reference's own Python code where
+/root/reference is mounted (kind "reference-python"), on the oracle port elsewhere.
 """
 import argparse
 import json
@@ -76,6 +86,15 @@ def sample_guides(img, n, seed):
     return np.ascontiguousarray(np.concatenate(out)[:n])
 
 
+def host_threads():
+    """threads the CPU arm uses: every core this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which is about its own workers, not about this measurement)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the bench runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -119,8 +138,8 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel, workload_ok):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json);
-    only reported when this run is the workload the capture was taken on"""
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json;
+    ncu cannot run inside a timed bench); only reported when this run is the workload it was taken on"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not workload_ok or not os.path.exists(p):
         return None
@@ -136,42 +155,106 @@ def measured_peak_gbs():
 
 # ------------------------------------------------------------------------------ CPU arm
 
-def cpu_offtarget_sample(img, guides_u8, n_windows_full, budget_s=12.0):
-    """The oracle port (all host cores) on a bounded sample: a slice of contig 1 x a subset of the
-    guides; the pair rate is scaled to whole-genome guides/sec."""
-    from oracle import oracle as O
-    O.lib()
-    cores = O.threads()
-    name, clen, _ = img.contigs[0]
-    reads = [O.rev_comp(bytes(g).decode() + PAM) for g in guides_u8[:256]]
-    seed_mms, seed_len, e = O.bowtie_args(PAM, **OT_KW)
-    slice_len, n_reads, spent = 200_000, min(64, len(reads)), 0.0
-    while True:
-        seq = img.fetch(0, 0, min(slice_len, clen))
+class CpuOfftarget:
+    """Seed-indexed C port of the off-target search on the host cores (oracle/guido_oracle.c).
+
+    The index over the whole genome is built once (the bowtie-build counterpart, reported but not
+    timed); a step searches a bounded sample of the guides against it with every host thread."""
+
+    def __init__(self, img, build_budget_s=150.0):
+        from oracle import oracle as O
+        self.O = O
+        self.cores = O.set_threads(host_threads())
         t0 = time.perf_counter()
-        O.bowtie_n_count([(name, seq)], reads[:n_reads], seed_mms, seed_len, e)
+        contigs, bases = [], 0
+        total = sum(c[1] for c in img.contigs)
+        # contigs are added largest-first until the build budget would be overrun (a small host):
+        # the windows-per-bucket, and with it the per-guide work, scale with the indexed fraction
+        order = sorted(range(len(img.contigs)), key=lambda i: -img.contigs[i][1])
+        est_rate = None
+        for n_done, i in enumerate(order):
+            name, clen, goff = img.contigs[i]
+            if est_rate is not None and (bases + clen) / est_rate > build_budget_s and n_done >= 2:
+                break
+            contigs.append((name, img.fetch(i, 0, clen).encode(), goff))
+            bases += clen
+            if n_done == 0:  # calibrate on the first contig
+                t1 = time.perf_counter()
+                probe = O.SeedIndex(contigs, PAM, OT_KW["core_length"])
+                probe.close()
+                est_rate = clen / max(time.perf_counter() - t1, 1e-3) * 0.8
+        self.fraction = bases / total
+        self.index = O.SeedIndex(contigs, PAM, OT_KW["core_length"])
+        self.build_s = time.perf_counter() - t0
+        self.n_windows = self.index.n_windows
+        del contigs
+
+    def step(self, guides_u8):
+        t0 = time.perf_counter()
+        hits = self.index.search(guides_u8, OT_KW["core_mismatches"], OT_KW["total_mismatches"])
         dt = time.perf_counter() - t0
-        spent += dt
-        pairs_per_s = 2.0 * len(seq) * n_reads / dt  # every window, both strands (bowtie's search space)
-        if dt > budget_s / 3 or spent > budget_s or slice_len >= clen:
-            break
-        scale = min(8.0, max(2.0, (budget_s / 2) / max(dt, 1e-3)))
-        if n_reads < len(reads):
-            n_reads = min(len(reads), int(n_reads * scale))
-        else:
-            slice_len = int(slice_len * scale)
-    return {"value": pairs_per_s / n_windows_full, "unit": "guides/s", "cores": cores, "kind": "port",
-            "sample": f"oracle C port of the bowtie -n rule (brute force, all {cores} host threads): "
-                      f"{len(seq)} bp of contig 1 x {n_reads} guides in {dt:.2f} s = {pairs_per_s:.3e} "
-                      "window-guide pairs/s, scaled to every window of the whole genome",
-            "pairs_per_s": pairs_per_s}
+        return len(guides_u8) / dt, hits, dt
+
+    def baseline(self, guides_u8, budget_s=12.0):
+        n = min(len(guides_u8), 2000)
+        rate, hits, dt = self.step(guides_u8[:n])
+        n = int(min(len(guides_u8), max(n, rate * budget_s)))
+        rate, hits, dt = self.step(guides_u8[:n])
+        return self.describe(rate, n, hits, dt)
+
+    def describe(self, rate, n, hits, dt):
+        scale = ""
+        value = rate
+        if self.fraction < 0.999:
+            # per-guide work = bucket look-ups + windows per bucket x checks; the second term grows with
+            # the indexed fraction, so scaling the whole rate by it is pessimistic for the CPU by at
+            # most the look-up share
+            value = rate * self.fraction
+            scale = (f"; index covers {self.fraction:.2f} of the genome (build budget), rate scaled by that fraction")
+        return {"value": value, "unit": "guides/s", "cores": self.cores, "kind": "port",
+                "sample": f"seed-indexed C port of the bowtie -n search + guido's PAM filter (oracle/guido_oracle.c; bowtie "
+                          f"1.3.1 itself is not in this image): {n} of the guides against {self.n_windows} PAM-valid "
+                          f"windows ({self.fraction:.2f} of the genome), {self.cores} host threads, {dt:.2f} s, "
+                          f"{hits} hits; index build {self.build_s:.1f} s not timed (bowtie-build counterpart){scale}",
+                "index_build_s": self.build_s, "genome_fraction": self.fraction}
 
 
-def cpu_pam_sample(img, budget_s=10.0):
+def reference_python():
+    """the reference package itself (unmodified, imported from /root/reference through stub modules for
+    its absent third-party imports), or None where the reference is not mounted (the GPU box)"""
+    try:
+        from oracle import ref_loader
+        if ref_loader.available():
+            return ref_loader.load_reference()
+    except Exception:
+        pass
+    return None
+
+
+def cpu_pam_sample(img, budget_s=8.0):
+    """PAM scan on the host: the reference's own `_find_guides_in_interval` (two regex passes + one
+    Guide per hit, guido/locus.py:158-211) where it can be imported, the oracle's C scan elsewhere;
+    one thread, as the reference runs.  Expressed in the same algorithmic bytes/base as the GPU line."""
     from oracle import oracle as O
     O.lib()
-    name, clen, _ = img.contigs[0]
-    n = min(clen, 4_000_000)
+    ref = reference_python()
+    if ref is not None:
+        n = min(img.contigs[0][1], 200_000)
+        seq = img.fetch(0, 0, n)
+        loc = ref.Locus(sequence=seq, name="chr1", start=1)
+        t0 = time.perf_counter()
+        reps, hits = 0, 0
+        while time.perf_counter() - t0 < budget_s / 2:
+            hits = len(loc._find_guides_in_interval(seq, 1, PAM))
+            reps += 1
+        dt = time.perf_counter() - t0
+        bases_per_s = n * reps / dt
+        bytes_per_base = 0.25 + 4.0 * hits / n
+        return {"value": bases_per_s * bytes_per_base / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference-python",
+                "sample": f"reference Locus._find_guides_in_interval (regex scan + Guide objects, guido/locus.py:158-211), "
+                          f"1 thread: {n} bp x {reps} reps in {dt:.2f} s = {bases_per_s / 1e6:.3f} Mb/s, "
+                          "expressed in the same algorithmic bytes/base", "bases_per_s": bases_per_s}
+    n = min(img.contigs[0][1], 4_000_000)
     seq = img.fetch(0, 0, n)
     t0 = time.perf_counter()
     reps = 0
@@ -182,8 +265,8 @@ def cpu_pam_sample(img, budget_s=10.0):
     bases_per_s = n * reps / dt
     bytes_per_base = 0.25 + 4.0 * (len(fw) + len(rv)) / n
     return {"value": bases_per_s * bytes_per_base / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
-            "sample": f"oracle C scan (1 thread, as the reference runs): {n} bp x {reps} reps in {dt:.2f} s = "
-                      f"{bases_per_s / 1e6:.1f} Mb/s, expressed in the same algorithmic bytes/base",
+            "sample": f"oracle C scan only, no Guide construction (1 thread, as the reference runs): {n} bp x {reps} reps "
+                      f"in {dt:.2f} s = {bases_per_s / 1e6:.1f} Mb/s, expressed in the same algorithmic bytes/base",
             "bases_per_s": bases_per_s}
 
 
@@ -209,6 +292,9 @@ class Runner:
             self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def allmax(self, x):
+        return self.allsum(x, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
     def timed(self, step, steps, warmup):
         """W warm-up steps, then K steps timed by CUDA events on the launching stream (L2 flushed
         between steps, outside the events), bracketed by barrier + synchronize; max over ranks."""
@@ -227,7 +313,7 @@ class Runner:
         self.barrier()
         t1 = time.time()
         ms = sum(s.elapsed_time(e) for s, e in ev)
-        ms_step = self.allsum(ms, self.dist.ReduceOp.MAX if self.world > 1 else None) / steps
+        ms_step = self.allmax(ms) / steps
         clocks = self.sampler.summary(t0, t1) if self.sampler else None
         return ms_step, launches, clocks
 
@@ -241,7 +327,7 @@ class Runner:
             out = fn()
         self.barrier()
         ms = (time.perf_counter() - t0) * 1e3 / reps
-        return self.allsum(ms, self.dist.ReduceOp.MAX if self.world > 1 else None), out
+        return self.allmax(ms), out
 
 
 def run_pam(R, img, steps, warmup):
@@ -268,7 +354,7 @@ def run_pam(R, img, steps, warmup):
     launches_per_scan = int(st0.n_launches)
     ms_step, launches, clocks = R.timed(step, steps, warmup)
     kt = img.kernel_times(steps)
-    kernel_ms = R.allsum(float(np.mean(kt)), dist.ReduceOp.MAX if R.world > 1 else None)
+    kernel_ms = R.allmax(float(np.mean(kt)))
     hits_rank = float(d_counts.sum().item())
     G = info.total_bases
     hits = R.allsum(hits_rank)
@@ -289,14 +375,31 @@ def run_pam(R, img, steps, warmup):
             "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
 
 
+def hits_checksum(torch, d_hits, n):
+    """order-independent 64-bit checksum of n 16-byte hit records on the device (sum of mixed words)"""
+    if n == 0:
+        return 0
+    w = d_hits[:n].view(torch.int64).reshape(-1, 2)
+    x = w[:, 0] * -7046029254386353131 + (w[:, 1] ^ (w[:, 0] >> 29)) * -4658895280553007687
+    x = (x ^ (x >> 31)) * 6364136223846793005
+    return int(x.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
 def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     N, torch, dist = R.N, R.torch, R.dist
     n_guides = len(guides_u8)
     enc = N.encode_guides([bytes(g).decode() for g in guides_u8])
     d_guides = torch.from_numpy(enc.view(np.int32).copy()).to(R.dev)
-    cap = max(1 << 20, 256 * n_guides // R.world + (1 << 18))
-    d_hits = torch.empty((cap, 4), dtype=torch.int32, device=R.dev)
+    # per-rank hit slot of the merge: record 0 is the header (this rank's count), the hits follow
+    stride = max(1 << 20, 256 * n_guides // R.world + (1 << 18)) + 1
+    d_send = torch.empty((stride, 4), dtype=torch.int32, device=R.dev)
+    d_hits = d_send[1:]
+    cap = stride - 1
     d_count = torch.zeros(1, dtype=torch.int64, device=R.dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=R.dev)
+    if R.world > 1:
+        d_gath = torch.empty((R.world * stride, 4), dtype=torch.int32, device=R.dev)
+        d_merged = torch.empty((R.world * stride, 4), dtype=torch.int32, device=R.dev)
     use_index = algo != N.OT_SCAN
     # genome-side index (PAM-site table): guide independent, part of the built genome like the
     # reference's bowtie-build output, so it is built before -- not inside -- the timed region
@@ -322,20 +425,29 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
         img.offtarget_search_dev(d_guides.data_ptr(), n_guides, PAM, OT_KW["core_length"],
                                  OT_KW["core_mismatches"], OT_KW["total_mismatches"], algo,
                                  d_hits.data_ptr(), cap, d_count.data_ptr(), R.stream.cuda_stream)
-        if R.world > 1:  # merge the per-GPU hit lists: counts, then the (padded) records
-            allc = torch.empty(R.world, dtype=torch.int64, device=R.dev)
-            dist.all_gather_into_tensor(allc, d_count)
-            m = int(allc.max().item())
-            if m > cap:
-                raise RuntimeError(f"hit buffer too small: {m} > {cap}")
-            merged = torch.empty((R.world * max(m, 1), 4), dtype=torch.int32, device=R.dev)
-            dist.all_gather_into_tensor(merged, d_hits[:max(m, 1)].contiguous())
+        if R.world > 1:
+            # merge of the per-GPU hit lists: the count rides in the header record, ONE padded
+            # all-gather, concat on the device -- no host round trip inside the step
+            d_send[0, :2].copy_(d_count.view(torch.int32))
+            dist.all_gather_into_tensor(d_gath, d_send)
+            img.concat_hits_dev(d_gath.data_ptr(), R.world, stride, d_merged.data_ptr(), d_merged.shape[0],
+                                d_total.data_ptr(), R.stream.cuda_stream)
+            return launches_per_search + 2
         return launches_per_search
 
     ms_step, launches, clocks = R.timed(step, steps, warmup)
     kt = img.kernel_times(steps)
-    region_ms = R.allsum(float(np.mean(kt)), dist.ReduceOp.MAX if R.world > 1 else None)
+    region_ms = R.allmax(float(np.mean(kt)))
     kernel_ms = region_ms
+    n_rank = int(d_count.item())
+    if n_rank > cap:
+        raise RuntimeError(f"hit buffer too small: {n_rank} > {cap}")
+    if R.world > 1:
+        hits = int(d_total.item())
+        checksum = hits_checksum(torch, d_merged, hits)
+    else:
+        hits = n_rank
+        checksum = hits_checksum(torch, d_hits, hits)
     if table is not None:
         # roofline pass: in the timed steps above the join runs as one launch per key slice next
         # to the index build of the following slice, so its event pair brackets both.  The same
@@ -351,15 +463,15 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
                 step()
             torch.cuda.synchronize()
             kt = img.kernel_times(steps)
-            kernel_ms = R.allsum(float(np.mean(kt)), dist.ReduceOp.MAX if R.world > 1 else None)
+            kernel_ms = R.allmax(float(np.mean(kt)))
         finally:
             del os.environ["GUIDO_OT_OVERLAP"]
-    hits = int(R.allsum(float(d_count.item())))
 
-    # end to end through the public API, host buffers in and out.  One GPU: guido_offtarget_search
-    # (letters up, search, device sort, one copy into pinned host memory).  Several GPUs:
-    # parallel.DeviceMerge -- plane words up, search, NCCL all-gather of the hit lists, device sort,
-    # one copy of the merged list into pinned host memory on every rank.
+    # end to end through the public API, host buffers in and out.  One GPU:
+    # guido_offtarget_search_packed (letters up, search, device sort, key-presence flags, one copy of the
+    # 8-byte records into pinned host memory).  Several GPUs: parallel.DeviceMerge -- letters up, search,
+    # one NCCL all-gather, device concat + sort, then every rank copies ITS 1/N of the packed list into a
+    # host segment shared by the ranks (all PCIe links busy instead of one).
     merge = None
     if R.world > 1:
         from guido_b200.parallel import DeviceMerge
@@ -367,11 +479,10 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
 
     def e2e():
         if merge is not None:
-            # the merged list is needed on ONE host: rank 0 copies it down, the others keep it in HBM
-            h = merge.search(guides_u8, pam=PAM, algo=algo, to_host=R.rank == 0, **OT_KW)
-            return 20 * n_guides, 16 * len(h) + 8 * R.world + 8
+            h = merge.search(guides_u8, pam=PAM, algo=algo, to_host="shared", **OT_KW)
+            return 20 * n_guides, 8 * len(h) // R.world + 8 * (R.world + 2)
         st = N.Stats()
-        img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=False, stats=st, pinned=True, **OT_KW)
+        img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=True, stats=st, pinned=True, packed=True, **OT_KW)
         return int(st.bytes_h2d), int(st.bytes_d2h)
 
     e2e_ms, (h2d, d2h) = R.wall(e2e, 3)
@@ -381,7 +492,8 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     # algorithmic bytes of the search kernel on this rank: genome planes once, one 8-byte bucket
     # lookup per window, 4 bytes per index key compared, 16 bytes per hit written
     sites, visited = float(st.n_sites), float(st.n_pairs) if use_index else 0.0
-    hits_rank = float(d_count.item())
+    hits_rank = float(n_rank)
+    blocks = False
     if table is not None:
         # join over the site table.  Block join (>= 8 keys per bucket): 5 B per table slot (the 320-byte
         # blocks of 64 windows, buckets padded to whole blocks: + 32 slots per bucket on average), 8 B per
@@ -393,18 +505,229 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
         n_buckets = 4.0 ** OT_KW["core_length"]
         parts = R.world if getattr(R.a, "key_sharded", False) else 1  # key-sharded ranks build 1/N of the index
         slots = sites + 32.0 * n_buckets / parts
-        if n_keys >= 8.0 * n_buckets and sites * parts >= 64.0 * n_buckets:
+        blocks = n_keys >= 8.0 * n_buckets and sites * parts >= 64.0 * n_buckets
+        if blocks:
             alg_bytes_rank = 5.0 * slots + (8.0 * n_keys + 8.0 * n_buckets) / parts + 40.0 * hits_rank
         else:
             alg_bytes_rank = 16.0 * slots + (4.0 * n_keys + 4.0 * n_buckets) / parts + 36.0 * hits_rank
     else:
         alg_bytes_rank = 0.25 * span + (8.0 * sites + 4.0 * visited if use_index else 0.0) + 16.0 * hits_rank
-    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "table": table,
+    return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "checksum": checksum, "table": table,
             "kernel_ms": kernel_ms, "region_ms": region_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
             "alg_bytes_rank": alg_bytes_rank, "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
-            "pairs_scan": float(st.n_pairs) if not use_index else None,
+            "pairs_scan": float(st.n_pairs) if not use_index else None, "blocks": blocks,
             "e2e_ms": e2e_ms, "h2d": h2d, "d2h": d2h}
 
+
+# ------------------------------------------------------------------------------ configs[4]: TTTV + MMEJ
+
+def exon_set(lens, seed=1006, n_genes=5000):
+    """5 000 genes x 3-8 exons x 100-500 bp on a synthetic genome: (contig,
+    start0, end0) per exon, non-overlapping inside a gene"""
+    rng = np.random.default_rng(seed)
+    lens = np.asarray(lens, dtype=np.int64)
+    exons = []
+    for _ in range(n_genes):
+        ci = int(rng.choice(len(lens), p=lens / lens.sum()))
+        at = int(rng.integers(1000, lens[ci] - 20000))
+        for _ in range(int(rng.integers(3, 9))):
+            ln = int(rng.integers(100, 501))
+            exons.append((ci, at, at + ln))
+            at += ln + int(rng.integers(100, 1500))
+    return np.array(exons, dtype=np.int64)
+
+
+def run_mmej(R, args):
+    """TTTV scan of a 100 Mb genome + MMEJ enumeration for every guide whose cut lies in an exon"""
+    N, torch = R.N, R.torch
+    from guido_b200 import _native
+    lens = [12_500_000] * 8
+    img = N.Image.synth(lens, seed=1006, n_frac=0.005).upload(device=R.dev.index)
+    exons = exon_set(lens)
+    pam, P = "TTTV", 4
+    goff = np.array([c[2] for c in img.contigs], dtype=np.int64)
+    ex_lo, ex_hi = goff[exons[:, 0]] + exons[:, 1], goff[exons[:, 0]] + exons[:, 2]
+    order = np.argsort(ex_lo)
+    ex_lo, ex_hi = ex_lo[order], ex_hi[order]
+
+    def guides_in_exons():
+        fw, rv = img.pam_scan_genome(pam, N.SCAN_GUIDE, pinned=True)
+        # the reference's geometry (guides.py:53-67): '+' cut = p - 3, '-' cut = p + P + 3
+        cut = np.concatenate([fw.astype(np.int64) - 3, rv.astype(np.int64) + P + 3])
+        k = np.searchsorted(ex_lo, cut, side="right") - 1
+        keep = (k >= 0) & (cut < ex_hi[np.maximum(k, 0)])
+        return cut[keep], len(fw) + len(rv)
+
+    def step():
+        cut, n_sites = guides_in_exons()
+        w = img.fetch_windows(cut - 75, 150)  # 150-bp window around the cut (guides.py:69-106)
+        ok = ~(w == ord("N")).any(axis=1)
+        wins = w[ok]
+        blob = wins.tobytes().decode()
+        windows = [blob[i * 150:(i + 1) * 150] for i in range(len(wins))]
+        st = N.Stats()
+        tuples, offsets, n_cand = _native.mmej_batch(windows, [75] * len(windows), device=R.dev.index, stats=st)
+        return len(windows), int(n_cand.sum()), len(tuples), float(st.kernel_ms), n_sites
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    k_ms = 0.0
+    steps = max(min(args.steps, 10), 1)
+    for _ in range(steps):
+        n_guides, n_cand, n_kept, kms, n_sites = step()
+        k_ms += kms
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    k_ms /= steps
+    out = {"metric": "guides/sec, Cas12a TTTV scan + MMEJ enumeration over a 5k-gene exon set (BASELINE configs[4])",
+           "value": n_guides / (ms * 1e-3), "unit": "guides/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 1),
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 letters / u32 bit masks",
+           "data": "synthetic",
+           "config": {"workload": "TTTV scan of a synthetic 100 Mb genome (8 contigs), guides with the cut inside one of "
+                                  f"{len(exons)} exons of 5000 genes, MMEJ candidates of every 150-bp window",
+                      "pam_sites": n_sites, "guides": n_guides, "mmej_candidates": n_cand, "mmej_kept": n_kept,
+                      "timing": "host wall clock of the whole step through the C-ABI calls (scan -> host filter -> window "
+                                "fetch -> guido_mmej_batch with host buffers)"},
+           "gpu_launches": steps * 2,
+           "mmej_kernel": {"kernel": "mmej_kernel", "kernel_ms": k_ms, "windows_per_s": n_guides / (k_ms * 1e-3),
+                           "candidates_per_s": n_cand / (k_ms * 1e-3)},
+           "e2e": {"value": n_guides / (ms * 1e-3), "unit": "guides/s", "ms_per_step": ms,
+                   "h2d_bytes_per_step": 150 * n_guides + 12 * n_guides, "d2h_bytes_per_step": 4 * n_sites + 4 * n_kept + 12 * n_guides}}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_mmej_sample(img, exons, pam)
+    return out
+
+
+def cpu_mmej_sample(img, exons, pam, budget_s=15.0):
+    """`_find_guides_in_interval(..., "TTTV")` + `generate_mmej_patterns` per guide on a bounded sample
+    of the exons: the reference's own code where it is mounted, the oracle port elsewhere; 1 thread"""
+    from oracle import oracle as O
+    O.lib()
+    ref = reference_python()
+    t0 = time.perf_counter()
+    n_guides = n_exons = 0
+    for ci, a, b in exons.tolist():
+        lo = max(a - 100, 0)
+        seq = img.fetch(ci, lo, b - a + 200)
+        if ref is not None:
+            loc = ref.Locus(sequence=seq, name="c", start=lo + 1)
+            for g in loc._find_guides_in_interval(seq, lo + 1, pam):
+                if a < g.absolute_cut_pos <= b and "N" not in g.locus_seq:
+                    ref.mmej.generate_mmej_patterns(g.relative_cut_pos, g.locus_seq, 20)
+                    n_guides += 1
+        else:
+            for g in O.guide_records(seq, lo + 1, pam, chromosome="c"):
+                if a < g["absolute_cut_pos"] <= b and "N" not in g["locus_seq"]:
+                    O.mmej_tuples(g["locus_seq"], g["relative_cut_pos"])
+                    n_guides += 1
+        n_exons += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    kind = "reference-python" if ref is not None else "port"
+    what = ("reference Locus._find_guides_in_interval + mmej.generate_mmej_patterns (guido/locus.py:158-211, mmej.py:8-120)"
+            if ref is not None else "oracle port (Python guide records + C MMEJ enumeration, no pattern dicts)")
+    return {"value": n_guides / dt, "unit": "guides/s", "cores": 1, "kind": kind,
+            "sample": f"{what}, 1 thread: {n_exons} exons, {n_guides} guides in {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------ configs[0]: locus through the API
+
+def run_locus(R, args):
+    """find_guides + off-targets (<=3 mm) for chr2:1,000,001-1,100,000 of a synthetic 10 Mb genome through
+    the drop-in Python API (Genome.build -> locus_from_coordinates -> find_guides -> find_off_targets)"""
+    import tempfile
+    import guido_b200 as guido
+    N = R.N
+    lens = [2_500_000] * 4
+    names = ["chr1", "chr2", "chr3", "chr4"]
+    img = N.Image.synth(lens, seed=1001, n_frac=0.005, names=names)
+    tmp = tempfile.mkdtemp(prefix="guido_bench_")
+    fa = os.path.join(tmp, "g10.fa")
+    with open(fa, "w") as fh:
+        for i, (name, clen, _) in enumerate(img.contigs):
+            s = img.fetch(i, 0, clen)
+            fh.write(f">{name}\n")
+            fh.writelines(s[j:j + 60] + "\n" for j in range(0, len(s), 60))
+    t0 = time.perf_counter()
+    g = guido.Genome("g10", genome_file_abspath=fa)
+    g.build()
+    build_s = time.perf_counter() - t0
+
+    def once():
+        loc = guido.locus_from_coordinates(g, "chr2", 1_000_001, 1_100_000)
+        t0 = time.perf_counter()
+        guides = loc.find_guides()
+        t1 = time.perf_counter()
+        found = loc.find_off_targets(total_mismatches=3)
+        t2 = time.perf_counter()
+        return len(guides), sum(len(v) for v in found.values()), (t1 - t0) * 1e3, (t2 - t1) * 1e3
+
+    for _ in range(max(min(args.warmup, 3), 1)):
+        once()
+    fg, ot = [], []
+    steps = max(min(args.steps, 5), 1)
+    for _ in range(steps):
+        n_guides, n_hits, a, b = once()
+        fg.append(a); ot.append(b)
+    ms = float(np.mean(fg) + np.mean(ot))
+    out = {"metric": "guides/sec through the Python API: find_guides + off-target search (<=3 mm) on a 100 kb locus of a "
+                     "10 Mb genome (BASELINE configs[0])",
+           "value": n_guides / (ms * 1e-3), "unit": "guides/s", "n_gpus": 1, "steps": steps,
+           "warmup": max(min(args.warmup, 3), 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "u32 bit planes", "data": "synthetic",
+           "config": {"workload": "Genome.build (FASTA -> image) once; per step locus_from_coordinates(chr2:1000001-1100000) -> "
+                                  "find_guides() -> find_off_targets(total_mismatches=3); host wall clock, Python records included",
+                      "guides": n_guides, "off_target_records": n_hits, "find_guides_ms": float(np.mean(fg)),
+                      "find_off_targets_ms": float(np.mean(ot)), "genome_build_s": build_s},
+           "gpu_launches": None,
+           "e2e": {"value": n_guides / (ms * 1e-3), "unit": "guides/s", "ms_per_step": ms,
+                   "h2d_bytes_per_step": 20 * n_guides, "d2h_bytes_per_step": 16 * n_hits}}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_locus_sample(img, names)
+    return out
+
+
+def cpu_locus_sample(img, names):
+    """the reference's own find_guides + run_bowtie (its real parsing / filtering / record building, the bowtie
+    subprocess replaced by the oracle's brute-force C search: oracle/fake_bowtie.py) on the same locus"""
+    from oracle import oracle as O
+    O.set_threads(host_threads())
+    ref = reference_python()
+    contigs = [(n, img.fetch(i, 0, img.contigs[i][1])) for i, n in enumerate(names)]
+    seq = contigs[1][1][1_000_000:1_100_000]
+    if ref is None:
+        t0 = time.perf_counter()
+        guides = O.find_guides_records(seq, 1_000_001, None, chromosome="chr2")
+        t1 = time.perf_counter()
+        sub = guides[:512]
+        O.off_target_records(sub, contigs, total_mismatches=3)
+        t2 = time.perf_counter()
+        ot_s = (t2 - t1) * len(guides) / max(len(sub), 1)
+        return {"value": len(guides) / ((t1 - t0) + ot_s), "unit": "guides/s", "cores": O.threads(), "kind": "port",
+                "sample": f"oracle port: find_guides_records {len(guides)} guides in {t1 - t0:.2f} s (1 thread, Python); "
+                          f"off_target_records of {len(sub)} guides (brute-force C search, {O.threads()} threads) in "
+                          f"{t2 - t1:.2f} s, scaled to all guides"}
+    from oracle import fake_bowtie
+    loc = ref.Locus(sequence=seq, name="chr2", start=1_000_001)
+    t0 = time.perf_counter()
+    guides = loc.find_guides()
+    t1 = time.perf_counter()
+    loc.guides = guides[:512]
+    loc.genome = fake_bowtie.FakeGenome("idx")
+    with fake_bowtie.patched(ref, {"idx": contigs}):
+        found = loc.find_off_targets(total_mismatches=3)
+    t2 = time.perf_counter()
+    ot_s = (t2 - t1) * len(guides) / 512
+    return {"value": len(guides) / ((t1 - t0) + ot_s), "unit": "guides/s", "cores": O.threads(), "kind": "reference-python",
+            "sample": f"reference Locus.find_guides: {len(guides)} guides in {t1 - t0:.2f} s (1 thread); reference "
+                      f"find_off_targets/run_bowtie for 512 of them with the bowtie subprocess replaced by the oracle's brute-force "
+                      f"C search ({O.threads()} threads): {t2 - t1:.2f} s, {sum(len(v) for v in found.values())} records, scaled to all guides"}
+
+
+# ------------------------------------------------------------------------------ main
 
 def main():
     ap = argparse.ArgumentParser()
@@ -412,7 +735,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="offtarget", choices=["offtarget", "pam"])
+    ap.add_argument("--workload", default="offtarget", choices=["offtarget", "pam", "mmej", "locus"])
     ap.add_argument("--genome", default=None)
     ap.add_argument("--guides", type=int, default=None)
     ap.add_argument("--algo", default="auto", choices=["auto", "scan", "index", "table"])
@@ -448,6 +771,17 @@ def main():
     R = Runner(args, N, torch, dist, rank, world, local_rank)
     peak, peak_src = measured_peak_gbs()
 
+    if args.workload in ("mmej", "locus"):
+        if rank == 0:
+            out = run_mmej(R, args) if args.workload == "mmej" else run_locus(R, args)
+            print(json.dumps(out), flush=True)
+        if R.sampler:
+            R.sampler.stop()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
     img = N.Image.synth(lens, seed=seed, n_frac=n_frac)
     # Multi-GPU off-target search: by default every rank keeps the whole image (0.8 GB) and tables /
     # searches 1/N of the core-key space (guido_site_table_partition), so the per-search guide index
@@ -460,7 +794,6 @@ def main():
     else:
         img.upload(device=local_rank, shard_ix=rank, n_shards=world)
     args.key_sharded = key_sharded
-    G = img.info.total_bases
     out = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic"}
 
@@ -491,15 +824,14 @@ def main():
         gps = args.guides / (r["ms_per_step"] * 1e-3)
         use_index = algo != N.OT_SCAN
         use_table = r["table"] is not None
-        # the join compares bit-sliced (32 keys per LOP3 lane) once buckets hold >= 16 keys on average
-        sliced = use_table and 436 * args.guides >= 8 * 4 ** OT_KW["core_length"] and r["sites"] >= 64 * 4 ** OT_KW["core_length"]
-        kernel = ("ot_join_blocks_kernel" if sliced else "ot_join_kernel" if use_table else
+        blocks = r["blocks"]
+        kernel = ("ot_join_blocks_kernel" if blocks else "ot_join_kernel" if use_table else
                   "ot_kernel<index>" if use_index else "ot_kernel<scan>")
         algo_desc = ("guide-side seed index joined with the genome's PAM-site table" if use_table else
                      "seed index + streaming window scan" if use_index else "brute-force window x guide scan")
         alg_desc = ("per GPU: 5 B per slot of the bit-sliced site table (buckets padded to 64 slots) + 8 B per index "
-                    "entry + 8 B of offsets per bucket + 40 B per hit; the compare itself is ALU-pipe bound, see "
-                    "int_pipe" if sliced else
+                    "entry + 8 B of offsets per bucket + 40 B per hit; the compare itself is bound by the ALU pipe and the "
+                    "shared-memory data pipe, see int_pipe" if blocks else
                     "per GPU: 16 B per table slot + 4 B per index key + 4 B per bucket offset + 36 B per hit" if use_table else
                     "per GPU: 0.25 B/base planes + 8 B bucket lookup per window + 4 B per index "
                     "key compared + 16 B per hit" if use_index else
@@ -507,19 +839,26 @@ def main():
                     "integer-issue bound, see int_pipe)")
         out.update({
             "value": gps, "unit": "guides/s", "ms_per_step": r["ms_per_step"],
-            "dtype": "u32 bit planes (bit-sliced LOP3 carry-save count)" if sliced else "u32 bit planes (XOR/OR + popc)", "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "dtype": "u32 bit planes (bit-sliced LOP3 carry-save count)" if blocks else "u32 bit planes (XOR/OR + popc)",
+            "gpu_launches": r["launches"], "clocks": r["clocks"],
             "config": {"workload": f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
                                    + (" (BASELINE configs[3] on N GPUs)" if args.genome == "human" else " (BASELINE configs[2])"),
                        "pam": PAM, "algo": algo_desc,
                        "l2": "flushed between steps; the shard's site table / planes + index keys exceed L2",
                        "parallelism": (f"PAM-site table partitioned by core k-mer range x{world} (whole image on every "
-                                       "rank), guide index built in the same parts, NCCL all-gather of hit lists"
+                                       "rank), guide index built in the same parts, one padded NCCL all-gather of the hit lists "
+                                       "(count in a header record) + device concat"
                                        if key_sharded else
-                                       f"genome sharded x{world}, guides replicated, NCCL all-gather of hit lists"),
-                       "hits": r["hits"], "windows": r["sites"], "index_keys_compared": r["visited"],
+                                       f"genome sharded x{world}, guides replicated, one padded NCCL all-gather of the hit lists"),
+                       "hits": r["hits"], "hits_checksum": f"{r['checksum']:016x}",
+                       "windows": r["sites"], "index_keys_compared": r["visited"],
                        "site_table": r["table"]},
             "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],
-                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "what": ("guido_offtarget_search_packed: 20 letters per guide up; search, device sort, key-presence flags; "
+                             "8-byte hit records + 1 flag byte per guide down into pinned host memory" if world == 1 else
+                             "parallel.DeviceMerge: letters up on every rank; search, one all-gather, concat + sort on every GPU; "
+                             "every rank copies its 1/N of the 8-byte records into a host segment shared by the ranks")},
             "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                          "frac": r["kernel_gbs_per_gpu"] / peak,
                          "traffic": ncu_traffic(kernel, use_index and args.genome == "human" and args.guides == 100_000 and world == 1),
@@ -536,15 +875,17 @@ def main():
         if use_index and r["visited"]:
             sm_mhz = (r["clocks"] or {}).get("sm_mhz") or 1965.0
             per_gpu = r["visited"] / world / (r["kernel_ms"] * 1e-3)
-            if sliced:
-                # per (entry, block of 32 windows): 10 four-byte shared-memory loads (the mismatch words of
-                # the entry's own letters) + 18 LOP3 of carry-save counting on the ALU pipe (16 lanes/clk
-                # per SM sub-partition = 2 warp-instr/clk/SM); `visited` = entries x slots compared
-                out["int_pipe"] = {"pair_compares_per_s_per_gpu": per_gpu, "lop3_per_32_windows": 18, "loads_per_32_windows": 10,
-                                   "alu_warp_instr_per_clk_per_sm_for_compare": per_gpu / 32 * 18 / 32 / 148 / (sm_mhz * 1e6),
+            if blocks:
+                # per (entry, 32 windows): one 4-byte shared-memory word per distal base (ten 8-byte loads per 64
+                # windows) + 14 LOP3 (bias class "at most 2 of 10", most passes) or 18 LOP3 of carry-save counting on
+                # the ALU pipe (16 lanes/clk per SM sub-partition = 2 warp-instr/clk/SM); `visited` = entries x slots
+                out["int_pipe"] = {"pair_compares_per_s_per_gpu": per_gpu, "lop3_per_32_windows": "14 (bias 5 passes) / 18",
+                                   "shared_loads_per_64_windows": 10,
+                                   "alu_warp_instr_per_clk_per_sm_for_compare_at_14": per_gpu / 32 * 14 / 32 / 148 / (sm_mhz * 1e6),
                                    "alu_peak_warp_instr_per_clk_per_sm": 2, "sm_mhz": sm_mhz,
-                                   "note": "no XOR/OR stage and no POPC: per-letter mismatch words are loaded, an 18-LOP3 "
-                                           "carry-save tree counts them"}
+                                   "note": "no XOR/OR stage and no POPC: per-letter mismatch words are loaded, a LOP3 carry-save "
+                                           "tree counts them; ncu (profiles/r2_join.md): ALU pipe and shared-memory data pipe both "
+                                           "~65 % busy"}
             else:
                 # the popc kernels do one POPC per key compared: 16 lanes/clk/SM on sm_100
                 out["int_pipe"] = {"key_compares_per_s_per_gpu": per_gpu, "popc_per_clk_per_sm": per_gpu / 148 / (sm_mhz * 1e6),
@@ -553,6 +894,13 @@ def main():
         if not use_index and r["pairs_scan"]:
             out["int_pipe"] = {"pairs_per_s_per_gpu": r["pairs_scan"] / (r["kernel_ms"] * 1e-3), "ops_per_pair": 4,
                                "note": "2 LOP3 + POPC + ISETP per (window, guide) pair"}
+        if not args.no_cpu_baseline and world == 1 and rank == 0:
+            # the CPU arm of the same workload, beside the GPU number (index over the whole genome, a
+            # bounded sample of the guides per measurement)
+            img.site_table_free()
+            cpu = CpuOfftarget(img)
+            out["cpu_baseline"] = cpu.baseline(guides_u8)
+            cpu.index.close()
         if not args.no_pam and world == 1:
             # second half of the metric in the same run: NGG scan of the 273 Mb genome (configs[1])
             img.close()
@@ -564,13 +912,12 @@ def main():
                                "hits": p["hits"], "bases_per_s": p["bases"] / (p["ms_per_step"] * 1e-3),
                                "roofline": {"bound": "hbm", "achieved": p["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                                             "frac": p["kernel_gbs_per_gpu"] / peak, "kernel": p["kernel"],
-                                            "kernel_ms": p["kernel_ms"]},
+                                            "kernel_ms": p["kernel_ms"],
+                                            "traffic": ncu_traffic(p["kernel"], True)},
                                "e2e": {"value": p["e2e_gbs"], "unit": "GB/s", "ms_per_step": p["e2e_ms"],
                                        "d2h_bytes_per_step": p["d2h"]}}
-            img = img2
-        if not args.no_cpu_baseline and world == 1 and rank == 0:
-            img3 = N.Image.synth(lens, seed=seed, n_frac=n_frac) if not args.no_pam else img
-            out["cpu_baseline"] = cpu_offtarget_sample(img3, guides_u8, 2.0 * G)
+            if not args.no_cpu_baseline and rank == 0:
+                out["pam_scan"]["cpu_baseline"] = cpu_pam_sample(img2)
     if R.sampler:
         R.sampler.stop()
     if rank == 0:
@@ -581,36 +928,52 @@ def main():
 
 
 def run_reference(args, N, lens, seed, n_frac, gdesc):
-    """CPU arm: the reference's own path is bowtie 1.3.1 + Python; bowtie is not in this image, so the
-    oracle's C restatement of its -n rule (all host cores) stands in, on a bounded sample."""
+    """CPU arm.  Off-target search: the seed-indexed C port on every host thread, index over the whole
+    genome built once (bowtie-build counterpart), exactly --steps timed searches of a bounded guide
+    sample after --warmup untimed ones.  PAM scan: the reference's own Python where it is mounted."""
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.workload in ("mmej", "locus"):
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU arm of --workload {args.workload} is the cpu_baseline "
+                                                                "object of the b200 line"}), flush=True)
+        return
     img = N.Image.synth(lens, seed=seed, n_frac=n_frac)
     G = img.info.total_bases
-    vals, cb = [], None
-    t_all = time.perf_counter()
-    guides_u8 = sample_guides(img, min(args.guides, 512), seed + 1) if args.workload == "offtarget" else None
-    for i in range(args.warmup + max(1, args.steps)):
-        if args.workload == "pam":
-            cb = cpu_pam_sample(img, budget_s=6.0)
-        else:
-            cb = cpu_offtarget_sample(img, guides_u8, 2.0 * G, budget_s=8.0)
-        if i >= args.warmup:
-            vals.append(cb["value"])
-        if time.perf_counter() - t_all > 150:
-            break
-    v = float(np.mean(vals)) if vals else cb["value"]
-    cb["value"] = v
-    if args.workload == "offtarget":
-        ms = args.guides / v * 1e3
-        workload = f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
-    else:
+    vals = []
+    if args.workload == "pam":
+        cb = None
+        for i in range(warmup + steps):
+            cb = cpu_pam_sample(img, budget_s=max(1.0, min(6.0, 120.0 / (warmup + steps))))
+            if i >= warmup:
+                vals.append(cb["value"])
+        v = float(np.mean(vals))
+        cb["value"] = v
         ms = G / cb["bases_per_s"] * 1e3
         workload = f"whole-genome NGG PAM scan, both strands, {gdesc}"
+        dtype = "regex over str" if cb["kind"] == "reference-python" else "u8 letters"
+    else:
+        guides_u8 = sample_guides(img, args.guides, seed + 1)
+        cpu = CpuOfftarget(img)
+        # sample size per step: about 100 s of search in total
+        rate, _, _ = cpu.step(guides_u8[:1000])
+        n = int(min(len(guides_u8), max(1000, rate * 100.0 / (warmup + steps))))
+        hits = dt = 0
+        for i in range(warmup + steps):
+            lo = (i * n) % max(len(guides_u8) - n, 1)
+            rate, hits, dt = cpu.step(guides_u8[lo:lo + n])
+            if i >= warmup:
+                vals.append(rate)
+        cb = cpu.describe(float(np.mean(vals)), n, hits, dt)
+        v = cb["value"]
+        ms = args.guides / v * 1e3
+        workload = f"{args.guides} SpCas9 guides, <=4 mm (core 10 / <=2) vs {gdesc}"
+        dtype = "u32 2-bit codes (XOR + popcount per indexed window)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": cb["unit"], "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64 (2-bit XOR + popcount)", "data": "synthetic",
+        "steps": len(vals), "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": workload,
-                   "note": "bounded sample scaled to the whole workload; ms_per_step is the projected full-job time"},
+                   "note": "every step is a bounded sample of the workload (a slice of the guides against the whole genome); "
+                           "ms_per_step is the projected time of the full job at the measured rate"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -69,10 +69,15 @@ _SIGNATURES = {
     "guido_pam_scan_genome_dev": (ctypes.c_int, [_vp, _cp, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     "guido_offtarget_search": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _i64,
                                               _P(_i64), _vp, _P(Stats)]),
+    "guido_offtarget_search_packed": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _i64,
+                                                     _P(_i64), _vp, _P(Stats)]),
+    "guido_hits_expand": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
                                                   _i64, _vp, _vp]),
     "guido_offtarget_raw_flags": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _vp]),
     "guido_hits_sort_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "guido_hits_concat_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
+    "guido_hits_pack_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "guido_encode_guides_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
     "guido_site_table_free": (ctypes.c_int, [_vp]),
@@ -353,10 +358,13 @@ class Image:
         return self
 
     def offtarget_search(self, protos, pam="NGG", core_length=10, core_mismatches=2,
-                         total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False):
+                         total_mismatches=4, algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False,
+                         packed=False):
         """protos: list of 20-nt strings (or an (n,20) uint8 array of letters).
 
         Returns (hits structured array sorted by (guide, gpos, strand), raw_flags uint8[n] | None).
+        ``packed=True``: hits come back as uint64 ``guide << 33 | gpos << 1 | strand`` (half the
+        device-to-host bytes); ``expand_hits`` turns them into the structured records on the host.
         """
         if isinstance(protos, np.ndarray):
             blob = np.ascontiguousarray(protos, dtype=np.uint8).tobytes()
@@ -371,18 +379,26 @@ class Image:
         flags = np.zeros(n, np.uint8) if want_raw_flags else None
         st = stats if stats is not None else Stats()
         cap = max(4096, 32 * n, getattr(self, "_ot_hint", 0))
+        dtype = np.uint64 if packed else OT_HIT_DTYPE
+        call = lib().guido_offtarget_search_packed if packed else lib().guido_offtarget_search
         while True:
-            hits = self._pinned("hits", cap, OT_HIT_DTYPE) if pinned else np.empty(cap, OT_HIT_DTYPE)
+            hits = self._pinned("hits", cap, dtype) if pinned else np.empty(cap, dtype)
             nh = ctypes.c_int64()
-            rc = lib().guido_offtarget_search(self._h, blob, n, pam.encode(), core_length,
-                                              core_mismatches, total_mismatches, algo, hits.ctypes.data,
-                                              cap, ctypes.byref(nh), _ptr(flags), ctypes.byref(st))
+            rc = call(self._h, blob, n, pam.encode(), core_length, core_mismatches, total_mismatches, algo,
+                      hits.ctypes.data, cap, ctypes.byref(nh), _ptr(flags), ctypes.byref(st))
             if rc == ERR_CAPACITY:
                 cap = nh.value
                 continue
             check(rc)
             self._ot_hint = nh.value + nh.value // 16 + 16  # right-size the next call's buffer
             return hits[:nh.value], flags
+
+    def expand_hits(self, packed, pam_len=3):
+        """uint64 packed hits -> structured records (window planes cut from the host image)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        out = np.empty(len(packed), OT_HIT_DTYPE)
+        check(lib().guido_hits_expand(self._h, packed.ctypes.data, len(packed), pam_len, out.ctypes.data))
+        return out
 
     def offtarget_raw_flags(self, protos, pam="NGG", core_length=10, core_mismatches=2, total_mismatches=4):
         """uint8[n]: 1 where the guide has any raw bowtie alignment in this handle's stretch of the
@@ -405,6 +421,14 @@ class Image:
     def encode_guides_dev(self, d_letters, n_guides, d_out, d_bad=None, stream=0):
         """n x 20 letters in HBM -> n x {hi, lo} plane words in HBM; asynchronous"""
         check(lib().guido_encode_guides_dev(self._h, d_letters, n_guides, d_out, d_bad, stream))
+
+    def concat_hits_dev(self, d_gathered, n_parts, stride, d_out, cap, d_total, stream=0):
+        """padded, header-prefixed per-rank lists (one all-gather) -> one contiguous list; asynchronous"""
+        check(lib().guido_hits_concat_dev(self._h, d_gathered, n_parts, stride, d_out, cap, d_total, stream))
+
+    def pack_hits_dev(self, d_hits, n_hits, d_out, stream=0):
+        """device-resident 16-byte records -> 8-byte guide << 33 | gpos << 1 | strand; asynchronous"""
+        check(lib().guido_hits_pack_dev(self._h, d_hits, n_hits, d_out, stream))
 
     def sort_hits_dev(self, d_hits, n_hits, n_guides, stream=0):
         """device-resident hit records -> (guide, gpos, strand) order, in place, asynchronous"""

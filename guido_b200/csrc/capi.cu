@@ -473,6 +473,22 @@ int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_g
     return encode_guides_device(ds, (const char *)d_letters, n_guides, (uint2 *)d_out, bad, (cudaStream_t)stream);
 }
 
+int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride, void *d_out,
+                          int64_t cap, void *d_total, void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (!d_gathered || !d_out || !d_total || stride < 1 || cap < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    return concat_hits_device(img->dev, (const guido_ot_hit *)d_gathered, n_parts, (uint64_t)stride, (guido_ot_hit *)d_out,
+                              (uint64_t)cap, (unsigned long long *)d_total, (cudaStream_t)stream);
+}
+
+int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, void *d_out, void *stream) {
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_hits < 0 || (n_hits && (!d_hits || !d_out))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    return pack_hits_device(img->dev, (const guido_ot_hit *)d_hits, (uint64_t)n_hits, (unsigned long long *)d_out, (cudaStream_t)stream);
+}
+
 int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream) {
     int rc = need_device(img);
     if (rc) return rc;
@@ -537,10 +553,13 @@ int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_gu
     return relaxed_flag_pass(img, protos, todo, pam, core_len, core_mm, total_mm, flags, nullptr, nullptr, nullptr, nullptr);
 }
 
-int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
-                           int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
-                           guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
-                           guido_stats *stats) {
+}  // extern "C"
+
+// `packed`: hits_out receives 8-byte records (guide << 33 | gpos << 1 | strand) instead of guido_ot_hit
+static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                                 int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                                 void *hits_out, bool packed, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                                 guido_stats *stats) {
     int rc = need_device(img);
     if (rc) return rc;
     OtParams op;
@@ -616,8 +635,17 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
     if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;
     if (trace) { cudaStreamSynchronize(st); lap("sort done"); }
     int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
-    if (ncopy) GUIDO_CUDA(cudaMemcpyAsync(hits, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
-    int64_t d2h = 16 + ncopy * 16, h2d = kProto * n_guides;
+    const int64_t rec_bytes = packed ? 8 : (int64_t)sizeof(guido_ot_hit);
+    if (ncopy && packed) {
+        // the sort's scratch (d_out[1]) is free again: pack into it
+        if ((rc = ensure_bytes(&ds->d_out[1], &ds->out_cap[1], ncopy * 8))) return rc;
+        if ((rc = pack_hits_device(ds, (const guido_ot_hit *)ds->d_out[0], (uint64_t)ncopy, (unsigned long long *)ds->d_out[1], st))) return rc;
+        launches += 1;
+        GUIDO_CUDA(cudaMemcpyAsync(hits_out, ds->d_out[1], (size_t)ncopy * 8, cudaMemcpyDeviceToHost, st));
+    } else if (ncopy) {
+        GUIDO_CUDA(cudaMemcpyAsync(hits_out, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
+    }
+    int64_t d2h = 16 + ncopy * rec_bytes, h2d = kProto * n_guides;
     if (raw_flags && n_guides > 0) {
         // a valid hit is a raw alignment: mark the guides that own one (on the device -- walking
         // 1e7 hit records on the host costs more than the search)
@@ -662,6 +690,24 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
         return GUIDO_ERR_CAPACITY;
     }
     return GUIDO_OK;
+}
+
+extern "C" {
+
+int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                           int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                           guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                           guido_stats *stats) {
+    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, false, cap, n_hits,
+                                 raw_flags, stats);
+}
+
+int guido_offtarget_search_packed(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                                  int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                                  uint64_t *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                                  guido_stats *stats) {
+    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, true, cap, n_hits,
+                                 raw_flags, stats);
 }
 
 }  // extern "C"

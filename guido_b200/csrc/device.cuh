@@ -119,6 +119,9 @@ int sort_hits_device(DeviceState *ds, guido_ot_hit *d_hits, uint64_t n, int64_t 
                      int *n_launches);
 int encode_guides_device(DeviceState *ds, const char *d_letters, int64_t n, uint2 *d_out, unsigned long long *d_bad,
                          cudaStream_t stream);
+int pack_hits_device(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, unsigned long long *d_out, cudaStream_t stream);
+int concat_hits_device(DeviceState *ds, const guido_ot_hit *d_gathered, int n_parts, uint64_t stride, guido_ot_hit *d_out,
+                       uint64_t cap, unsigned long long *d_total, cudaStream_t stream);
 int mark_hit_guides(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uint8_t *d_flags, cudaStream_t stream);
 bool ot_index_applicable(const OtParams &op, int64_t n_guides);
 

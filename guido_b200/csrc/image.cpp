@@ -450,6 +450,36 @@ int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64
     return GUIDO_OK;
 }
 
+// 8-byte wire records -> 16-byte records: the window planes come from the host copy of the image,
+// cut and oriented exactly as the search kernels do it (offtarget.cu, ot_kernel)
+int guido_hits_expand(const guido_image *img, const uint64_t *packed, int64_t n, int32_t pam_len, guido_ot_hit *out) {
+    if (!img || n < 0 || pam_len < 1 || pam_len > kMaxPam || (n && (!packed || !out))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    const int W = kProto + pam_len;
+    const uint32_t wmask = (1u << W) - 1;
+    const int64_t n_words = (int64_t)img->planes.size();
+    auto rev = [&](uint32_t x) {  // reverse the low W bits
+        uint32_t r = 0;
+        for (int i = 0; i < W; i++) r |= ((x >> i) & 1u) << (W - 1 - i);
+        return r;
+    };
+    for (int64_t i = 0; i < n; i++) {
+        const uint64_t k = packed[i];
+        const uint32_t strand = (uint32_t)(k & 1), gpos = (uint32_t)((k >> 1) & 0xffffffffull), guide = (uint32_t)(k >> 33);
+        const int64_t b = gpos >> 6;
+        const int sh = (int)(gpos & 63);
+        if (2 * b + 1 >= n_words) { set_error("hit %lld lies outside the image", (long long)i); return GUIDO_ERR_ARG; }
+        uint64_t lo = img->planes[(size_t)(2 * b)] >> sh, hi = img->planes[(size_t)(2 * b + 1)] >> sh;
+        if (sh && 2 * b + 3 < n_words) {
+            lo |= img->planes[(size_t)(2 * b + 2)] << (64 - sh);
+            hi |= img->planes[(size_t)(2 * b + 3)] << (64 - sh);
+        }
+        uint32_t h = (uint32_t)hi & wmask, l = (uint32_t)lo & wmask;
+        if (strand) { h = (rev(h) ^ wmask) | 0x80000000u; l = rev(l) ^ wmask; }
+        out[i].guide = guide; out[i].gpos = gpos; out[i].hi = h; out[i].lo = l;
+    }
+    return GUIDO_OK;
+}
+
 int guido_encode_guides(const char *protos, int64_t n, uint32_t *out) {
     uint8_t code[256];  // table lookup: a switch on random letters mispredicts on every second one
     memset(code, 0xff, sizeof code);

@@ -40,6 +40,61 @@ __global__ void __launch_bounds__(256) merge_hits_kernel(const unsigned long lon
     }
 }
 
+// 16-byte records -> 8-byte wire format: guide << 33 | gpos << 1 | strand (the sort key itself; the
+// window planes can be re-derived from the image, guido_hits_expand)
+__global__ void __launch_bounds__(256) pack_hits_kernel(const guido_ot_hit *hits, uint64_t n, unsigned long long *out) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(hits);
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+        const uint4 h = src[i];
+        out[i] = ((unsigned long long)h.x << 33) | ((unsigned long long)h.y << 1) | (h.z >> 31);
+    }
+}
+
+int pack_hits_device(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, unsigned long long *d_out, cudaStream_t stream) {
+    if (n == 0) return GUIDO_OK;
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ds->sm_count * 16);
+    pack_hits_kernel<<<grid, 256, 0, stream>>>(d_hits, n, d_out);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
+// Merge of per-rank hit lists after ONE padded all-gather: part r sits at gathered[r * stride ..],
+// its record 0 is a header whose first 8 bytes hold the part's hit count, the hits follow.  The parts
+// are copied back to back into `out`; *total receives the sum.  No host round trip between the
+// search, the gather and this kernel.
+__global__ void __launch_bounds__(256) concat_hits_kernel(const uint4 *gathered, int n_parts, unsigned long long stride,
+                                                           uint4 *out, unsigned long long cap, unsigned long long *total) {
+    __shared__ unsigned long long s_off[65];
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int r = 0; r < n_parts; r++) {
+            const uint4 h = gathered[(size_t)r * stride];
+            unsigned long long c = ((unsigned long long)h.y << 32) | h.x;
+            if (c > stride - 1) c = stride - 1;  // a part that overflowed its slot: the caller re-runs with a larger stride
+            s_off[r] = run;
+            run += c;
+        }
+        s_off[n_parts] = run;
+        if (blockIdx.x == 0) *total = run;
+    }
+    __syncthreads();
+    for (int r = 0; r < n_parts; r++) {
+        const unsigned long long n = s_off[r + 1] - s_off[r];
+        const uint4 *src = gathered + (size_t)r * stride + 1;
+        for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256ull)
+            if (s_off[r] + i < cap) out[s_off[r] + i] = src[i];
+    }
+}
+
+int concat_hits_device(DeviceState *ds, const guido_ot_hit *d_gathered, int n_parts, uint64_t stride, guido_ot_hit *d_out,
+                       uint64_t cap, unsigned long long *d_total, cudaStream_t stream) {
+    if (n_parts < 1 || n_parts > 64 || stride < 1) { set_error("bad part count or stride"); return GUIDO_ERR_ARG; }
+    concat_hits_kernel<<<ds->sm_count * 4, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_gathered), n_parts, stride,
+                                                            reinterpret_cast<uint4 *>(d_out), cap, d_total);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
 __global__ void __launch_bounds__(256) mark_guides_kernel(const guido_ot_hit *hits, uint64_t n, uint8_t *flags) {
     for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull)
         flags[hits[i].guide] = 1;

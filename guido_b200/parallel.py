@@ -53,30 +53,73 @@ def all_gather_hits(hits, group=None, device=None):
 
 class DeviceMerge:
     """Off-target search of this rank's share + merge of all ranks' hits without leaving the GPUs
-    (NCCL process group): the guides' plane words go up once, the hits stay in HBM
-    (``guido_offtarget_search_dev``), the per-rank lists are all-gathered over NVLink, brought into
-    canonical (guide, gpos, strand) order on the device (``guido_hits_sort_dev``) and only then
-    copied to (pinned) host memory -- one device->host copy of the final list instead of a copy per
-    rank, an upload for the gather and a host sort.  Buffers are kept between calls."""
+    (NCCL process group).  The letters go up once and are packed on the device, the hits stay in
+    HBM (``guido_offtarget_search_dev``), and the per-rank lists travel in ONE fixed-size all-gather:
+    every rank sends ``stride`` records, the first one a header carrying its hit count (written by a
+    device-side copy), so no host round trip sits between search, gather and merge
+    (``guido_hits_concat_dev``).  The merged list is brought into canonical (guide, gpos, strand)
+    order on every GPU (``guido_hits_sort_dev``).
+
+    ``to_host``:
+      * ``"rank0"`` / True -- rank 0 copies the list to pinned host memory (16-byte records);
+      * ``"shared"`` -- every rank packs the list to 8-byte records (``guido_hits_pack_dev``) and copies
+        ITS 1/world of it into one host segment shared by the ranks of the node (a ``/dev/shm`` file,
+        page-locked in every process): all PCIe links carry 1/world of the bytes instead of one link
+        carrying all of them.  Returns the whole packed list (a view of the shared segment);
+      * False -- the sorted (n, 4) int32 device tensor.
+    Buffers are kept between calls; ``stride`` follows the largest per-rank count seen so far."""
 
     def __init__(self, image, group=None):
         import torch
         self.image, self.group = image, group
         self.dev = torch.device("cuda", int(image.info.device))  # the device the image was uploaded to
-        self.cap = 0
-        self.d_hits = self.d_count = self.d_bad = self.host = None
+        self.stride = 0
+        self.d_send = self.d_gath = self.d_merged = self.d_packed = None
+        self.d_count = self.d_total = self.d_bad = self.host = None
+        self.shared = None
+
+    def _shared_segment(self, n_records):
+        """uint64 view of a host segment all ranks of the node map and page-lock"""
+        import mmap
+        import os
+        import torch
+        import torch.distributed as dist
+        need = max(int(n_records), 1) * 8
+        if self.shared is not None and self.shared[0] >= need:
+            return self.shared[1]
+        rank = dist.get_rank(self.group)
+        size = (need + need // 4 + (1 << 20)) & ~4095
+        if self.shared is not None:
+            torch.cuda.cudart().cudaHostUnregister(self.shared[3])
+            self.shared[2].close()
+        path = f"/dev/shm/guido_b200_merge_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}_{size}"
+        if rank == 0:
+            with open(path, "wb") as fh:
+                fh.truncate(size)
+        dist.barrier(group=self.group)
+        fd = os.open(path, os.O_RDWR)
+        mm = mmap.mmap(fd, size)
+        os.close(fd)
+        dist.barrier(group=self.group)
+        if rank == 0:
+            os.unlink(path)  # the mappings keep the segment alive
+        arr = np.frombuffer(mm, dtype=np.uint64)
+        rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, size, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared merge segment failed: {rc}")
+        self.shared = (size, arr, mm, arr.ctypes.data)
+        return arr
 
     def search(self, protos, pam="NGG", core_length=10, core_mismatches=2, total_mismatches=4,
                algo=_native.OT_AUTO, to_host=True):
-        """-> merged hits (structured array in pinned host memory, or the (n,4) int32 device tensor
-        when ``to_host`` is false), identical on every rank"""
-        import torch
-        import torch.distributed as dist
+        """-> merged hits, identical on every rank (see the class docstring for ``to_host``)"""
         import os
         import sys
         import time
-        world = dist.get_world_size(self.group)
-        trace = os.environ.get("GUIDO_TRACE") and dist.get_rank(self.group) == 0
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        trace = os.environ.get("GUIDO_TRACE") and rank == 0
         t0 = time.perf_counter()
 
         def lap(what):  # GUIDO_TRACE=1: wall clock of the phases on stderr (rank 0; synchronises)
@@ -100,41 +143,59 @@ class DeviceMerge:
             d_guides = torch.empty((max(n, 1), 2), dtype=torch.int32, device=self.dev)
             if self.d_count is None:
                 self.d_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+                self.d_total = torch.zeros(1, dtype=torch.int64, device=self.dev)
                 self.d_bad = torch.empty(1, dtype=torch.int64, device=self.dev)
             self.d_bad.fill_(-1)
             self.image.encode_guides_dev(d_letters.data_ptr(), n, d_guides.data_ptr(), self.d_bad.data_ptr(),
                                          stream.cuda_stream)
-            if self.cap == 0:
-                self.cap = max(1 << 16, 64 * n // world)
+            if self.stride == 0:
+                self.stride = max(1 << 16, 64 * n // world) + 1
             while True:
-                if self.d_hits is None or self.d_hits.shape[0] < self.cap:
-                    self.d_hits = torch.empty((self.cap, 4), dtype=torch.int32, device=self.dev)
+                if self.d_send is None or self.d_send.shape[0] < self.stride:
+                    self.d_send = torch.empty((self.stride, 4), dtype=torch.int32, device=self.dev)
+                    self.d_gath = torch.empty((world * self.stride, 4), dtype=torch.int32, device=self.dev)
+                    self.d_merged = torch.empty((world * self.stride, 4), dtype=torch.int32, device=self.dev)
+                stride = self.d_send.shape[0]
                 self.image.offtarget_search_dev(d_guides.data_ptr(), n, pam, core_length, core_mismatches,
-                                                total_mismatches, algo, self.d_hits.data_ptr(), self.cap,
+                                                total_mismatches, algo, self.d_send[1:].data_ptr(), stride - 1,
                                                 self.d_count.data_ptr(), stream.cuda_stream)
+                self.d_send[0, :2].copy_(self.d_count.view(torch.int32))  # the header: this rank's count
                 lap("search")
-                allc = torch.empty(world, dtype=torch.int64, device=self.dev)
-                dist.all_gather_into_tensor(allc, self.d_count, group=self.group)
-                counts = allc.tolist()
-                lap("counts")
-                bad = int(self.d_bad.item())
+                dist.all_gather_into_tensor(self.d_gath, self.d_send, group=self.group)
+                lap("gather")
+                self.image.concat_hits_dev(self.d_gath.data_ptr(), world, stride, self.d_merged.data_ptr(),
+                                           self.d_merged.shape[0], self.d_total.data_ptr(), stream.cuda_stream)
+                # the one host read of the call: every rank's count (overflow check), the total, bad letters
+                heads = self.d_gath[::stride, :2].contiguous().view(torch.int64).reshape(-1)
+                info = torch.cat([heads, self.d_total, self.d_bad]).tolist()
+                counts, total, bad = info[:world], info[world], info[world + 1]
+                lap("concat")
                 if bad != -1:
                     raise ValueError(f"guide {bad // 32} holds a letter outside A/C/G/T at position {bad % 32 + 1}")
-                m = max(counts)
-                if m <= self.cap:
+                if max(counts) <= stride - 1:
                     break
-                self.cap = m + m // 8  # the exact need is known now: one more pass
-            m = max(m, 1)
-            gathered = torch.empty((world * m, 4), dtype=torch.int32, device=self.dev)
-            dist.all_gather_into_tensor(gathered, self.d_hits[:m], group=self.group)
-            merged = gathered if world == 1 else torch.cat([gathered[r * m:r * m + c] for r, c in enumerate(counts)])
-            total = sum(counts)
-            merged = merged[:total]
-            lap("gather")
+                self.stride = max(counts) + max(counts) // 8 + 1  # the exact need is known now: one more pass
+                self.d_send = None
+            merged = self.d_merged[:total]
             if total > 1:
                 self.image.sort_hits_dev(merged.data_ptr(), total, n, stream.cuda_stream)
             lap("sort")
             if not to_host:
+                return merged
+            if to_host == "shared":
+                if self.d_packed is None or self.d_packed.shape[0] < total:
+                    self.d_packed = torch.empty(total + total // 8 + 16, dtype=torch.int64, device=self.dev)
+                self.image.pack_hits_dev(merged.data_ptr(), total, self.d_packed.data_ptr(), stream.cuda_stream)
+                seg = self._shared_segment(total)
+                lo, hi = total * rank // world, total * (rank + 1) // world
+                if hi > lo:
+                    dst = torch.from_numpy(seg[lo:hi].view(np.int64))
+                    dst.copy_(self.d_packed[lo:hi], non_blocking=True)
+                stream.synchronize()
+                dist.barrier(group=self.group)  # every part of the segment is in place
+                lap("on the host")
+                return seg[:total]
+            if to_host == "rank0" and rank != 0:
                 return merged
             if self.host is None or self.host.shape[0] < total:
                 self.host = torch.empty((total + total // 8 + 16, 4), dtype=torch.int32, pin_memory=True)

@@ -166,6 +166,20 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
                            int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                            guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                            guido_stats *stats);
+/* Same search, 8 bytes per hit on the wire instead of 16: hits[i] = guide << 33 | gpos << 1 | strand
+ * (the canonical sort key; n_guides < 2^31).  The window planes of guido_ot_hit are a function of
+ * (gpos, strand) and the image, so the host re-derives them where it needs them
+ * (guido_hits_expand) -- halves the device-to-host copy, which is most of a large search's
+ * end-to-end time.  Everything else (order, raw_flags, capacity convention) as above. */
+int guido_offtarget_search_packed(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                                  int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                                  uint64_t *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                                  guido_stats *stats);
+/* packed records -> guido_ot_hit records, planes cut from the HOST copy of the image exactly as the
+ * kernels cut them from HBM (host-only; pam_len = length of the PAM the search used).  Feeds the
+ * record building of run_bowtie (guido/off_targets.py:201-225). */
+int guido_hits_expand(const guido_image *img, const uint64_t *packed, int64_t n_hits, int32_t pam_len,
+                      guido_ot_hit *out);
 /* key presence alone: flags[g] = 1 when guide g has at least one RAW bowtie alignment in this
  * handle's stretch of the genome (the relaxed all-window pass guido_offtarget_search runs for the
  * guides without a valid hit; brute force, meant for the few guides that have none anywhere).
@@ -188,6 +202,17 @@ int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_g
  * file order; guido_b200 fixes the order so 1/2/4/8-GPU outputs are byte-identical).  n_guides
  * bounds the guide field.  Asynchronous on `stream`; scratch memory belongs to the handle. */
 int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream);
+/* Merge of per-GPU hit lists after ONE padded NCCL all-gather (no host round trip between the
+ * search and the merge): every rank sends `stride` records, record 0 a header whose first 8 bytes
+ * hold its hit count (copy d_count there on the device), the hits behind it.  d_gathered =
+ * n_parts x stride records; the parts are copied back to back into d_out (cap records) and
+ * *d_total (device u64) receives their sum.  A part whose count exceeds stride - 1 is cut (the
+ * caller compares the headers with stride afterwards and repeats the step with a larger one).
+ * Under the merge of the per-shard bowtie outputs a multi-GPU run_bowtie needs. */
+int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride,
+                          void *d_out, int64_t cap, void *d_total, void *stream);
+/* device-resident guido_ot_hit records -> the 8-byte wire format of guido_offtarget_search_packed */
+int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, void *d_out, void *stream);
 /* Genome-side index of the off-target search, the counterpart of the `bowtie-build` index files
  * (guido/genome.py:156-171): every PAM-valid window of the uploaded shard (both strands, guide
  * orientation) grouped by its core_len PAM-proximal bases, 20 bytes per window in HBM.  Guide

@@ -76,6 +76,14 @@ static int comp_set(int s) {
     return ((s & 1) << 3) | ((s & 2) << 1) | ((s & 4) >> 1) | ((s & 8) >> 3);
 }
 
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -265,6 +273,171 @@ int64_t orc_bowtie_n_count(const char *const *contigs, const int64_t *lens, int 
                            int seed_mms, int seed_len, int qual_ceiling) {
     return orc_bowtie_n(contigs, lens, n_contigs, reads, n_reads, R, seed_mms, seed_len,
                         qual_ceiling, NULL, 0);
+}
+
+/* --------------------------------------------- seed-indexed search (CPU baseline) */
+
+/*
+ * The same alignment rule organised the way an index-based aligner runs it, for bench.py's CPU
+ * arm: bowtie 1 does not compare a read with every window either -- `bowtie-build` indexes the
+ * genome once (guido/genome.py:157-164) and `-n` mode backtracks over the <= n seed mismatches,
+ * then extends.  Here: orc_seed_index_build (the bowtie-build counterpart, not timed) tables every
+ * window that guido can keep -- N-free, PAM letters matching the fixed letters of the pattern
+ * exactly (off_targets.py:169-198), both strands -- under its core k-mer; orc_seed_index_search
+ * (timed) enumerates, per read, the cores within core_mm substitutions, and checks the distal
+ * bases of the windows filed there against total_mm.  It finds exactly the alignments
+ * orc_bowtie_n finds that survive guido's PAM filter (tests/test_oracle_golden.py).
+ * Brute force (orc_bowtie_n) stays the parity oracle; this is a throughput baseline.
+ */
+typedef struct {
+    int cl, dl, P;
+    uint64_t n;
+    uint32_t *off;   /* 4^cl + 1 bucket starts */
+    uint32_t *dist;  /* per window: dl distal bases, 2 bits each, guide orientation (base 0 = 5' end) */
+    uint64_t *where; /* per window: global position << 1 | strand */
+} orc_seed_index;
+
+/* window of W = 20 + P codes in GUIDE orientation (codes[0] = 5' end of the protospacer) -> key / distal */
+static inline void split_window(const uint8_t *codes, int cl, int dl, uint32_t *key, uint32_t *dist) {
+    uint32_t k = 0, d = 0;
+    for (int i = 0; i < dl; i++) d |= (uint32_t)codes[i] << (2 * i);
+    for (int i = 0; i < cl; i++) k |= (uint32_t)codes[dl + i] << (2 * i);
+    *key = k; *dist = d;
+}
+
+/* pam_sets[P]: base sets (A=1,C=2,G=4,T=8) of the PAM in guide orientation; 15 = any */
+static int window_at(const char *g, int64_t L, int64_t q, int strand, const int *pam_sets, int P, uint8_t *codes) {
+    const int W = 20 + P;
+    if (q < 0 || q + W > L) return 0;
+    for (int i = 0; i < W; i++) {
+        int c = code_of(up(strand ? g[q + W - 1 - i] : g[q + i]));
+        if (c < 0) return 0;
+        if (strand) c = 3 - c;
+        codes[i] = (uint8_t)c;
+        if (i >= 20 && !((pam_sets[i - 20] >> c) & 1)) return 0;
+    }
+    return 1;
+}
+
+void orc_seed_index_free(orc_seed_index *ix) {
+    if (!ix) return;
+    free(ix->off); free(ix->dist); free(ix->where); free(ix);
+}
+
+/* goffs[c]: global coordinate of base 0 of contig c (what the caller wants back in `where`) */
+orc_seed_index *orc_seed_index_build(const char *const *contigs, const int64_t *lens, const int64_t *goffs,
+                                     int n_contigs, const char *pam, int core_len) {
+    int P = (int)strlen(pam);
+    if (P < 1 || P > 8 || core_len < 1 || core_len > 12) return NULL;
+    int pam_sets[8];
+    for (int i = 0; i < P; i++) {  /* letters outside A/C/G/T constrain nothing (they are N in the read) */
+        char c = up(pam[i]);
+        pam_sets[i] = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? iupac_set(c) : 15;
+    }
+    orc_seed_index *ix = (orc_seed_index *)calloc(1, sizeof *ix);
+    ix->cl = core_len; ix->dl = 20 - core_len; ix->P = P;
+    const size_t nb = (size_t)1 << (2 * core_len);
+    ix->off = (uint32_t *)calloc(nb + 1, sizeof(uint32_t));
+    uint32_t *cnt = (uint32_t *)calloc(nb, sizeof(uint32_t));
+    /* pass 1: histogram, pass 2: scatter */
+    for (int pass = 0; pass < 2; pass++) {
+        for (int ci = 0; ci < n_contigs; ci++) {
+            const char *g = contigs[ci];
+            const int64_t L = lens[ci];
+#pragma omp parallel for schedule(static)
+            for (int64_t q = 0; q < L; q++) {
+                uint8_t codes[32];
+                for (int strand = 0; strand < 2; strand++) {
+                    if (!window_at(g, L, q, strand, pam_sets, P, codes)) continue;
+                    uint32_t key, dist;
+                    split_window(codes, ix->cl, ix->dl, &key, &dist);
+                    if (pass == 0) {
+#pragma omp atomic
+                        cnt[key]++;
+                    } else {
+                        uint32_t slot;
+#pragma omp atomic capture
+                        slot = cnt[key]++;
+                        ix->dist[slot] = dist;
+                        ix->where[slot] = ((uint64_t)(goffs[ci] + q) << 1) | (uint64_t)strand;
+                    }
+                }
+            }
+        }
+        if (pass == 0) {
+            uint64_t run = 0;
+            for (size_t k = 0; k < nb; k++) { ix->off[k] = (uint32_t)run; run += cnt[k]; cnt[k] = ix->off[k]; }
+            ix->off[nb] = (uint32_t)run;
+            ix->n = run;
+            if (run >= (1ull << 32)) { free(cnt); orc_seed_index_free(ix); return NULL; }
+            ix->dist = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(run + 1));
+            ix->where = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(run + 1));
+        }
+    }
+    free(cnt);
+    return ix;
+}
+
+uint64_t orc_seed_index_size(const orc_seed_index *ix) { return ix ? ix->n : 0; }
+
+/* protos: n_guides x 20 letters (guide orientation).  out (optional, cap records): guide << 33 |
+ * position << 1 | strand, unordered.  Returns the number of alignments. */
+int64_t orc_seed_index_search(const orc_seed_index *ix, const char *protos, int64_t n_guides, int core_mm,
+                              int total_max, uint64_t *out, int64_t cap) {
+    const int cl = ix->cl, dl = ix->dl;
+    const uint32_t LOW = 0x55555555u;
+    int64_t total = 0, cursor = 0;
+    if (core_mm > 3) core_mm = 3;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : total)
+    for (int64_t gi = 0; gi < n_guides; gi++) {
+        uint8_t codes[20];
+        int ok = 1;
+        for (int i = 0; i < 20; i++) {
+            int c = code_of(up(protos[gi * 20 + i]));
+            if (c < 0) { ok = 0; break; }
+            codes[i] = (uint8_t)c;
+        }
+        if (!ok) continue;
+        uint32_t key = 0, dist = 0;
+        for (int i = 0; i < dl; i++) dist |= (uint32_t)codes[i] << (2 * i);
+        for (int i = 0; i < cl; i++) key |= (uint32_t)codes[dl + i] << (2 * i);
+        int64_t mine = 0;
+        /* every core within core_mm substitutions: nm positions, each xor-ed with 1..3 */
+        for (int nm = 0; nm <= core_mm; nm++) {
+            const int budget = total_max - nm;
+            if (budget < 0 || nm > cl) break;
+            int pos[3] = {0, 1, 2};
+            for (;;) {
+                const int n_sub = 1 << (2 * nm);
+                for (int sub = 0; sub < n_sub; sub++) {
+                    uint32_t k = key;
+                    int valid = 1;
+                    for (int i = 0; i < nm; i++) {
+                        const uint32_t x = (uint32_t)(sub >> (2 * i)) & 3u;
+                        if (!x) { valid = 0; break; }
+                        k ^= x << (2 * pos[i]);
+                    }
+                    if (!valid) continue;
+                    for (uint32_t s = ix->off[k]; s < ix->off[k + 1]; s++) {
+                        const uint32_t x = ix->dist[s] ^ dist;
+                        if (__builtin_popcount((x | (x >> 1)) & LOW) > budget) continue;
+                        mine++;
+                        if (out) {
+                            const int64_t at = __atomic_fetch_add(&cursor, 1, __ATOMIC_RELAXED);
+                            if (at < cap) out[at] = ((uint64_t)gi << 33) | ix->where[s];
+                        }
+                    }
+                }
+                int i = nm - 1;  /* next combination of nm positions out of cl */
+                while (i >= 0 && pos[i] == cl - nm + i) i--;
+                if (i < 0) break;
+                pos[i]++;
+                for (int j = i + 1; j < nm; j++) pos[j] = pos[j - 1] + 1;
+            }
+        }
+        total += mine;
+    }
+    return total;
 }
 
 /* ------------------------------------------------------------------ MMEJ */

@@ -72,12 +72,76 @@ def lib():
         L.orc_mmej.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
         L.orc_threads.restype = ctypes.c_int
+        L.orc_set_threads.argtypes = [ctypes.c_int]
+        L.orc_seed_index_build.restype = ctypes.c_void_p
+        L.orc_seed_index_build.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        L.orc_seed_index_free.argtypes = [ctypes.c_void_p]
+        L.orc_seed_index_size.restype = ctypes.c_uint64
+        L.orc_seed_index_size.argtypes = [ctypes.c_void_p]
+        L.orc_seed_index_search.restype = ctypes.c_int64
+        L.orc_seed_index_search.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int64]
         _lib = L
     return _lib
 
 
 def threads():
     return int(lib().orc_threads())
+
+
+def set_threads(n):
+    """Number of OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1: the CPU arm of
+    bench.py sets the count it wants explicitly)."""
+    lib().orc_set_threads(int(n))
+    return threads()
+
+
+class SeedIndex:
+    """CPU seed-indexed off-target search (throughput baseline of bench.py; see guido_oracle.c).
+
+    ``contigs``: list of (name, sequence bytes/str, global offset).  Building is the counterpart
+    of ``bowtie-build`` (guido/genome.py:157-164); ``search`` the counterpart of the bowtie call of
+    guido/off_targets.py:151-167 followed by guido's PAM filter (:169-198)."""
+
+    def __init__(self, contigs, pam="NGG", core_length=10):
+        seqs = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
+        self._keep = seqs
+        arr = (ctypes.c_char_p * len(seqs))(*seqs)
+        lens = (ctypes.c_int64 * len(seqs))(*[len(s) for s in seqs])
+        offs = (ctypes.c_int64 * len(seqs))(*[int(c[2]) for c in contigs])
+        self._h = lib().orc_seed_index_build(arr, lens, offs, len(seqs), pam.encode(), core_length)
+        if not self._h:
+            raise ValueError("seed index: bad PAM / core length, or more than 2^32 windows")
+        self.n_windows = int(lib().orc_seed_index_size(self._h))
+        self._keep = None  # the index holds what it needs
+
+    def search(self, protos_u8, core_mismatches=2, total_max=4, want_hits=False):
+        """protos_u8: (n, 20) uint8 letters.  Returns the hit count, or a sorted uint64 array
+        guide << 33 | global position << 1 | strand when ``want_hits``."""
+        blob = np.ascontiguousarray(protos_u8, dtype=np.uint8)
+        n = blob.shape[0]
+        if not want_hits:
+            return int(lib().orc_seed_index_search(self._h, blob.tobytes(), n, core_mismatches, total_max, None, 0))
+        cap = max(1024, 64 * n)
+        while True:
+            out = np.empty(cap, np.uint64)
+            got = int(lib().orc_seed_index_search(self._h, blob.tobytes(), n, core_mismatches, total_max,
+                                                  out.ctypes.data, cap))
+            if got <= cap:
+                return np.sort(out[:got])
+            cap = got
+
+    def close(self):
+        if self._h:
+            lib().orc_seed_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # --------------------------------------------------------------------------- helpers

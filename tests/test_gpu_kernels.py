@@ -269,6 +269,31 @@ def test_offtarget_guides_are_packed_on_the_device(native):
     assert enc.tolist() == native.encode_guides(["acgtacgtacgtacgtacgt"]).tolist()
 
 
+@pytest.mark.parametrize("pam", ["NGG", "TTTV", "NNGRRT"])
+def test_offtarget_packed_hits_expand(native, pam):
+    """the 8-byte wire format + host-side expansion reproduces the 16-byte records bit for bit
+    (both strands, windows across 64-base block borders, PAM lengths 3 / 4 / 6)"""
+    contigs = util.synthetic_contigs(41, [150000, 40000, 513], n_runs=4, iupac=3)
+    rng = np.random.default_rng(19)
+    img = native.Image.from_seqs(contigs).upload()
+    P = len(pam)
+    # guides that do have sites for this PAM, on both strands: the protospacers next to real PAM hits
+    fw, rv = img.pam_scan_genome(pam, native.SCAN_STRICT)
+    comp = np.zeros(256, np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    wf = img.fetch_windows(rng.choice(fw, 60, replace=False).astype(np.int64) - 20, 20)
+    wr = comp[img.fetch_windows(rng.choice(rv, 60, replace=False).astype(np.int64) + P, 20)[:, ::-1]]
+    protos = np.ascontiguousarray(np.concatenate([wf, wr]))
+    full, f1 = img.offtarget_search(protos, pam=pam)
+    packed, f2 = img.offtarget_search(protos, pam=pam, packed=True)
+    assert packed.dtype == np.uint64 and len(packed) == len(full) >= 120 and np.array_equal(f1, f2)
+    assert np.array_equal(packed >> np.uint64(33), full["guide"].astype(np.uint64))
+    assert np.all(np.diff(packed.astype(np.uint64)) > 0)      # the packed word is the sort key
+    assert (full["hi"] >> 31).any() and not (full["hi"] >> 31).all()
+    assert np.array_equal(img.expand_hits(packed, P), full)
+
+
 @pytest.mark.parametrize("total", [0, 2, 4, 6, 8])
 @pytest.mark.parametrize("sliced", [True, False])
 def test_offtarget_join_variants(native, monkeypatch, total, sliced):

@@ -62,7 +62,7 @@ def test_device_merge_single_rank_group(native):
                                 device_id=torch.device("cuda", int(img.info.device)))
     try:
         m = DeviceMerge(img)
-        m.cap = 8  # far too small: the first pass only counts, the second is right-sized
+        m.stride = 9  # far too small: the first pass only counts, the second is right-sized
         got = m.search(protos).copy()
         assert np.array_equal(got, want)
         as_u8 = np.frombuffer("".join(protos).encode(), np.uint8).reshape(-1, 20)
@@ -73,6 +73,9 @@ def test_device_merge_single_rank_group(native):
             m.search([protos[0], protos[1][:4] + "N" + protos[1][5:]])
         with pytest.raises(ValueError, match="20 nt"):
             m.search(["ACGT"])
+        packed = m.search(protos, to_host="shared")  # 8-byte records in the node-shared pinned segment
+        want_packed, _ = img.offtarget_search(protos, want_raw_flags=False, packed=True)
+        assert packed.dtype == np.uint64 and np.array_equal(packed, want_packed)
         few = m.search(protos[:3])
         w3, _ = img.offtarget_search(protos[:3], want_raw_flags=False)
         assert np.array_equal(few, w3)

@@ -121,3 +121,34 @@ def test_bowtie_rule_budget(oracle):
         oracle.bowtie_args("NGG", 10, 3, 4)
     with pytest.raises(ValueError):
         oracle.bowtie_args("NGG", 10, 2, 1)
+
+
+def test_seed_index_port_equals_brute_force(oracle):
+    """the seed-indexed CPU search (bench.py's CPU arm) reports exactly the alignments of the
+    brute-force oracle that survive guido's PAM filter -- both strands, N runs, IUPAC letters,
+    several parameter sets"""
+    import numpy as np
+    from tests import util
+    contigs = util.synthetic_contigs(71, [90000, 30000, 400], n_runs=4, iupac=5)
+    rng = np.random.default_rng(5)
+    protos = []
+    s0 = contigs[0][1].upper()
+    while len(protos) < 150:
+        p = int(rng.integers(0, len(s0) - 23))
+        w = s0[p:p + 20]
+        if set(w) - set("ACGT"):
+            continue
+        w = list(w)
+        for _ in range(int(rng.integers(0, 5))):
+            w[int(rng.integers(0, 20))] = "ACGT"[int(rng.integers(0, 4))]
+        protos.append("".join(w))
+    P = np.frombuffer("".join(protos).encode(), np.uint8).reshape(-1, 20)
+    for pam, kw in (("NGG", {}), ("NAG", dict(core_mismatches=1, total_mismatches=3)), ("TGG", dict(core_mismatches=3))):
+        valid, _ = util.oracle_valid_hits(oracle, contigs, protos, pam, **kw)
+        ix = oracle.SeedIndex([(n, s, i << 24) for i, (n, s) in enumerate(contigs)], pam, kw.get("core_length", 10))
+        n_unk = pam.count("N")
+        hits = ix.search(P, kw.get("core_mismatches", 2), kw.get("total_mismatches", 4) + 1 - n_unk, want_hits=True)
+        assert ix.search(P, kw.get("core_mismatches", 2), kw.get("total_mismatches", 4) + 1 - n_unk) == len(hits)
+        got = {(int(h >> 33), contigs[int((h >> 1) & 0xffffffff) >> 24][0], int((h >> 1) & 0xffffff), "-" if h & 1 else "+")
+               for h in hits.tolist()}
+        assert got == valid and len(valid) > 0
