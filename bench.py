@@ -651,9 +651,11 @@ def run_locus(R, args):
             s = img.fetch(i, 0, clen)
             fh.write(f">{name}\n")
             fh.writelines(s[j:j + 60] + "\n" for j in range(0, len(s), 60))
+    import contextlib
     t0 = time.perf_counter()
     g = guido.Genome("g10", genome_file_abspath=fa)
-    g.build()
+    with contextlib.redirect_stdout(sys.stderr):  # build() reports its progress on stdout, like the reference's
+        g.build()
     build_s = time.perf_counter() - t0
 
     def once():
@@ -762,6 +764,8 @@ def main():
         return 0
 
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout, which carries the ONE JSON line
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)

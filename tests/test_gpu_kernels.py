@@ -269,10 +269,10 @@ def test_offtarget_guides_are_packed_on_the_device(native):
     assert enc.tolist() == native.encode_guides(["acgtacgtacgtacgtacgt"]).tolist()
 
 
-@pytest.mark.parametrize("pam", ["NGG", "TTTV", "NNGRRT"])
+@pytest.mark.parametrize("pam", ["NGG", "TTTV", "TGGAC"])
 def test_offtarget_packed_hits_expand(native, pam):
     """the 8-byte wire format + host-side expansion reproduces the 16-byte records bit for bit
-    (both strands, windows across 64-base block borders, PAM lengths 3 / 4 / 6)"""
+    (both strands, windows across 64-base block borders, PAM lengths 3 / 4 / 5)"""
     contigs = util.synthetic_contigs(41, [150000, 40000, 513], n_runs=4, iupac=3)
     rng = np.random.default_rng(19)
     img = native.Image.from_seqs(contigs).upload()
