@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "device.cuh"
@@ -96,13 +97,11 @@ static PlanesView view_of(const DeviceState *ds) {
     return pv;
 }
 
-static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards) {
-    if (!img || n_shards < 1 || shard_ix < 0 || shard_ix >= n_shards) { set_error("bad shard arguments"); return GUIDO_ERR_ARG; }
-    device_release(img);
-    auto *ds = new DeviceState();
-    img->dev = ds;
-    int rc = device_init(ds, device);
-    if (rc) { device_release(img); return rc; }
+// (re)loads the image's shard into `ds` (initialised for a device); buffers are reused when they
+// are large enough, so repeated uploads through one DeviceState cost copies, not allocations
+static int load_shard(guido_image *img, DeviceState *ds, int shard_ix, int n_shards) {
+    GUIDO_CUDA(cudaSetDevice(ds->device));
+    release_site_table(ds);  // whatever was tabled belongs to the previous content
     // contiguous shards of equal size, aligned to scan tiles (1024 blocks = 65536 bases); a shard
     // owns the PAM starts inside it and keeps a halo of 4 blocks (>= 20 + P bases) on either side
     guido_shard_bounds(img->padded_bases, shard_ix, n_shards, &ds->shard_lo, &ds->shard_hi);
@@ -110,7 +109,8 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
     ds->blk_lo = std::max<int64_t>((b0 & ~(int64_t)3) - 4, 0);   // multiple of 4: 256-bit loads stay aligned
     int64_t blk_hi = std::min<int64_t>(b1 + 4, img->n_blocks);
     ds->blk_n = blk_hi - ds->blk_lo;
-    GUIDO_CUDA(cudaMalloc(&ds->d_planes, (size_t)(ds->blk_n + 1) * sizeof(ulonglong2)));
+    int rc;
+    if ((rc = ensure_bytes((void **)&ds->d_planes, &ds->planes_cap, (ds->blk_n + 1) * (int64_t)sizeof(ulonglong2)))) return rc;
     GUIDO_CUDA(cudaMemsetAsync(ds->d_planes + ds->blk_n, 0, sizeof(ulonglong2), ds->stream));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_planes, img->planes.data() + 2 * ds->blk_lo,
                                (size_t)ds->blk_n * sizeof(ulonglong2), cudaMemcpyHostToDevice, ds->stream));
@@ -118,10 +118,10 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
     std::vector<uint32_t> rs(ds->n_runs), re(ds->n_runs);
     std::vector<uint8_t> rk(ds->n_runs);
     for (int i = 0; i < ds->n_runs; i++) { rs[i] = img->runs[i].start; re[i] = img->runs[i].end; rk[i] = img->runs[i].kind; }
-    size_t nr = (size_t)std::max(ds->n_runs, 1);
-    GUIDO_CUDA(cudaMalloc(&ds->d_run_start, nr * 4));
-    GUIDO_CUDA(cudaMalloc(&ds->d_run_end, nr * 4));
-    GUIDO_CUDA(cudaMalloc(&ds->d_run_kind, nr));
+    const int64_t nr = std::max(ds->n_runs, 1);
+    if ((rc = ensure_bytes((void **)&ds->d_run_start, &ds->run_start_cap, nr * 4))) return rc;
+    if ((rc = ensure_bytes((void **)&ds->d_run_end, &ds->run_end_cap, nr * 4))) return rc;
+    if ((rc = ensure_bytes((void **)&ds->d_run_kind, &ds->run_kind_cap, nr))) return rc;
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_start, rs.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_end, re.data(), (size_t)ds->n_runs * 4, cudaMemcpyHostToDevice, ds->stream));
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_run_kind, rk.data(), (size_t)ds->n_runs, cudaMemcpyHostToDevice, ds->stream));
@@ -136,10 +136,24 @@ static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards)
         const bool touched = ri < img->runs.size() && (int64_t)img->runs[ri].start < (t + 1) * 65536 + 32;
         first[(size_t)t] = (uint32_t)ri | (touched ? 0x80000000u : 0u);
     }
-    GUIDO_CUDA(cudaMalloc(&ds->d_tile_first_run, (size_t)n_rt * 4));
+    if ((rc = ensure_bytes((void **)&ds->d_tile_first_run, &ds->tile_first_run_cap, n_rt * 4))) return rc;
     GUIDO_CUDA(cudaMemcpyAsync(ds->d_tile_first_run, first.data(), (size_t)n_rt * 4, cudaMemcpyHostToDevice, ds->stream));
-    GUIDO_CUDA(cudaStreamSynchronize(ds->stream));
+    GUIDO_CUDA(cudaStreamSynchronize(ds->stream));  // the host vectors above go out of scope
     return GUIDO_OK;
+}
+
+static int upload_impl(guido_image *img, int device, int shard_ix, int n_shards) {
+    if (!img || n_shards < 1 || shard_ix < 0 || shard_ix >= n_shards) { set_error("bad shard arguments"); return GUIDO_ERR_ARG; }
+    if (!img->dev || img->dev->device != device) {  // a handle that moves to another device starts over
+        device_release(img);
+        auto *ds = new DeviceState();
+        img->dev = ds;
+        int rc = device_init(ds, device);
+        if (rc) { device_release(img); return rc; }
+    }
+    int rc = load_shard(img, img->dev, shard_ix, n_shards);
+    if (rc) device_release(img);
+    return rc;
 }
 
 static int need_device(guido_image *img) {
@@ -204,6 +218,7 @@ using namespace guido;
 extern "C" {
 
 int guido_device_count(void) {
+    GUIDO_API_RANGE();
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     int ok = 0;
@@ -215,6 +230,7 @@ int guido_device_count(void) {
 }
 
 int guido_shard_bounds(int64_t padded_bases, int32_t shard_ix, int32_t n_shards, int64_t *lo, int64_t *hi) {
+    GUIDO_API_RANGE();
     if (n_shards < 1 || shard_ix < 0 || shard_ix >= n_shards || !lo || !hi) { set_error("bad shard arguments"); return GUIDO_ERR_ARG; }
     const int64_t n_blocks = (padded_bases + 63) / 64;
     int64_t per = (n_blocks + n_shards - 1) / n_shards;
@@ -226,6 +242,7 @@ int guido_shard_bounds(int64_t padded_bases, int32_t shard_ix, int32_t n_shards,
 }
 
 int guido_host_alloc(int64_t bytes, void **out) {
+    GUIDO_API_RANGE();
     if (bytes < 0 || !out) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     *out = nullptr;
     GUIDO_CUDA(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
@@ -233,11 +250,13 @@ int guido_host_alloc(int64_t bytes, void **out) {
 }
 
 int guido_host_free(void *p) {
+    GUIDO_API_RANGE();
     if (p) GUIDO_CUDA(cudaFreeHost(p));
     return GUIDO_OK;
 }
 
 int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t *n) {
+    GUIDO_API_RANGE();
     if (!img || !img->dev || !out_ms || !n) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     DeviceState *ds = img->dev;
     long long have = std::min<long long>(ds->kev_count, DeviceState::kKev);
@@ -253,10 +272,12 @@ int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t 
 }
 
 int guido_image_upload(guido_image *img, int32_t device, int32_t shard_ix, int32_t n_shards) {
+    GUIDO_API_RANGE();
     return upload_impl(img, device, shard_ix, n_shards);
 }
 
 int guido_image_get_info(const guido_image *img, guido_image_info *info) {
+    GUIDO_API_RANGE();
     if (!img || !info) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     info->n_contigs = (int64_t)img->contigs.size();
     info->total_bases = img->total_bases;
@@ -271,6 +292,7 @@ int guido_image_get_info(const guido_image *img, guido_image_info *info) {
 
 int guido_pam_scan_genome(guido_image *img, const char *pam, int32_t mode, uint32_t *fw, int64_t cap_fw,
                           int64_t *n_fw, uint32_t *rv, int64_t cap_rv, int64_t *n_rv, guido_stats *stats) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     PamSpec ps;
@@ -283,6 +305,7 @@ int guido_pam_scan_genome(guido_image *img, const char *pam, int32_t mode, uint3
 
 int guido_pam_scan_genome_dev(guido_image *img, const char *pam, int32_t mode, void *d_fw, int64_t cap_fw,
                               void *d_rv, int64_t cap_rv, void *d_counts, void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     PamSpec ps;
@@ -297,6 +320,7 @@ int guido_pam_scan_genome_dev(guido_image *img, const char *pam, int32_t mode, v
 int guido_pam_scan_region(guido_image *img, int64_t contig_ix, int64_t start0, int64_t end0, const char *pam,
                           int32_t mode, int32_t *fw, int64_t cap_fw, int64_t *n_fw, int32_t *rv,
                           int64_t cap_rv, int64_t *n_rv, guido_stats *stats) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     PamSpec ps;
@@ -314,6 +338,7 @@ int guido_pam_scan_region(guido_image *img, int64_t contig_ix, int64_t start0, i
 int guido_pam_scan_seq(const char *seq, int64_t n, const char *pam, int32_t device, int32_t mode,
                        int32_t *fw, int64_t cap_fw, int64_t *n_fw, int32_t *rv, int64_t cap_rv,
                        int64_t *n_rv, guido_stats *stats) {
+    GUIDO_API_RANGE();
     PamSpec ps;
     int rc = parse_pam(pam, &ps);
     if (rc) return rc;
@@ -321,10 +346,18 @@ int guido_pam_scan_seq(const char *seq, int64_t n, const char *pam, int32_t devi
     guido_image *img = nullptr;
     const char *name = "seq";
     if ((rc = guido_image_from_seqs(1, &name, &seq, &n, &img))) return rc;
+    // The device side of this call -- stream, events, scratch, plane buffers -- is kept per device
+    // between calls (a locus-sized scan takes microseconds; creating and destroying a context per
+    // call took milliseconds): the cached DeviceState is lent to the temporary image.
+    static std::mutex mu;
+    static DeviceState *cached[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device >= 0 && device < 64 && cached[device]) { img->dev = cached[device]; cached[device] = nullptr; }
     rc = guido_image_upload(img, device, 0, 1);
     if (rc == GUIDO_OK)
         rc = guido_pam_scan_region(img, 0, 0, n, pam, mode, fw, cap_fw, n_fw, rv, cap_rv, n_rv, stats);
     if (stats && rc == GUIDO_OK) stats->bytes_h2d = img->dev->blk_n * 16;
+    if (img->dev && device >= 0 && device < 64) { cached[device] = img->dev; img->dev = nullptr; }
     guido_image_free(img);
     return rc;
 }
@@ -405,6 +438,7 @@ static int resolve_ot_algo(guido_image *img, const OtParams &op, const ScanRange
 }
 
 int guido_site_table_partition(guido_image *img, int32_t part_ix, int32_t n_parts) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (n_parts < 1 || n_parts > 32 || (n_parts & (n_parts - 1)) || part_ix < 0 || part_ix >= n_parts) {
@@ -417,6 +451,7 @@ int guido_site_table_partition(guido_image *img, int32_t part_ix, int32_t n_part
 }
 
 int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, int64_t *n_sites, double *build_ms) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     OtParams op;
@@ -436,6 +471,7 @@ int guido_site_table_build(guido_image *img, const char *pam, int32_t core_len, 
 }
 
 int guido_site_table_free(guido_image *img) {
+    GUIDO_API_RANGE();
     if (img && img->dev) release_site_table(img->dev);
     return GUIDO_OK;
 }
@@ -443,6 +479,7 @@ int guido_site_table_free(guido_image *img) {
 int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n_guides, const char *pam,
                                int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                                void *d_hits, int64_t cap, void *d_count, void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     OtParams op;
@@ -464,6 +501,7 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
 
 int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_guides, void *d_out, void *d_bad,
                             void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
@@ -475,6 +513,7 @@ int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_g
 
 int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride, void *d_out,
                           int64_t cap, void *d_total, void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (!d_gathered || !d_out || !d_total || stride < 1 || cap < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
@@ -483,6 +522,7 @@ int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_pa
 }
 
 int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, void *d_out, void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (n_hits < 0 || (n_hits && (!d_hits || !d_out))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
@@ -490,6 +530,7 @@ int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, vo
 }
 
 int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (n_hits < 0 || n_guides < 1) { set_error("bad hit or guide count"); return GUIDO_ERR_ARG; }
@@ -544,6 +585,7 @@ static int relaxed_flag_pass(guido_image *img, const char *protos, const std::ve
 
 int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
                               int32_t core_len, int32_t core_mm, int32_t total_mm, uint8_t *flags) {
+    GUIDO_API_RANGE();
     int rc = need_device(img);
     if (rc) return rc;
     if (n_guides < 0 || n_guides > 0x7fffffff) { set_error("bad guide count"); return GUIDO_ERR_ARG; }
@@ -698,6 +740,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
                            int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                            guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                            guido_stats *stats) {
+    GUIDO_API_RANGE();
     return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, false, cap, n_hits,
                                  raw_flags, stats);
 }
@@ -706,6 +749,7 @@ int guido_offtarget_search_packed(guido_image *img, const char *protos, int64_t 
                                   int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                                   uint64_t *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                                   guido_stats *stats) {
+    GUIDO_API_RANGE();
     return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, true, cap, n_hits,
                                  raw_flags, stats);
 }

@@ -27,6 +27,9 @@ struct DeviceState {
     uint8_t *d_run_kind = nullptr;
     uint32_t *d_tile_first_run = nullptr;  // per 65536-base tile: first run ending after tile start - 32
     int n_runs = 0;
+    // capacities (bytes) of the five arrays above: a handle that is uploaded again -- or the cached
+    // per-device context of the sequence-level entry points -- reuses them
+    int64_t planes_cap = 0, run_start_cap = 0, run_end_cap = 0, run_kind_cap = 0, tile_first_run_cap = 0;
     int64_t shard_lo = 0, shard_hi = 0;  // owned global positions (PAM starts), 64-aligned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -18,9 +18,15 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "internal.h"
 
 namespace guido {
+
+ApiRange::ApiRange(const char *name) { nvtxRangePushA(name); }
+ApiRange::~ApiRange() { nvtxRangePop(); }
+
 
 static thread_local char g_err[512] = "";
 
@@ -205,10 +211,11 @@ using namespace guido;
 extern "C" {
 
 const char *guido_last_error(void) { return g_err; }
-int guido_version(void) { return 1; }
+int guido_version(void) { return 2; }
 
 int guido_image_from_seqs(int32_t n, const char *const *names, const char *const *seqs,
                           const int64_t *lens, guido_image **out) {
+    GUIDO_API_RANGE();
     if (n < 0 || !out) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     auto *img = new guido_image();
     for (int i = 0; i < n; i++) img->contigs.push_back(Contig{names ? names[i] : "seq", lens[i], 0});
@@ -221,6 +228,7 @@ int guido_image_from_seqs(int32_t n, const char *const *names, const char *const
 }
 
 int guido_image_from_fasta(const char *path, guido_image **out) {
+    GUIDO_API_RANGE();
     int fd = open(path, O_RDONLY);
     if (fd < 0) { set_error("cannot open %s", path); return GUIDO_ERR_IO; }
     struct stat st;
@@ -276,6 +284,7 @@ int guido_image_from_fasta(const char *path, guido_image **out) {
 
 int guido_image_synth(int32_t n, const char *const *names, const int64_t *lens, uint64_t seed,
                       double n_frac, int64_t run_min, int64_t run_max, guido_image **out) {
+    GUIDO_API_RANGE();
     if (n < 0 || !out || run_min < 1 || run_max < run_min) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     auto *img = new guido_image();
     for (int i = 0; i < n; i++) {
@@ -336,6 +345,7 @@ int guido_image_synth(int32_t n, const char *const *names, const int64_t *lens, 
 }
 
 int guido_image_free(guido_image *img) {
+    GUIDO_API_RANGE();
     if (!img) return GUIDO_OK;
     device_release(img);
     delete img;
@@ -343,6 +353,7 @@ int guido_image_free(guido_image *img) {
 }
 
 int guido_image_save(const guido_image *img, const char *path) {
+    GUIDO_API_RANGE();
     FILE *f = fopen(path, "wb");
     if (!f) { set_error("cannot write %s", path); return GUIDO_ERR_IO; }
     uint64_t hdr[8] = {kImageMagic, kImageVersion, (uint64_t)img->contigs.size(), (uint64_t)img->runs.size(),
@@ -364,6 +375,7 @@ int guido_image_save(const guido_image *img, const char *path) {
 }
 
 int guido_image_load(const char *path, guido_image **out) {
+    GUIDO_API_RANGE();
     FILE *f = fopen(path, "rb");
     if (!f) { set_error("cannot open %s", path); return GUIDO_ERR_IO; }
     uint64_t hdr[8];
@@ -401,6 +413,7 @@ int guido_image_load(const char *path, guido_image **out) {
 
 int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t name_cap,
                        int64_t *len, int64_t *goff) {
+    GUIDO_API_RANGE();
     if (!img || ix < 0 || ix >= (int64_t)img->contigs.size()) { set_error("contig index out of range"); return GUIDO_ERR_ARG; }
     const Contig &c = img->contigs[(size_t)ix];
     if (name && name_cap > 0) { strncpy(name, c.name.c_str(), (size_t)name_cap - 1); name[name_cap - 1] = 0; }
@@ -410,6 +423,7 @@ int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t n
 }
 
 int guido_image_fetch(const guido_image *img, int64_t ix, int64_t start0, int64_t n, char *out) {
+    GUIDO_API_RANGE();
     if (!img || ix < 0 || ix >= (int64_t)img->contigs.size()) { set_error("contig index out of range"); return GUIDO_ERR_ARG; }
     const Contig &c = img->contigs[(size_t)ix];
     if (start0 < 0 || n < 0 || start0 + n > c.len) { set_error("range outside contig"); return GUIDO_ERR_ARG; }
@@ -430,6 +444,7 @@ int guido_image_fetch(const guido_image *img, int64_t ix, int64_t start0, int64_
 }
 
 int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64_t n, int32_t width, char *out) {
+    GUIDO_API_RANGE();
     if (!img || width < 0 || n < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     static const char L[4] = {'A', 'C', 'G', 'T'};
     for (int64_t w = 0; w < n; w++) {
@@ -453,6 +468,7 @@ int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64
 // 8-byte wire records -> 16-byte records: the window planes come from the host copy of the image,
 // cut and oriented exactly as the search kernels do it (offtarget.cu, ot_kernel)
 int guido_hits_expand(const guido_image *img, const uint64_t *packed, int64_t n, int32_t pam_len, guido_ot_hit *out) {
+    GUIDO_API_RANGE();
     if (!img || n < 0 || pam_len < 1 || pam_len > kMaxPam || (n && (!packed || !out))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     const int W = kProto + pam_len;
     const uint32_t wmask = (1u << W) - 1;
@@ -481,6 +497,7 @@ int guido_hits_expand(const guido_image *img, const uint64_t *packed, int64_t n,
 }
 
 int guido_encode_guides(const char *protos, int64_t n, uint32_t *out) {
+    GUIDO_API_RANGE();
     uint8_t code[256];  // table lookup: a switch on random letters mispredicts on every second one
     memset(code, 0xff, sizeof code);
     code['A'] = code['a'] = 0; code['C'] = code['c'] = 1; code['G'] = code['g'] = 2; code['T'] = code['t'] = 3;

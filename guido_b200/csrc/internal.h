@@ -55,6 +55,14 @@ struct guido_image {
 
 namespace guido {
 
+// NVTX range around a C-ABI entry point (visible in nsys / ncu timelines; a no-op without a tool
+// attached: nvtx3 is header-only and resolves its injection library lazily)
+struct ApiRange {
+    explicit ApiRange(const char *name);
+    ~ApiRange();
+};
+#define GUIDO_API_RANGE() ::guido::ApiRange guido_api_range_(__func__)
+
 void set_error(const char *fmt, ...);
 int parse_pam(const char *pam, PamSpec *spec);  // GUIDO_ERR_PAM on unknown letter
 int image_finalize_layout(guido_image *img);     // assigns goff / padded_bases / n_blocks

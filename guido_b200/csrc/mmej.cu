@@ -17,6 +17,7 @@
 // Scores are float64 functions of small integers and stay on the host (bit-exact with Python).
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "device.cuh"
@@ -208,6 +209,7 @@ using namespace guido;
 extern "C" int guido_mmej_batch(const char *windows, const int64_t *offsets, const int32_t *cuts, int64_t n,
                                 int32_t device, uint32_t *out_tuples, int64_t cap, int64_t *out_offsets,
                                 int32_t *n_cand, guido_stats *stats) {
+    GUIDO_API_RANGE();
     if (n < 0 || (n > 0 && (!windows || !offsets || !cuts)) || !out_offsets) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
     if (n > 0x7fffffff) { set_error("too many windows"); return GUIDO_ERR_ARG; }
     for (int64_t g = 0; g < n; g++) {
@@ -220,34 +222,50 @@ extern "C" int guido_mmej_batch(const char *windows, const int64_t *offsets, con
     }
     out_offsets[0] = 0;
     if (n == 0) return GUIDO_OK;
-    DeviceState ds;
-    int rc = device_init(&ds, device);
-    if (rc) return rc;
+    // Stream, events and device buffers are kept per device between calls (grown on demand): a
+    // locus-sized batch runs for milliseconds, a context and nine allocations per call cost as much
+    struct Ctx {
+        DeviceState ds;
+        void *win = nullptr, *off = nullptr, *cuts = nullptr, *seg_start = nullptr, *seg_count = nullptr, *ncand = nullptr,
+             *todo = nullptr, *scratch = nullptr, *out = nullptr;
+        int64_t win_cap = 0, off_cap = 0, cuts_cap = 0, seg_start_cap = 0, seg_count_cap = 0, ncand_cap = 0, todo_cap = 0,
+                scratch_cap = 0, out_cap = 0;
+    };
+    static std::mutex mu;
+    static Ctx *cached[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= 64) { set_error("device %d out of range", (int)device); return GUIDO_ERR_ARG; }
+    if (!cached[device]) {
+        Ctx *c = new Ctx();
+        int rc0 = device_init(&c->ds, device);
+        if (rc0) { delete c; return rc0; }
+        cached[device] = c;
+    }
+    Ctx &cx = *cached[device];
+    DeviceState &ds = cx.ds;
+    int rc;
+    GUIDO_CUDA(cudaSetDevice(device));
     const int64_t total_len = offsets[n];
-    char *d_win = nullptr; long long *d_off = nullptr, *d_seg_start = nullptr; int *d_cuts = nullptr, *d_seg_count = nullptr, *d_ncand = nullptr, *d_todo = nullptr;
-    uint32_t *d_scratch = nullptr, *d_out = nullptr;
     unsigned long long *d_cursor = ds.d_counts;
     std::vector<long long> seg_start((size_t)n);
     std::vector<int> seg_count((size_t)n), ncand((size_t)n);
     std::vector<uint32_t> h_out;
     int launches = 0;
     float kernel_ms = 0;
-    auto cleanup = [&]() {
-        cudaFree(d_win); cudaFree(d_off); cudaFree(d_seg_start); cudaFree(d_cuts); cudaFree(d_seg_count);
-        cudaFree(d_ncand); cudaFree(d_todo); cudaFree(d_scratch); cudaFree(d_out);
-        cudaFree(ds.d_counts); cudaFree(ds.d_tile_counter);
-        for (auto &e : ds.ev) if (e) cudaEventDestroy(e);
-        if (ds.stream) cudaStreamDestroy(ds.stream);
-    };
+    auto cleanup = [&]() {};  // the buffers stay with the cached context
 #define MM_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("CUDA error %s at %s:%d", cudaGetErrorName(e_), __FILE__, __LINE__); cleanup(); return GUIDO_ERR_CUDA; } } while (0)
+#define MM_BYTES(p, need) do { if ((rc = ensure_bytes(&cx.p, &cx.p##_cap, (int64_t)(need)))) return rc; } while (0)
     cudaStream_t st = ds.stream;
     MM_CUDA(cudaEventRecord(ds.ev[0], st));
-    MM_CUDA(cudaMalloc(&d_win, (size_t)std::max<int64_t>(total_len, 1)));
-    MM_CUDA(cudaMalloc(&d_off, (size_t)(n + 1) * 8));
-    MM_CUDA(cudaMalloc(&d_cuts, (size_t)n * 4));
-    MM_CUDA(cudaMalloc(&d_seg_start, (size_t)n * 8));
-    MM_CUDA(cudaMalloc(&d_seg_count, (size_t)n * 4));
-    MM_CUDA(cudaMalloc(&d_ncand, (size_t)n * 4));
+    MM_BYTES(win, std::max<int64_t>(total_len, 1));
+    MM_BYTES(off, (n + 1) * 8);
+    MM_BYTES(cuts, n * 4);
+    MM_BYTES(seg_start, n * 8);
+    MM_BYTES(seg_count, n * 4);
+    MM_BYTES(ncand, n * 4);
+    char *d_win = (char *)cx.win; long long *d_off = (long long *)cx.off, *d_seg_start = (long long *)cx.seg_start;
+    int *d_cuts = (int *)cx.cuts, *d_seg_count = (int *)cx.seg_count, *d_ncand = (int *)cx.ncand, *d_todo = nullptr;
+    uint32_t *d_scratch = nullptr, *d_out = nullptr;
     MM_CUDA(cudaMemcpyAsync(d_win, windows, (size_t)total_len, cudaMemcpyHostToDevice, st));
     MM_CUDA(cudaMemcpyAsync(d_off, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     MM_CUDA(cudaMemcpyAsync(d_cuts, cuts, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -263,13 +281,12 @@ extern "C" int guido_mmej_batch(const char *windows, const int64_t *offsets, con
         int grid = std::min<int64_t>((n_items + kMmejWarps - 1) / kMmejWarps, (int64_t)ds.sm_count * 8);
         grid = std::max(grid, 1);
         const size_t per_warp = (size_t)scratch_cap + scratch_cap / 32;
-        cudaFree(d_scratch); d_scratch = nullptr;
-        MM_CUDA(cudaMalloc(&d_scratch, per_warp * 4 * (size_t)grid * kMmejWarps));
-        cudaFree(d_out); d_out = nullptr;
-        MM_CUDA(cudaMalloc(&d_out, (size_t)out_cap * 4));
+        MM_BYTES(scratch, per_warp * 4 * (size_t)grid * kMmejWarps);
+        MM_BYTES(out, out_cap * 4);
+        d_scratch = (uint32_t *)cx.scratch; d_out = (uint32_t *)cx.out;
         if (!todo.empty()) {
-            cudaFree(d_todo); d_todo = nullptr;
-            MM_CUDA(cudaMalloc(&d_todo, todo.size() * 4));
+            MM_BYTES(todo, todo.size() * 4);
+            d_todo = (int *)cx.todo;
             MM_CUDA(cudaMemcpyAsync(d_todo, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, st));
         }
         MM_CUDA(cudaMemsetAsync(d_cursor, 0, 8, st));
@@ -340,6 +357,7 @@ extern "C" int guido_mmej_batch(const char *windows, const int64_t *offsets, con
     }
     cleanup();
 #undef MM_CUDA
+#undef MM_BYTES
     if (!todo.empty()) { set_error("mmej: %zu windows exceed the candidate scratch", todo.size()); return GUIDO_ERR_NOMEM; }
     if (total_kept > cap) { set_error("output capacity too small: need %lld tuples", (long long)total_kept); return GUIDO_ERR_CAPACITY; }
     return GUIDO_OK;

@@ -39,6 +39,10 @@ class Locus:
         self.pam = ""
         self.guides = []
         self._layers = {}
+        # (contig name, 0-based start) when the sequence was cut from `genome` by one of the factory
+        # functions: find_guides then scans the genome image resident in HBM instead of uploading
+        # the locus sequence again
+        self._image_region = None
 
         if is_sequence_like(sequence):
             self.start = sequence.start
@@ -136,6 +140,26 @@ class Locus:
         pams_fw, pams_rv = _native.pam_scan_seq(fwd_seq, pam)
         return self._guides_from_pam_positions(fwd_seq, start, pam, pams_fw.tolist(), pams_rv.tolist())
 
+    def _scan_locus(self, upper, pam):
+        """PAM starts of both strands relative to the locus start.  A locus cut from a built genome
+        is scanned in place on the genome image in HBM (``guido_pam_scan_region``: no sequence
+        traffic at all); any other sequence goes to the device for the call (``guido_pam_scan_seq``)."""
+        region = self._image_region
+        if region is not None and self.genome is not None and getattr(self.genome, "bowtie_index", None):
+            try:
+                img = self.genome.device_image()
+                ci = img.contig_index(region[0])
+                n = len(upper)
+                if 0 <= region[1] and region[1] + n <= img.contigs[ci][1]:
+                    k = min(n, 96)  # the resident image must be the sequence the locus holds
+                    if img.fetch(ci, region[1], k) == upper[:k] and img.fetch(ci, region[1] + n - k, k) == upper[n - k:]:
+                        return img.pam_scan_region(ci, region[1], region[1] + n, pam, _native.SCAN_REGEX)
+            except (KeyError, OSError, ValueError, RuntimeError):
+                # no usable image for this genome (built with bowtie_ignore, file moved, ...): the
+                # sequence itself goes to the device -- still the GPU, which fails loudly if there is none
+                pass
+        return _native.pam_scan_seq(upper, pam)
+
     def find_guides(self, pam="NGG", min_flanking_length=0, selected_features="all"):
         """Find gRNAs in the locus (both strands), sorted by cut position and named gRNA-1..n.
 
@@ -163,7 +187,7 @@ class Locus:
         P = len(pam)
         upper = whole.upper()
         # one device scan for the whole locus; every interval slices the sorted hit lists
-        all_fw, all_rv = _native.pam_scan_seq(upper, pam)
+        all_fw, all_rv = self._scan_locus(upper, pam)
 
         for interval_start, interval_end in self.intervals:
             a = max(interval_start - min_flanking_length - self.start, 0)
@@ -262,8 +286,12 @@ def locus_from_coordinates(genome, chromosome, start, end):
         table = intersect(read_annotation(ann_path), chromosome, start, end)
         table = renamed(table, ann_path)
         if len(table) > 0:
-            return Locus(genome=genome, sequence=locus_sequence, annotation=table)
-    return Locus(genome=genome, sequence=locus_sequence, annotation=None)
+            loc = Locus(genome=genome, sequence=locus_sequence, annotation=table)
+            loc._image_region = (chromosome, int(start) - 1)
+            return loc
+    loc = Locus(genome=genome, sequence=locus_sequence, annotation=None)
+    loc._image_region = (chromosome, int(start) - 1)
+    return loc
 
 
 def locus_from_sequence(sequence, sequence_name=None):
@@ -290,6 +318,8 @@ def locus_from_gene(genome, gene_name):
         inside = (((ann["Start"] >= start) & (ann["Start"] <= end)) | ((ann["End"] >= start) & (ann["End"] <= end)))
         locus_annotation = ann[related & (ann["Chromosome"] == chromosome) & inside]
         locus_sequence = FastaFile(str(genome.genome_file_abspath)).get_seq(chromosome, start, end)
-        return Locus(genome=genome, sequence=locus_sequence, annotation=locus_annotation)
+        loc = Locus(genome=genome, sequence=locus_sequence, annotation=locus_annotation)
+        loc._image_region = (chromosome, start - 1)
+        return loc
     except Exception as e:
         raise ValueError(f"Gene {gene_name} not found. (Error: {e})")

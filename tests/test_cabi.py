@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/guido_b200.h but not exported"
     assert set(_native.EXPORTED_SYMBOLS) == set(names)
-    assert _native.lib().guido_version() == 1
+    assert _native.lib().guido_version() == 2
 
 
 def test_hit_record_layout():

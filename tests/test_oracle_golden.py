@@ -152,3 +152,27 @@ def test_seed_index_port_equals_brute_force(oracle):
         got = {(int(h >> 33), contigs[int((h >> 1) & 0xffffffff) >> 24][0], int((h >> 1) & 0xffffff), "-" if h & 1 else "+")
                for h in hits.tolist()}
         assert got == valid and len(valid) > 0
+
+
+def test_bowtie_rows_fixture(oracle):
+    """raw rows of a REAL bowtie 1.3.1 run (written by tools/compare_with_bowtie.py --write-golden on a
+    machine that has bowtie) pin oracle.bowtie_n; skipped while no fixture has been generated"""
+    import glob
+    import gzip
+    import json
+    import os
+    import pytest
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "bowtie_rows", "*.json.gz")))
+    if not files:
+        pytest.skip("no bowtie fixture yet: run tools/compare_with_bowtie.py --write-golden where bowtie 1.3.1 is installed")
+    for f in files:
+        g = json.load(gzip.open(f, "rt"))
+        contigs = [tuple(c) for c in g["contigs"]]
+        for case in g["cases"]:
+            pam = case["pam"]
+            seed_mms, seed_len, e = oracle.bowtie_args(pam, case["core_length"], case["core_mismatches"], case["total_mismatches"])
+            reads = oracle.reads_for_guides([p + pam for p in g["protos"]], pam)
+            names = [str(i) for i in range(len(reads))]
+            ours = oracle.bowtie_tsv(oracle.bowtie_n(contigs, reads, seed_mms, seed_len, e), names, reads)
+            rows = lambda tsv: {tuple(l.split("\t")[i] for i in (0, 1, 2, 3, 7)) for l in tsv.splitlines() if l.count("\t") >= 7}
+            assert rows(ours) == rows(case["tsv"]), (f, case["pam"])
