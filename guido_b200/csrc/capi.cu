@@ -659,9 +659,10 @@ static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n
                                 ds->d_counts + 1, st, &launches);
         if (rc) return rc;
         GUIDO_CUDA(cudaEventRecord(ds->ev[2], st));
-        unsigned long long c2[3];
+        unsigned long long c2[4];
         GUIDO_CUDA(cudaMemcpyAsync(c2, ds->d_counts, sizeof c2, cudaMemcpyDeviceToHost, st));
         GUIDO_CUDA(cudaStreamSynchronize(st));
+        if (c2[3]) { set_error("internal: %llu seed-index buckets were gathered with a wrong size", c2[3]); return GUIDO_ERR_CUDA; }
         float ms = 0;
         cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
         kernel_ms += ms;

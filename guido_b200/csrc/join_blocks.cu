@@ -25,9 +25,10 @@
 // of the next bucket with two bulk-TMA copies (cp.async.bulk -> UBLKCP, completion on the warp's own
 // mbarrier) into the other half of a double buffer while the warp compares the current one; no
 // CTA barrier anywhere in the loop.  Buckets are handed out in groups by an atomic ticket.
-// Non-empty result words are queued per warp (one shared-memory atomic and one 16-byte store by
-// the lane that has one) and turned into hit records by all 32 lanes, 32 at a time: one atomic on
-// the global cursor per round, the gathers (guide id, window slot) go out behind it.
+// Non-empty result words are queued per warp (a vote gives every lane that has one its slot: one
+// predicated 16-byte store, no shared-memory atomic, no divergent region) and turned into hit
+// records by all 32 lanes, 32 at a time: one atomic on the global cursor per round, the gathers
+// (guide id, window slot) go out behind it.
 #include "scan_common.cuh"
 #include "join_blocks.cuh"
 
@@ -40,6 +41,14 @@ namespace {
 #endif
 #ifndef BJ_MIN_CTAS
 #define BJ_MIN_CTAS 3
+#endif
+#ifndef BJ_ROLL
+#define BJ_ROLL 0
+#endif
+#if BJ_ROLL
+#define BJ_UNROLL_PRAGMA _Pragma("unroll 1")
+#else
+#define BJ_UNROLL_PRAGMA _Pragma("unroll")
 #endif
 constexpr int kBjWarps = BJ_WARPS;               // warps per CTA (they do not interact)
 constexpr int kBjCapBlocks = 7;                  // 64-window blocks per stage buffer (larger buckets go in pieces)
@@ -59,8 +68,6 @@ struct __align__(16) BjWarpSmem {
     uint4 meta[kBjGroupMax];                     // per bucket of the ticket: {first block, blocks, first entry, entries}
     uint4 q[kBjQueue];                           // parked results: {hit bits of windows 0..31, 32..63, entry, block}
     unsigned long long bar[2];                   // mbarriers: "stage s is full"
-    uint32_t qn;                                 // entries asked for in q (may run past kBjQueue: those went out directly)
-    uint32_t pad_[3];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -149,21 +156,11 @@ __device__ __forceinline__ void bj_write_hits(const BjArgs &a, uint32_t r, uint3
     }
 }
 
-// a lane whose result found the queue full takes it to the global list by itself (rare: more than
-// 33 non-empty results inside one pass, e.g. many copies of a guide against a repeat)
-__device__ __noinline__ void bj_emit_direct(const BjArgs &a, uint4 v) {
-    unsigned long long dst = atomicAdd(a.count, (unsigned long long)(__popc(v.x) + __popc(v.y)));
-    const uint32_t guide = __ldg(&a.ent[v.z]).y;
-    bj_write_hits(a, v.x, guide, (size_t)v.w * 64u, dst);
-    bj_write_hits(a, v.y, guide, (size_t)v.w * 64u + 32u, dst);
-}
-
 // parked results -> hit records, lane i takes entry i; only whole rounds of 32 unless `all`.  The
 // cursor is moved first and the gathers go out behind it, so a round costs one memory round trip.
 // Whatever stays is moved to the front of the queue.
-__device__ __noinline__ void bj_flush(const BjArgs &a, BjWarpSmem &ws, bool all) {
+__device__ __noinline__ uint32_t bj_flush(const BjArgs &a, BjWarpSmem &ws, uint32_t qn, bool all) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t qn = min(ws.qn, (uint32_t)kBjQueue);
     uint32_t done = 0;
     while (done + 32u <= qn || (all && done < qn)) {
         const uint32_t i = done + lane;
@@ -202,8 +199,8 @@ __device__ __noinline__ void bj_flush(const BjArgs &a, BjWarpSmem &ws, bool all)
     if (lane < left) v = ws.q[done + lane];
     __syncwarp();
     if (lane < left) ws.q[lane] = v;
-    if (lane == 0) ws.qn = left;
     __syncwarp();
+    return left;
 }
 
 // one pass of <= 32 entries (R of them valid) over the nblk blocks of the stage buffer; with
@@ -211,11 +208,13 @@ __device__ __noinline__ void bj_flush(const BjArgs &a, BjWarpSmem &ws, bool all)
 // `e_first`: global index of the pass's first entry, `e_rel` its index inside the bucket.
 template <int S>
 __device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const BjStage &st, uint32_t nblk,
-                                        uint32_t gblk0, uint32_t e_first, uint32_t e_rel, uint32_t R) {
+                                        uint32_t gblk0, uint32_t e_first, uint32_t e_rel, uint32_t R, uint32_t &qn) {
     constexpr uint32_t kPer = 32 / S;
     constexpr int kIters = (kBjCapBlocks + S - 1) / S;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r_ix = lane & (kPer - 1), s_ix = lane / kPer;
+    uint32_t lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     const bool valid = r_ix < R;
     const uint32_t e = e_first + (valid ? r_ix : 0u);
     uint32_t w = 15u << 20;  // bias 15 never hits
@@ -237,28 +236,30 @@ __device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const B
         uint32_t rx = short_tree ? tree_at_most2(mx) : tree_any(mx, k);
         uint32_t ry = short_tree ? tree_at_most2(my) : tree_any(my, k);
         if (S > 1 && it * S + s_ix >= nblk) rx = ry = 0;  // this copy's block is beyond the piece
-        if (rx | ry) {
-            const uint4 v = make_uint4(rx, ry, e, gblk0 + it * S + s_ix);
-            const uint32_t pos = atomicAdd(&ws.qn, 1u);
-            if (pos < (uint32_t)kBjQueue) ws.q[pos] = v;
-            else bj_emit_direct(a, v);
+        // non-empty results are parked in the warp's queue: slot = queue length (a warp-uniform
+        // register) + rank among the lanes that have one -- a vote and a predicated store, no
+        // shared-memory atomic and no divergent region; whole rounds of 32 leave at once
+        const bool has = (rx | ry) != 0u;
+        const uint32_t hm = __ballot_sync(kFull, has);
+        if (hm) {
+            if (has) ws.q[qn + (uint32_t)__popc(hm & lt)] = make_uint4(rx, ry, e, gblk0 + it * S + s_ix);
+            qn += (uint32_t)__popc(hm);
+            if (qn >= 32u) { __syncwarp(); qn = bj_flush(a, ws, qn, false); }
         }
     };
     if (at_most2) {
-#pragma unroll
+        BJ_UNROLL_PRAGMA
         for (int it = 0; it < kIters; it++) {
             if ((uint32_t)(it * S) >= nblk) break;
             step(it, true);
         }
     } else {
-#pragma unroll
+        BJ_UNROLL_PRAGMA
         for (int it = 0; it < kIters; it++) {
             if ((uint32_t)(it * S) >= nblk) break;
             step(it, false);
         }
     }
-    __syncwarp();
-    if (ws.qn >= 32u) bj_flush(a, ws, false);
 }
 
 }  // namespace
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(kBjWarps * 32, BJ_MIN_CTAS) ot_join_blocks_ker
     extern __shared__ __align__(128) unsigned char bj_smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     BjWarpSmem &ws = reinterpret_cast<BjWarpSmem *>(bj_smem)[warp];
-    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); ws.qn = 0; }
+    if (lane == 0) { mbar_init(&ws.bar[0], 1); mbar_init(&ws.bar[1], 1); }
+    uint32_t qn = 0;  // results parked in ws.q (warp-uniform)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     uint32_t parity = 0;  // bit s: phase of bar[s] the next wait on it looks for
@@ -326,9 +328,9 @@ __global__ void __launch_bounds__(kBjWarps * 32, BJ_MIN_CTAS) ot_join_blocks_ker
                 parity ^= 1u << s;
                 for (uint32_t g0 = 0; g0 < K; g0 += 32) {
                     const uint32_t R = min(K - g0, 32u);
-                    if (R > 16 || nblk == 1) bj_pass<1>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
-                    else if (R > 8 || nblk == 2) bj_pass<2>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
-                    else bj_pass<4>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R);
+                    if (R > 16 || nblk == 1) bj_pass<1>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R, qn);
+                    else if (R > 8 || nblk == 2) bj_pass<2>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R, qn);
+                    else bj_pass<4>(a, ws, ws.st[s], nblk, m.x + piece, m.z + g0, g0, R, qn);
                 }
             }
             __syncwarp();  // every lane is done with stage s before it is refilled
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kBjWarps * 32, BJ_MIN_CTAS) ot_join_blocks_ker
         }
     }
     __syncwarp();
-    if (ws.qn) bj_flush(a, ws, true);
+    if (qn) bj_flush(a, ws, qn, true);
     if (a.site_count) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) compared += __shfl_xor_sync(kFull, compared, o);

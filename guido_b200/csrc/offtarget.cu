@@ -919,6 +919,181 @@ __global__ void __launch_bounds__(256) idx_back_cursor_kernel(const uint32_t *of
     if (k < n_buckets) back[k] = (offsets[k + 1] & ~pad_mask) - (offsets[k] & pad_mask);
 }
 
+// ---- entries by GATHER: bucket-major, no atomics, coalesced stores ---------------------------------
+//
+// The scatter above costs one returning L2 atomic and one isolated 8-byte store per entry (43.6 M of
+// each for 100 k guides) and has to walk the guides once per L2-sized slice.  The same index can be
+// read off the guides' OWN cores: bucket b holds the guides whose core is one of the 436 neighbours
+// of b (<= core_mm substitutions), only ~9 % of all cores carry a guide, and which ones do is a
+// 1 Mbit map.  So: guides sorted by core (counting sort on the exact histogram the Hamming-ball
+// convolution starts from), a presence bitmap, and per bucket a warp that probes the 436 neighbour
+// bits, compacts the occupied ones IN VARIANT ORDER (largest core-mismatch class first, which is the
+// order the block join wants) and copies their guides into the bucket: consecutive lanes write
+// consecutive entries.
+//
+// The core positions are split in halves A (0..4) and B (5..9).  A CTA owns buckets that share their
+// B half, so all its probes fall into the 106 rows "B half within <= 2 substitutions" of the bitmap;
+// a row is 1024 bits (the A half: word = hi plane bits, bit = lo plane bits), 13.6 KB for all rows,
+// staged in shared memory once per CTA.  Lane l owns variants 14 l .. 14 l + 13 for the whole
+// kernel: row slot and A-half XOR masks sit in 14 registers, a probe is XOR, shift, LDS, shift.
+constexpr int kGatherPerLane = 14;                       // 32 x 14 = 448 >= 436 variants (core 10 / <= 2)
+constexpr int kGatherMaxVar = 32 * kGatherPerLane;
+constexpr int kGatherMaxRows = 106;                      // B halves within <= 2 substitutions; + 1 all-zero row
+constexpr int kGatherWarps = 8;
+constexpr int kGatherSub = 4;                            // CTAs per B tile: 256 buckets each
+
+struct GatherArgs {
+    const uint32_t *present;     // bit `key` set: some guide has this core (key = hi plane << 10 | lo plane)
+    const uint2 *core_rec;       // per core: {distal letters, guide} of its only guide, or {kCoreMulti | count, first guide in `sorted`}
+    const uint2 *sorted;         // guides in core order: {distal letters, guide}
+    const uint32_t *ent_off;     // n_buckets + 1: first entry of each bucket (even) | pad flag
+    uint2 *ent;
+    const uint32_t *probe;       // kGatherMaxVar words: row slot << 10 | A-half hi mask << 5 | A-half lo mask
+    const uint32_t *var_mask;    // kGatherMaxVar words: key XOR mask (20 bits) | bias << 20
+    const uint32_t *row_mask;    // kGatherMaxRows words: B-half hi mask << 5 | lo mask of each row
+    uint32_t n_rows;
+    uint32_t tile_lo;            // first B tile of this launch (tile = B-half hi bits << 5 | lo bits)
+    unsigned long long *err;     // += buckets whose gathered size differs from the scanned size
+};
+constexpr uint32_t kCoreMulti = 1u << 31;  // core_rec.x: several guides share this core
+
+__global__ void __launch_bounds__(256) core_present_kernel(const uint32_t *level0, uint32_t n_buckets, uint32_t *present) {
+    const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t w = __ballot_sync(kFull, k < n_buckets && level0[k] != 0u);
+    if ((threadIdx.x & 31) == 0 && k < n_buckets) present[k >> 5] = w;
+}
+
+// guides -> core order; core_start[] = exclusive scan of the core histogram, cursor[] a copy of it
+// (scan_fixup_kernel's second output).  A core with one guide gets that guide as its record.
+__global__ void __launch_bounds__(256) core_sort_kernel(const uint2 *guides, uint32_t n_guides, int cl, int dl,
+                                                        const uint32_t *core_start, uint32_t *cursor, uint2 *sorted, uint2 *core_rec) {
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= n_guides) return;
+    const uint2 G = __ldg(&guides[g]);
+    const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
+    const uint32_t key = (((G.x >> dl) & cmask) << cl) | ((G.y >> dl) & cmask);
+    const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
+    const uint2 rec = make_uint2(spread_bits(dlo) | (spread_bits(dh) << 1), g);
+    const uint32_t c0 = core_start[key], cnt = core_start[key + 1] - c0;
+    sorted[atomicAdd(&cursor[key], 1u)] = rec;
+    core_rec[key] = cnt == 1u ? rec : make_uint2(kCoreMulti | cnt, c0);  // (the guides of a shared core all write the same record)
+}
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const GatherArgs a) {
+    __shared__ uint32_t s_rows[(kGatherMaxRows + 1) * 32];
+    __shared__ uint32_t s_var[kGatherMaxVar];
+    __shared__ uint16_t s_list[kGatherWarps][kGatherMaxVar];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = a.tile_lo + blockIdx.x / kGatherSub, sub = blockIdx.x % kGatherSub;
+    const uint32_t hiB = tile >> 5, loB = tile & 31u;
+    for (uint32_t x = threadIdx.x; x < (kGatherMaxRows + 1) * 32; x += kGatherWarps * 32) {
+        const uint32_t row = x >> 5, hiA = x & 31u;
+        uint32_t w = 0;
+        if (row < a.n_rows) {
+            const uint32_t rm = __ldg(&a.row_mask[row]);
+            w = __ldg(&a.present[((hiB ^ (rm >> 5)) << 10) | (hiA << 5) | (loB ^ (rm & 31u))]);
+        }
+        s_rows[(row << 5) | (hiA ^ (row & 31u))] = w;  // swizzled: the probes of a round hit different banks
+    }
+    for (uint32_t x = threadIdx.x; x < (uint32_t)kGatherMaxVar; x += kGatherWarps * 32) s_var[x] = __ldg(&a.var_mask[x]);
+    uint32_t pk[kGatherPerLane];
+#pragma unroll
+    for (int r = 0; r < kGatherPerLane; r++) pk[r] = __ldg(&a.probe[lane * kGatherPerLane + r]);
+    __syncthreads();
+    uint16_t *list = s_list[warp];
+    constexpr uint32_t kPerCta = 1024 / kGatherSub;
+    auto key_of = [&](uint32_t b) {
+        const uint32_t abits = sub * kPerCta + b;  // hi plane bits << 5 | lo plane bits of the A half
+        return (hiB << 15) | ((abits >> 5) << 10) | (loB << 5) | (abits & 31u);
+    };
+    unsigned long long bad = 0;
+    uint32_t v0 = __ldg(&a.ent_off[key_of(warp)]), v1 = __ldg(&a.ent_off[key_of(warp) + 1]);
+    for (uint32_t b = warp; b < kPerCta; b += kGatherWarps) {
+        const uint32_t abits = sub * kPerCta + b;
+        const uint32_t key = key_of(b);
+        const uint32_t start = v0 & ~1u, size = (v1 & ~1u) - start - (v0 & 1u);
+        if (b + kGatherWarps < kPerCta) {  // the next bucket's bounds travel while this one is gathered
+            v0 = __ldg(&a.ent_off[key_of(b + kGatherWarps)]);
+            v1 = __ldg(&a.ent_off[key_of(b + kGatherWarps) + 1]);
+        }
+        uint32_t found = 0;
+#pragma unroll
+        for (int r = 0; r < kGatherPerLane; r++) {
+            const uint32_t t = pk[r] ^ abits;
+            found |= (__funnelshift_r(s_rows[t >> 5], 0u, t) & 1u) << r;  // the shift uses t & 31
+        }
+        // occupied neighbours in variant order -> list
+        const uint32_t n = (uint32_t)__popc(found);
+        uint32_t inc = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= (uint32_t)d) inc += t;
+        }
+        const uint32_t total = __shfl_sync(kFull, inc, 31);
+        uint32_t at = inc - n;
+        while (found) {
+            const uint32_t r = (uint32_t)__ffs((int)found) - 1u;
+            found &= found - 1u;
+            list[at++] = (uint16_t)(lane * kGatherPerLane + r);
+        }
+        __syncwarp();
+        // their guides -> the bucket: lane i takes list entries i and 32 + i of a round of 64 (both
+        // records are requested before either is used; a core mostly holds one guide)
+        uint32_t dst0 = start;
+        for (uint32_t t0 = 0; t0 < total; t0 += 64) {
+            uint2 rec[2];
+            uint32_t cnt[2], bias[2], ex[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t t = t0 + 32u * h + lane;
+                rec[h] = make_uint2(0u, 0u); cnt[h] = 0; bias[h] = 0;
+                if (t < total) {
+                    const uint32_t m = s_var[list[t]];
+                    rec[h] = __ldg(&a.core_rec[key ^ (m & 0xfffffu)]);
+                    bias[h] = m & 0xf00000u;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t t = t0 + 32u * h + lane;
+                cnt[h] = t < total ? ((rec[h].x & kCoreMulti) ? (rec[h].x & ~kCoreMulti) : 1u) : 0u;
+                ex[h] = cnt[h];
+            }
+            uint32_t tot0, tot1;
+            if (!__any_sync(kFull, ((rec[0].x | rec[1].x) & kCoreMulti) != 0u)) {
+                // one guide per core (the rule): an entry's place is its place in the list
+                tot0 = min(total - t0, 32u);
+                tot1 = total - t0 - tot0 > 32u ? 32u : total - t0 - tot0;
+                ex[0] = lane + cnt[0]; ex[1] = lane + cnt[1];
+            } else {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u0 = __shfl_up_sync(kFull, ex[0], d), u1 = __shfl_up_sync(kFull, ex[1], d);
+                    if (lane >= (uint32_t)d) { ex[0] += u0; ex[1] += u1; }
+                }
+                tot0 = __shfl_sync(kFull, ex[0], 31); tot1 = __shfl_sync(kFull, ex[1], 31);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t dst = dst0 + (h ? tot0 : 0u) + ex[h] - cnt[h];
+                if (cnt[h] == 1u && !(rec[h].x & kCoreMulti)) {
+                    a.ent[dst] = make_uint2(rec[h].x | bias[h], rec[h].y);
+                } else {
+                    for (uint32_t g = 0; g < cnt[h]; g++) {
+                        const uint2 G = __ldg(&a.sorted[rec[h].y + g]);
+                        a.ent[dst + g] = make_uint2(G.x | bias[h], G.y);
+                    }
+                }
+            }
+            dst0 += tot0 + tot1;
+        }
+        __syncwarp();  // the list is rewritten for the next bucket
+        if (lane == 0 && dst0 - start != size) bad++;
+    }
+    if (bad) atomicAdd(a.err, bad);
+}
+
 static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
     // all (xh, xl) with popc(xh | xl) <= cm over cl positions; per chosen position 3 substitutions
     out->clear();
@@ -964,7 +1139,15 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const char *hist_mode = getenv("GUIDO_IDX_HIST");
     const bool dp_counts = cl <= 10 && op.core_max >= 1 && op.core_max <= 3 && !(hist_mode && hist_mode[0] == 'a');
     const int64_t level_words = dp_counts ? (int64_t)(op.core_max + 1) * n_buckets : 0;
-    const int64_t bucket_words = (int64_t)n_scan + 2 * (int64_t)n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words;
+    // entries by gather (idx_gather_kernel) instead of the atomic scatter: 10-base cores, <= 2 core
+    // mismatches (448 probe slots); GUIDO_IDX_BUILD=scatter forces the scatter (tests, comparisons)
+    const char *build_mode = getenv("GUIDO_IDX_BUILD");
+    const bool gather = entries && dp_counts && cl == 10 && variants.size() <= (size_t)kGatherMaxVar &&
+                        !(build_mode && build_mode[0] == 's');
+    // gather scratch behind the levels: [present n_buckets/32][probe][var_mask][row_mask 128][sorted 2 n_guides][core_rec 2 n_buckets]
+    const int64_t gather_words = gather ? (int64_t)n_buckets / 32 + 2 * kGatherMaxVar + 128 + 2 * n_guides + 2 + 2 * (int64_t)n_buckets : 0;
+    const int64_t bucket_words = (int64_t)n_scan + 2 * (int64_t)n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words +
+                                 gather_words;
     int rc;
     if ((rc = ensure_bytes(&ds->d_bucket, &ds->bucket_cap, bucket_words * 4))) return rc;
     // popc format: every bucket is padded to a multiple of 8 slots; worst case allocated
@@ -987,7 +1170,68 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
     const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
     int slice_bits = part_bits;  // a partition is a union of slices
-    while (slice_bits < 5 && slice_bits < cl && ((used_slots * 8) >> slice_bits) > slice_bytes) slice_bits++;
+    // (the gather writes whole lines in bucket order and needs no slices: one launch, then one join)
+    while (!gather && slice_bits < 5 && slice_bits < cl && ((used_slots * 8) >> slice_bits) > slice_bytes) slice_bits++;
+    // gather tables.  Lane l owns the probe slots 14 l .. 14 l + 13 and the compacted list follows slot
+    // order, so the variants of the largest core-mismatch class (405 of 436) take the slots of lanes
+    // 0 .. 28 and the others follow: the block join meets the classes one after the other.  WHICH
+    // slot of its class a variant takes is free, and round r probes the slots {14 l + r}: they are
+    // dealt so that the 32 probes of a round fall into different shared-memory banks or onto the
+    // same word (a row is stored with its word index XORed by row & 31, see idx_gather_kernel).
+    std::vector<uint32_t> g_probe(kGatherMaxVar), g_var(kGatherMaxVar, 0u), g_row;
+    if (gather) {
+        auto cmm_of = [](uint32_t var) { return __builtin_popcount((var & 0xffffu) | (var >> 16)); };
+        struct Slot { uint32_t probe, var; };
+        std::vector<std::vector<Slot>> pool(2);  // [0]: largest class, [1]: the rest in class order
+        std::vector<uint32_t> by_class(variants);
+        std::stable_sort(by_class.begin(), by_class.end(), [&](uint32_t x, uint32_t y) { return cmm_of(x) > cmm_of(y); });
+        for (uint32_t v : by_class) {
+            const uint32_t xh = v & 0xffffu, xl = v >> 16;
+            const uint32_t rm = ((xh >> 5) << 5) | (xl >> 5);  // B half: hi mask << 5 | lo mask
+            size_t row = std::find(g_row.begin(), g_row.end(), rm) - g_row.begin();
+            if (row == g_row.size()) g_row.push_back(rm);
+            const uint32_t probe = ((uint32_t)row << 10) | (((xh & 31u) ^ ((uint32_t)row & 31u)) << 5) | (xl & 31u);
+            const uint32_t var = (xh << 10) | xl | (std::min<uint32_t>((uint32_t)cmm_of(v) + (uint32_t)(7 - op.total_max), 15u) << 20);
+            pool[cmm_of(v) == op.core_max ? 0 : 1].push_back(Slot{probe, var});
+        }
+        if (g_row.size() > (size_t)kGatherMaxRows) { set_error("internal: gather rows"); return GUIDO_ERR_ARG; }
+        const uint32_t zero_row = (uint32_t)g_row.size();
+        // lanes of the first pool: enough whole lanes for it; the second pool starts on the next lane
+        const int lanes0 = (int)((pool[0].size() + kGatherPerLane - 1) / kGatherPerLane);
+        if ((size_t)(32 - lanes0) * kGatherPerLane < pool[1].size()) { set_error("internal: gather slots"); return GUIDO_ERR_ARG; }
+        std::vector<int> bank_word(kGatherPerLane * 32, -1);   // per round and bank: the word probed there
+        std::vector<int> fill0(kGatherPerLane, 0), fill1(kGatherPerLane, 0);
+        for (auto &x : g_probe) x = 0xffffffffu;
+        auto place = [&](const Slot &sl, int which, bool allow_conflict) {
+            const int word = (int)(sl.probe >> 5), bank = word & 31;
+            const int lane_lo = which ? lanes0 : 0, lane_n = which ? 32 - lanes0 : lanes0;
+            std::vector<int> &fill = which ? fill1 : fill0;
+            for (int r = 0; r < kGatherPerLane; r++) {
+                if (fill[r] >= lane_n) continue;
+                int &bw = bank_word[r * 32 + bank];
+                if (bw != -1 && bw != word && !allow_conflict) continue;
+                if (bw == -1) bw = word;
+                const int slot = (lane_lo + fill[r]++) * kGatherPerLane + r;
+                g_probe[slot] = sl.probe; g_var[slot] = sl.var;
+                return true;
+            }
+            return false;
+        };
+        for (int which = 0; which < 2; which++) {
+            std::vector<Slot> left;
+            for (const Slot &sl : pool[which]) if (!place(sl, which, false)) left.push_back(sl);
+            for (const Slot &sl : left) place(sl, which, true);
+        }
+        // unused slots probe the all-zero row, at a word whose bank is free in their round
+        for (int slot = 0; slot < kGatherMaxVar; slot++) {
+            if (g_probe[slot] != 0xffffffffu) continue;
+            const int r = slot % kGatherPerLane;
+            int bank = 0;
+            for (int k = 0; k < 32; k++) if (bank_word[r * 32 + k] == -1 || bank_word[r * 32 + k] == (int)(zero_row * 32 + k)) { bank = k; break; }
+            bank_word[r * 32 + bank] = (int)(zero_row * 32 + bank);
+            g_probe[slot] = (zero_row << 10) | ((uint32_t)bank << 5);
+        }
+    }
     // variants grouped by the top slice_bits of their hi-plane mask (see idx_build_kernel)
     IdxArgs ia;
     {
@@ -1025,8 +1269,29 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     }
     scan_blocks_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, pad);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, n_scan_blocks);
-    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, fill, ia.pad_mask);
-    if (entries) idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
+    scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, gather ? nullptr : fill, ia.pad_mask);
+    if (entries && !gather) idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
+    GatherArgs ga;
+    if (gather) {
+        // guides in core order: the exact core histogram (level 0 of the convolution) is scanned in
+        // place -> first guide of each core, `fill` serves as the scatter cursor
+        uint32_t *levels = d_var + ((variants.size() + 15) & ~(size_t)15);
+        uint32_t *present = levels + level_words, *d_probe = present + n_buckets / 32, *d_gvar = d_probe + kGatherMaxVar,
+                 *d_row = d_gvar + kGatherMaxVar;
+        uint2 *sorted = reinterpret_cast<uint2 *>(d_row + 128 + (((uintptr_t)(d_row + 128) >> 2) & 1u));
+        uint2 *core_rec = sorted + n_guides;  // n_buckets records, only read where `present` is set
+        GUIDO_CUDA(cudaMemcpyAsync(d_probe, g_probe.data(), kGatherMaxVar * 4, cudaMemcpyHostToDevice, stream));
+        GUIDO_CUDA(cudaMemcpyAsync(d_gvar, g_var.data(), kGatherMaxVar * 4, cudaMemcpyHostToDevice, stream));
+        GUIDO_CUDA(cudaMemcpyAsync(d_row, g_row.data(), g_row.size() * 4, cudaMemcpyHostToDevice, stream));
+        core_present_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(levels, n_buckets, present);
+        if ((rc = exclusive_scan_u32(levels, n_scan, sums, fill, stream))) return rc;
+        core_sort_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, levels, fill, sorted,
+                                                                                 core_rec);
+        ga.present = present; ga.core_rec = core_rec; ga.sorted = sorted; ga.ent_off = counts;
+        ga.ent = reinterpret_cast<uint2 *>(keys); ga.probe = d_probe; ga.var_mask = d_gvar; ga.row_mask = d_row;
+        ga.n_rows = (uint32_t)g_row.size(); ga.tile_lo = 0; ga.err = ds->d_counts + 3;
+        if (n_launches) *n_launches += 5;
+    }
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");
     // 2 = one thread per window (default), 1 = one warp per window, 0 = flattened warp walk
@@ -1039,7 +1304,14 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     for (uint32_t p = (uint32_t)part_ix * per_part; p < ((uint32_t)part_ix + 1) * per_part; p++) {
         const uint32_t key_lo = p << key_shift, key_hi = (p + 1) << key_shift;
         ia.slice = p;
-        idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
+        if (gather) {
+            // the buckets of a slice share the top bits of their key = of the B tile index
+            const uint32_t tiles = 1024u >> slice_bits;
+            ga.tile_lo = p * tiles;
+            idx_gather_kernel<<<tiles * kGatherSub, kGatherWarps * 32, 0, stream>>>(ga);
+        } else {
+            idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
+        }
         GUIDO_CUDA(cudaGetLastError());
         if (after_slice && (rc = (*after_slice)(key_lo, key_hi))) return rc;
     }

@@ -401,6 +401,44 @@ def test_offtarget_join_big_buckets(native, monkeypatch, sliced):
     assert np.array_equal(merged, a)
 
 
+@pytest.mark.parametrize("cm,total", [(2, 4), (1, 3), (2, 2), (0, 2)])
+def test_index_build_gather_equals_scatter(native, monkeypatch, cm, total):
+    """the block join's seed index is built bucket-major by gathering the guides of the occupied
+    neighbour cores (default) or by the atomic scatter (GUIDO_IDX_BUILD=scatter, and core budgets the
+    gather does not cover): same hit list, also with cores shared by many guides and with a
+    partitioned key space"""
+    monkeypatch.setenv("GUIDO_OT_BLOCKS", "1")
+    contigs = util.synthetic_contigs(41, [260000, 30000], n_runs=3)
+    rng = np.random.default_rng(23)
+    img = native.Image.from_seqs(contigs).upload()
+    fw, _ = img.pam_scan_genome("NGG", native.SCAN_STRICT)     # guides that do have sites: real NGG windows, mutated
+    S, off = contigs[0][1].upper(), img.contigs[0][2]
+    protos = []
+    for p in rng.choice(fw[fw < off + len(S)], size=700, replace=False):
+        w = list(S[int(p) - off - 20:int(p) - off])
+        for _ in range(int(rng.integers(0, 4))):
+            w[int(rng.integers(0, 20))] = "ACGT"[int(rng.integers(0, 4))]
+        protos.append("".join(w))
+    protos = protos + protos[:3] * 40 + ["ACGTACGT" + p[8:] for p in protos[:50]]   # shared cores, other distal bases
+    kw = dict(core_length=10, core_mismatches=cm, total_mismatches=total, want_raw_flags=False)
+    ref, _ = img.offtarget_search(protos, algo=native.OT_SCAN, **kw)
+    out = {}
+    for mode in ("gather", "scatter"):
+        monkeypatch.setenv("GUIDO_IDX_BUILD", mode)
+        out[mode], _ = img.offtarget_search(protos, algo=native.OT_TABLE, **kw)
+        parts = []
+        for ix in range(4):
+            img.site_table_partition(ix, 4)
+            parts.append(img.offtarget_search(protos, algo=native.OT_TABLE, **kw)[0])
+        img.site_table_partition(0, 1)
+        merged = np.concatenate(parts)
+        merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
+        assert np.array_equal(merged, out[mode])
+    assert len(ref) > 100
+    assert np.array_equal(out["scatter"], ref)
+    assert np.array_equal(out["gather"], ref)
+
+
 @pytest.mark.parametrize("total", [3, 4, 5])
 def test_offtarget_block_join_full_passes(native, oracle, monkeypatch, total):
     """dense buckets on both sides (2 000 guides x 40 copies, a 24 Mb image): the block join runs
