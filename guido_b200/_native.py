@@ -84,6 +84,8 @@ _SIGNATURES = {
     "guido_site_table_partition": (ctypes.c_int, [_vp, _i32, _i32]),
     "guido_encode_guides": (ctypes.c_int, [_cp, _i64, _vp]),
     "guido_mmej_batch": (ctypes.c_int, [_cp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp, _P(Stats)]),
+    "guido_image_get_runs": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _P(ctypes.c_int64)]),
+    "guido_mmej_sites": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _P(Stats)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -295,6 +297,37 @@ class Image:
         out = np.empty((len(gpos), width), np.uint8)
         check(lib().guido_image_fetch_windows(self._h, gpos.ctypes.data, len(gpos), width, out.ctypes.data))
         return out
+
+    def runs(self):
+        """(starts, ends, kinds) of the non-ACGT runs (incl. the pads between contigs), sorted by start"""
+        n = ctypes.c_int64()
+        cap = max(int(self.info.n_runs), 1)
+        st, en, kd = np.empty(cap, np.uint32), np.empty(cap, np.uint32), np.empty(cap, np.uint8)
+        check(lib().guido_image_get_runs(self._h, st.ctypes.data, en.ctypes.data, kd.ctypes.data, cap, ctypes.byref(n)))
+        return st[:n.value], en[:n.value], kd[:n.value]
+
+    def mmej_sites(self, starts, lens, cuts, stats=None, cap_hint=None, pinned=False):
+        """MMEJ candidates of windows of the RESIDENT image: window g = global positions
+        [starts[g], starts[g] + lens[g]) (forward strand), cuts[g] relative to its start.
+        Returns (tuples, offsets, n_cand) like :func:`mmej_batch`; only 12 bytes per site go up."""
+        starts = np.ascontiguousarray(starts, dtype=np.uint32)
+        n = len(starts)
+        lens = np.ascontiguousarray(np.broadcast_to(np.asarray(lens, dtype=np.int32), (n,)))
+        cuts = np.ascontiguousarray(np.broadcast_to(np.asarray(cuts, dtype=np.int32), (n,)))
+        out_off = np.zeros(n + 1, np.int64)
+        n_cand = np.zeros(n, np.int32)
+        st = stats if stats is not None else Stats()
+        cap = int(cap_hint) if cap_hint else max(1024, 320 * n)
+        while True:
+            # pinned=True: a reused page-locked buffer (valid until the next call), like pam_scan_genome's
+            out = self._pinned("mmej", cap, np.uint32) if pinned else np.empty(cap, np.uint32)
+            rc = lib().guido_mmej_sites(self._h, starts.ctypes.data, lens.ctypes.data, cuts.ctypes.data, n, out.ctypes.data,
+                                        cap, out_off.ctypes.data, n_cand.ctypes.data, ctypes.byref(st))
+            if rc == ERR_CAPACITY:
+                cap = int(out_off[n])
+                continue
+            check(rc)
+            return out[:out_off[n]], out_off, n_cand
 
     # ---- PAM scan ---------------------------------------------------------------------
     def _pinned(self, name, n, dtype):

@@ -465,6 +465,20 @@ int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64
     return GUIDO_OK;
 }
 
+// the non-ACGT runs (incl. the pads between contigs), sorted by start: [start, end) global, kind 0 = N / pad
+int guido_image_get_runs(const guido_image *img, uint32_t *starts, uint32_t *ends, uint8_t *kinds, int64_t cap, int64_t *n_runs) {
+    GUIDO_API_RANGE();
+    if (!img || !n_runs) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    *n_runs = (int64_t)img->runs.size();
+    if ((int64_t)img->runs.size() > cap) return GUIDO_ERR_CAPACITY;
+    for (size_t i = 0; i < img->runs.size(); i++) {
+        if (starts) starts[i] = img->runs[i].start;
+        if (ends) ends[i] = img->runs[i].end;
+        if (kinds) kinds[i] = img->runs[i].kind;
+    }
+    return GUIDO_OK;
+}
+
 // 8-byte wire records -> 16-byte records: the window planes come from the host copy of the image,
 // cut and oriented exactly as the search kernels do it (offtarget.cu, ot_kernel)
 int guido_hits_expand(const guido_image *img, const uint64_t *packed, int64_t n, int32_t pam_len, guido_ot_hit *out) {

@@ -944,7 +944,8 @@ constexpr int kGatherSub = 4;                            // CTAs per B tile: 256
 
 struct GatherArgs {
     const uint32_t *present;     // bit `key` set: some guide has this core (key = hi plane << 10 | lo plane)
-    const uint2 *core_rec;       // per core: {distal letters, guide} of its only guide, or {kCoreMulti | count, first guide in `sorted`}
+    const uint2 *core_rec;       // per occupied core: {distal letters (| kCoreMulti), guide} of the first guide filed under it
+    const uint32_t *core_start;  // n_buckets + 1: first guide of each core in `sorted`
     const uint2 *sorted;         // guides in core order: {distal letters, guide}
     const uint32_t *ent_off;     // n_buckets + 1: first entry of each bucket (even) | pad flag
     uint2 *ent;
@@ -964,7 +965,8 @@ __global__ void __launch_bounds__(256) core_present_kernel(const uint32_t *level
 }
 
 // guides -> core order; core_start[] = exclusive scan of the core histogram, cursor[] a copy of it
-// (scan_fixup_kernel's second output).  A core with one guide gets that guide as its record.
+// (scan_fixup_kernel's second output).  The guide that lands first in a core's segment becomes the
+// core's record, flagged when the core holds more.
 __global__ void __launch_bounds__(256) core_sort_kernel(const uint2 *guides, uint32_t n_guides, int cl, int dl,
                                                         const uint32_t *core_start, uint32_t *cursor, uint2 *sorted, uint2 *core_rec) {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;
@@ -975,8 +977,9 @@ __global__ void __launch_bounds__(256) core_sort_kernel(const uint2 *guides, uin
     const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
     const uint2 rec = make_uint2(spread_bits(dlo) | (spread_bits(dh) << 1), g);
     const uint32_t c0 = core_start[key], cnt = core_start[key + 1] - c0;
-    sorted[atomicAdd(&cursor[key], 1u)] = rec;
-    core_rec[key] = cnt == 1u ? rec : make_uint2(kCoreMulti | cnt, c0);  // (the guides of a shared core all write the same record)
+    const uint32_t pos = atomicAdd(&cursor[key], 1u);
+    sorted[pos] = rec;
+    if (pos == c0) core_rec[key] = make_uint2(rec.x | (cnt > 1u ? kCoreMulti : 0u), g);  // the core's first guide stands for it
 }
 
 __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const GatherArgs a) {
@@ -1038,56 +1041,44 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const 
             list[at++] = (uint16_t)(lane * kGatherPerLane + r);
         }
         __syncwarp();
-        // their guides -> the bucket: lane i takes list entries i and 32 + i of a round of 64 (both
-        // records are requested before either is used; a core mostly holds one guide)
-        uint32_t dst0 = start;
+        // their guides -> the bucket.  Entry i of the list becomes entry i of the bucket: the record of
+        // its core IS a guide (the first one filed under that core), so there are no ranks to compute.
+        // The few cores that hold more guides (5 % for 100 k guides) are flagged; their other guides
+        // are appended behind the `total` regular entries, one flagged core at a time.
+        uint32_t ext = start + total;
         for (uint32_t t0 = 0; t0 < total; t0 += 64) {
             uint2 rec[2];
-            uint32_t cnt[2], bias[2], ex[2];
+            uint32_t key2[2], bias[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t t = t0 + 32u * h + lane;
-                rec[h] = make_uint2(0u, 0u); cnt[h] = 0; bias[h] = 0;
+                rec[h] = make_uint2(0u, 0u); key2[h] = 0; bias[h] = 0;
                 if (t < total) {
                     const uint32_t m = s_var[list[t]];
-                    rec[h] = __ldg(&a.core_rec[key ^ (m & 0xfffffu)]);
+                    key2[h] = key ^ (m & 0xfffffu);
+                    rec[h] = __ldg(&a.core_rec[key2[h]]);
                     bias[h] = m & 0xf00000u;
                 }
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t t = t0 + 32u * h + lane;
-                cnt[h] = t < total ? ((rec[h].x & kCoreMulti) ? (rec[h].x & ~kCoreMulti) : 1u) : 0u;
-                ex[h] = cnt[h];
-            }
-            uint32_t tot0, tot1;
-            if (!__any_sync(kFull, ((rec[0].x | rec[1].x) & kCoreMulti) != 0u)) {
-                // one guide per core (the rule): an entry's place is its place in the list
-                tot0 = min(total - t0, 32u);
-                tot1 = total - t0 - tot0 > 32u ? 32u : total - t0 - tot0;
-                ex[0] = lane + cnt[0]; ex[1] = lane + cnt[1];
-            } else {
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t u0 = __shfl_up_sync(kFull, ex[0], d), u1 = __shfl_up_sync(kFull, ex[1], d);
-                    if (lane >= (uint32_t)d) { ex[0] += u0; ex[1] += u1; }
-                }
-                tot0 = __shfl_sync(kFull, ex[0], 31); tot1 = __shfl_sync(kFull, ex[1], 31);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t dst = dst0 + (h ? tot0 : 0u) + ex[h] - cnt[h];
-                if (cnt[h] == 1u && !(rec[h].x & kCoreMulti)) {
-                    a.ent[dst] = make_uint2(rec[h].x | bias[h], rec[h].y);
-                } else {
-                    for (uint32_t g = 0; g < cnt[h]; g++) {
-                        const uint2 G = __ldg(&a.sorted[rec[h].y + g]);
-                        a.ent[dst + g] = make_uint2(G.x | bias[h], G.y);
+                if (t < total) a.ent[start + t] = make_uint2((rec[h].x & ~kCoreMulti) | bias[h], rec[h].y);
+                uint32_t mm = __ballot_sync(kFull, (rec[h].x & kCoreMulti) != 0u);
+                while (mm) {
+                    const int src = __ffs((int)mm) - 1;
+                    mm &= mm - 1u;
+                    const uint32_t k2 = __shfl_sync(kFull, key2[h], src), bs = __shfl_sync(kFull, bias[h], src);
+                    const uint32_t c0 = __ldg(&a.core_start[k2]), cnt = __ldg(&a.core_start[k2 + 1]) - c0;
+                    for (uint32_t g = 1 + lane; g < cnt; g += 32) {
+                        const uint2 G = __ldg(&a.sorted[c0 + g]);
+                        a.ent[ext + g - 1] = make_uint2(G.x | bs, G.y);
                     }
+                    ext += cnt - 1;
                 }
             }
-            dst0 += tot0 + tot1;
         }
+        const uint32_t dst0 = ext;
         __syncwarp();  // the list is rewritten for the next bucket
         if (lane == 0 && dst0 - start != size) bad++;
     }
@@ -1287,7 +1278,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         if ((rc = exclusive_scan_u32(levels, n_scan, sums, fill, stream))) return rc;
         core_sort_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, levels, fill, sorted,
                                                                                  core_rec);
-        ga.present = present; ga.core_rec = core_rec; ga.sorted = sorted; ga.ent_off = counts;
+        ga.present = present; ga.core_rec = core_rec; ga.core_start = levels; ga.sorted = sorted; ga.ent_off = counts;
         ga.ent = reinterpret_cast<uint2 *>(keys); ga.probe = d_probe; ga.var_mask = d_gvar; ga.row_mask = d_row;
         ga.n_rows = (uint32_t)g_row.size(); ga.tile_lo = 0; ga.err = ds->d_counts + 3;
         if (n_launches) *n_launches += 5;

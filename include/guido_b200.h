@@ -128,6 +128,13 @@ int guido_image_contig(const guido_image *img, int64_t ix, char *name, int64_t n
 int guido_image_fetch(const guido_image *img, int64_t contig_ix, int64_t start0, int64_t n,
                       char *out);
 
+/* the image's non-ACGT runs (N, IUPAC letters, the pads between contigs), sorted: [start, end) in
+ * global coordinates, kind 0 = N or pad.  GUIDO_ERR_CAPACITY with *n_runs set when cap is too small.
+ * (What a caller needs to tell N-free windows apart without fetching letters; the reference tests
+ * `"N" in sequence` on strings, guido/guides.py:312-330.) */
+int guido_image_get_runs(const guido_image *img, uint32_t *starts, uint32_t *ends, uint8_t *kinds, int64_t cap,
+                         int64_t *n_runs);
+
 /* decode n_windows windows of `width` letters starting at the given GLOBAL positions (host copy);
  * letters outside any contig come back as 'N'.  out: n_windows * width bytes. */
 int guido_image_fetch_windows(const guido_image *img, const int64_t *gpos, int64_t n_windows,
@@ -245,6 +252,16 @@ int guido_encode_guides(const char *protos, int64_t n_guides, uint32_t *out_hi_l
 int guido_mmej_batch(const char *windows, const int64_t *offsets, const int32_t *cuts, int64_t n,
                      int32_t device, uint32_t *out_tuples, int64_t cap, int64_t *out_offsets,
                      int32_t *n_cand, guido_stats *stats);
+
+/* The same enumeration for windows of the resident image: window g = global positions
+ * [starts[g], starts[g] + lens[g]) (forward strand, the orientation of Guide.locus_seq,
+ * guido/guides.py:69-84), cuts[g] relative to its start.  Nothing but 12 bytes per site goes up;
+ * windows that touch a non-ACGT run are read from the host copy of the image and take the general
+ * kernel.  Replaces the per-guide sequence[slice] + generate_mmej_patterns of
+ * guido/guides.py:132-182 when the guides come from a built Genome. */
+int guido_mmej_sites(const guido_image *img, const uint32_t *starts, const int32_t *lens, const int32_t *cuts,
+                     int64_t n, uint32_t *out_tuples, int64_t cap, int64_t *out_offsets, int32_t *n_cand,
+                     guido_stats *stats);
 
 #ifdef __cplusplus
 }

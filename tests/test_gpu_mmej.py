@@ -60,3 +60,42 @@ def test_mmej_limits(native):
         native.mmej_batch(["A" * 600], [300])
     t, offs, nc = native.mmej_batch([], [])
     assert len(t) == 0 and offs.tolist() == [0]
+
+
+def test_mmej_general_kernel_equals_fast(native, oracle, monkeypatch):
+    """the bit-parallel kernel (default) and the general byte-compare kernel give the same tuples"""
+    rng = np.random.default_rng(5)
+    windows = [util.random_dna(rng, int(n)) for n in rng.integers(20, 255, size=150)] + ["ACGT" * 30, "AAC" * 60]
+    cuts = [len(w) // 2 if i % 3 else min(len(w), 7 * i % 120) for i, w in enumerate(windows)]
+    fast = native.mmej_batch(windows, cuts)
+    monkeypatch.setenv("GUIDO_MMEJ_GENERAL", "1")
+    general = native.mmej_batch(windows, cuts)
+    for x, y in zip(fast, general):
+        assert np.array_equal(x, y)
+    _check(native, oracle, windows[:40], cuts[:40])
+
+
+def test_mmej_sites_on_the_resident_image(native, oracle):
+    """windows addressed by position in the uploaded image == the same windows sent as letters,
+    including windows over N runs / IUPAC letters (host fetch + general kernel) and clipped ones"""
+    contigs = util.synthetic_contigs(77, [30000, 8000], n_runs=6)
+    img = native.Image.from_seqs(contigs).upload()
+    rng = np.random.default_rng(6)
+    (_, l0, o0), (_, l1, o1) = img.contigs[0][:3], img.contigs[1][:3]
+    starts = np.concatenate([o0 + rng.integers(0, l0 - 160, size=300), o1 + rng.integers(0, l1 - 160, size=60),
+                             [o0, o0 + l0 - 150, o1 + l1 - 90]]).astype(np.int64)
+    lens = np.concatenate([np.full(360, 150), [150, 150, 90]]).astype(np.int32)
+    cuts = np.concatenate([np.full(300, 75), rng.integers(0, 150, size=60), [75, 75, 75]]).astype(np.int32)
+    # runs of the synthetic contigs: make sure some windows cover them
+    S0 = contigs[0][1].upper()
+    bad = [i for i, ch in enumerate(S0) if ch not in "ACGT"][:3]
+    for b in bad:
+        starts = np.append(starts, o0 + max(b - 70, 0)); lens = np.append(lens, 150); cuts = np.append(cuts, 75)
+    t1, off1, nc1 = img.mmej_sites(starts, lens, cuts)
+    windows = []
+    for s0, ln in zip(starts, lens):
+        windows.append(bytes(img.fetch_windows([s0], int(ln))[0]).decode())
+    t2, off2, nc2 = native.mmej_batch(windows, cuts.tolist())
+    assert np.array_equal(off1, off2) and np.array_equal(nc1, nc2) and np.array_equal(t1, t2)
+    assert any(set(w) - set("ACGT") for w in windows) or not bad
+    _check(native, oracle, windows[:25], cuts[:25].tolist())
