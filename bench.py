@@ -375,12 +375,13 @@ def run_pam(R, img, steps, warmup):
             "h2d": int(st.bytes_h2d), "d2h": int(st.bytes_d2h)}
 
 
-def hits_checksum(torch, d_hits, n):
-    """order-independent 64-bit checksum of n 16-byte hit records on the device (sum of mixed words)"""
+def hits_checksum(torch, d_packed, n):
+    """order-independent 64-bit checksum of n 8-byte hit records (guide << 33 | position << 1 | strand) on
+    the device: sum of the mixed words -- equal at every N iff the merged lists are equal as sets"""
     if n == 0:
         return 0
-    w = d_hits[:n].view(torch.int64).reshape(-1, 2)
-    x = w[:, 0] * -7046029254386353131 + (w[:, 1] ^ (w[:, 0] >> 29)) * -4658895280553007687
+    w = d_packed[:n]
+    x = (w ^ (w >> 29)) * -4658895280553007687
     x = (x ^ (x >> 31)) * 6364136223846793005
     return int(x.sum().item()) & 0xFFFFFFFFFFFFFFFF
 
@@ -390,16 +391,11 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     n_guides = len(guides_u8)
     enc = N.encode_guides([bytes(g).decode() for g in guides_u8])
     d_guides = torch.from_numpy(enc.view(np.int32).copy()).to(R.dev)
-    # per-rank hit slot of the merge: record 0 is the header (this rank's count), the hits follow
-    stride = max(1 << 20, 256 * n_guides // R.world + (1 << 18)) + 1
-    d_send = torch.empty((stride, 4), dtype=torch.int32, device=R.dev)
-    d_hits = d_send[1:]
-    cap = stride - 1
+    # this rank's hit records (16 bytes each)
+    cap = max(1 << 20, 256 * n_guides // R.world + (1 << 18))
+    d_hits = torch.empty((cap, 4), dtype=torch.int32, device=R.dev)
     d_count = torch.zeros(1, dtype=torch.int64, device=R.dev)
     d_total = torch.zeros(1, dtype=torch.int64, device=R.dev)
-    if R.world > 1:
-        d_gath = torch.empty((R.world * stride, 4), dtype=torch.int32, device=R.dev)
-        d_merged = torch.empty((R.world * stride, 4), dtype=torch.int32, device=R.dev)
     use_index = algo != N.OT_SCAN
     # genome-side index (PAM-site table): guide independent, part of the built genome like the
     # reference's bowtie-build output, so it is built before -- not inside -- the timed region
@@ -421,17 +417,31 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     guide_bits = max(1, int(np.ceil(np.log2(max(n_guides, 2)))))
     launches_per_search = int(st0.n_launches) - (2 + (33 + guide_bits + 7) // 8 if st0.bytes_d2h >= 16 + 2 * 16 else 0)
 
-    def step():
+    def search():
         img.offtarget_search_dev(d_guides.data_ptr(), n_guides, PAM, OT_KW["core_length"],
                                  OT_KW["core_mismatches"], OT_KW["total_mismatches"], algo,
                                  d_hits.data_ptr(), cap, d_count.data_ptr(), R.stream.cuda_stream)
+
+    stride = 0
+    if R.world > 1:
+        # the merge's slot per rank is sized from a first search (the largest per-rank count + 10 %):
+        # a slot that is cut shows in its header, the check after the timed region raises
+        search()
+        stride = int(R.allmax(float(d_count.item())) * 1.1) + 4096
+        d_send = torch.empty(stride, dtype=torch.int64, device=R.dev)
+        d_gath = torch.empty(R.world * stride, dtype=torch.int64, device=R.dev)
+        d_merged = torch.empty(R.world * stride, dtype=torch.int64, device=R.dev)
+
+    def step():
+        search()
         if R.world > 1:
-            # merge of the per-GPU hit lists: the count rides in the header record, ONE padded
-            # all-gather, concat on the device -- no host round trip inside the step
-            d_send[0, :2].copy_(d_count.view(torch.int32))
+            # merge of the per-GPU hit lists on the 8-byte wire format (guide << 33 | position << 1 |
+            # strand): the count rides in the header word, ONE padded all-gather over NVLink, concat
+            # on the device -- no host round trip inside the step
+            img.pack_send_dev(d_hits.data_ptr(), d_count.data_ptr(), stride - 1, d_send.data_ptr(), R.stream.cuda_stream)
             dist.all_gather_into_tensor(d_gath, d_send)
-            img.concat_hits_dev(d_gath.data_ptr(), R.world, stride, d_merged.data_ptr(), d_merged.shape[0],
-                                d_total.data_ptr(), R.stream.cuda_stream)
+            img.concat_packed_dev(d_gath.data_ptr(), R.world, stride, d_merged.data_ptr(), d_merged.shape[0],
+                                  d_total.data_ptr(), R.stream.cuda_stream)
             return launches_per_search + 2
         return launches_per_search
 
@@ -443,11 +453,16 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     if n_rank > cap:
         raise RuntimeError(f"hit buffer too small: {n_rank} > {cap}")
     if R.world > 1:
+        if n_rank > stride - 1:
+            raise RuntimeError(f"merge slot too small: {n_rank} > {stride - 1}")
         hits = int(d_total.item())
         checksum = hits_checksum(torch, d_merged, hits)
     else:
         hits = n_rank
-        checksum = hits_checksum(torch, d_hits, hits)
+        d_packed = torch.empty(max(hits, 1), dtype=torch.int64, device=R.dev)
+        img.pack_hits_dev(d_hits.data_ptr(), hits, d_packed.data_ptr(), R.stream.cuda_stream)
+        checksum = hits_checksum(torch, d_packed, hits)
+        del d_packed
     if table is not None:
         # roofline pass: in the timed steps above the join runs as one launch per key slice next
         # to the index build of the following slice, so its event pair brackets both.  The same

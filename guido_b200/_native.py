@@ -78,6 +78,8 @@ _SIGNATURES = {
     "guido_hits_sort_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "guido_hits_concat_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
     "guido_hits_pack_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "guido_hits_pack_send_dev": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "guido_packed_concat_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
     "guido_encode_guides_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "guido_site_table_build": (ctypes.c_int, [_vp, _cp, _i32, _P(_i64), _P(ctypes.c_double)]),
     "guido_site_table_free": (ctypes.c_int, [_vp]),
@@ -458,6 +460,14 @@ class Image:
     def concat_hits_dev(self, d_gathered, n_parts, stride, d_out, cap, d_total, stream=0):
         """padded, header-prefixed per-rank lists (one all-gather) -> one contiguous list; asynchronous"""
         check(lib().guido_hits_concat_dev(self._h, d_gathered, n_parts, stride, d_out, cap, d_total, stream))
+
+    def pack_send_dev(self, d_hits, d_count, cap, d_send, stream=0):
+        """hits -> 8-byte wire records behind a header word that holds *d_count (read on the device); asynchronous"""
+        check(lib().guido_hits_pack_send_dev(self._h, d_hits, d_count, cap, d_send, stream))
+
+    def concat_packed_dev(self, d_gathered, n_parts, stride, d_out, cap, d_total, stream=0):
+        """concat_hits_dev for slots of 8-byte wire records; asynchronous"""
+        check(lib().guido_packed_concat_dev(self._h, d_gathered, n_parts, stride, d_out, cap, d_total, stream))
 
     def pack_hits_dev(self, d_hits, n_hits, d_out, stream=0):
         """device-resident 16-byte records -> 8-byte guide << 33 | gpos << 1 | strand; asynchronous"""

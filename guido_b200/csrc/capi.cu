@@ -529,6 +529,25 @@ int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, vo
     return pack_hits_device(img->dev, (const guido_ot_hit *)d_hits, (uint64_t)n_hits, (unsigned long long *)d_out, (cudaStream_t)stream);
 }
 
+int guido_hits_pack_send_dev(guido_image *img, const void *d_hits, const void *d_count, int64_t cap, void *d_send, void *stream) {
+    GUIDO_API_RANGE();
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (!d_hits || !d_count || !d_send || cap < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    return pack_send_device(img->dev, (const guido_ot_hit *)d_hits, (const unsigned long long *)d_count, (uint64_t)cap,
+                            (unsigned long long *)d_send, (cudaStream_t)stream);
+}
+
+int guido_packed_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride, void *d_out,
+                            int64_t cap, void *d_total, void *stream) {
+    GUIDO_API_RANGE();
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (!d_gathered || !d_out || !d_total || stride < 1 || cap < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    return concat_packed_device(img->dev, (const unsigned long long *)d_gathered, n_parts, (uint64_t)stride,
+                                (unsigned long long *)d_out, (uint64_t)cap, (unsigned long long *)d_total, (cudaStream_t)stream);
+}
+
 int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t n_guides, void *stream) {
     GUIDO_API_RANGE();
     int rc = need_device(img);

@@ -125,6 +125,10 @@ int encode_guides_device(DeviceState *ds, const char *d_letters, int64_t n, uint
 int pack_hits_device(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, unsigned long long *d_out, cudaStream_t stream);
 int concat_hits_device(DeviceState *ds, const guido_ot_hit *d_gathered, int n_parts, uint64_t stride, guido_ot_hit *d_out,
                        uint64_t cap, unsigned long long *d_total, cudaStream_t stream);
+int pack_send_device(DeviceState *ds, const guido_ot_hit *d_hits, const unsigned long long *d_count, uint64_t cap,
+                     unsigned long long *d_send, cudaStream_t stream);
+int concat_packed_device(DeviceState *ds, const unsigned long long *d_gathered, int n_parts, uint64_t stride,
+                         unsigned long long *d_out, uint64_t cap, unsigned long long *d_total, cudaStream_t stream);
 int mark_hit_guides(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uint8_t *d_flags, cudaStream_t stream);
 bool ot_index_applicable(const OtParams &op, int64_t n_guides);
 

@@ -254,7 +254,8 @@ int guido_image_from_fasta(const char *path, guido_image **out) {
                 const char *nl = (const char *)memchr(buf + e, '\n', sz - e);
                 size_t le = nl ? (size_t)(nl - buf) : sz;
                 size_t ll = le - e;
-                if (ll && buf[le - 1] == '\r') ll--;
+                // carriage returns are skipped wherever they stand, exactly as the packing pass does
+                if (ll && memchr(buf + e, '\r', ll)) ll -= (size_t)std::count(buf + e, buf + le, '\r');
                 len += (int64_t)ll;
                 e = nl ? le + 1 : sz;
             }
@@ -384,26 +385,42 @@ int guido_image_load(const char *path, guido_image **out) {
         set_error("%s is not a guido-b200 genome image", path);
         return GUIDO_ERR_IO;
     }
-    auto *img = new guido_image();
+    // the header counts come from the file: nothing is allocated from them before they are checked
+    // against the file's size, and no exception may cross the extern "C" boundary
+    struct stat sb;
+    if (fstat(fileno(f), &sb) != 0) { fclose(f); set_error("cannot stat %s", path); return GUIDO_ERR_IO; }
+    const uint64_t fsize = (uint64_t)sb.st_size;
+    const bool sane = hdr[2] <= fsize / 24 && hdr[3] <= fsize / 12 && hdr[4] <= fsize / 16 && hdr[5] < (1ull << 32) &&
+                      hdr[4] * 64 >= hdr[5] && hdr[6] <= hdr[5];
+    if (!sane) { fclose(f); set_error("corrupt image header in %s", path); return GUIDO_ERR_IO; }
+    guido_image *img = nullptr;
     bool ok = true;
-    for (uint64_t i = 0; i < hdr[2] && ok; i++) {
-        uint64_t m[3];
-        ok = fread(m, sizeof m, 1, f) == 1;
-        std::string name((size_t)(ok ? m[0] : 0), '\0');
-        if (ok && m[0]) ok = fread(&name[0], m[0], 1, f) == 1;
-        img->contigs.push_back(Contig{name, (int64_t)m[1], (int64_t)m[2]});
-    }
-    for (uint64_t i = 0; i < hdr[3] && ok; i++) {
-        uint32_t m[3];
-        ok = fread(m, sizeof m, 1, f) == 1;
-        img->runs.push_back(Run{m[0], m[1], (uint8_t)(m[2] & 0xff), (char)((m[2] >> 8) & 0xff)});
-    }
-    img->n_blocks = (int64_t)hdr[4];
-    img->padded_bases = (int64_t)hdr[5];
-    img->total_bases = (int64_t)hdr[6];
-    if (ok) {
-        img->planes.resize((size_t)(2 * img->n_blocks));
-        ok = img->planes.empty() || fread(img->planes.data(), 8, img->planes.size(), f) == img->planes.size();
+    try {
+        img = new guido_image();
+        for (uint64_t i = 0; i < hdr[2] && ok; i++) {
+            uint64_t m[3];
+            ok = fread(m, sizeof m, 1, f) == 1 && m[0] <= 4096;
+            std::string name((size_t)(ok ? m[0] : 0), '\0');
+            if (ok && m[0]) ok = fread(&name[0], m[0], 1, f) == 1;
+            if (ok) img->contigs.push_back(Contig{name, (int64_t)m[1], (int64_t)m[2]});
+        }
+        for (uint64_t i = 0; i < hdr[3] && ok; i++) {
+            uint32_t m[3];
+            ok = fread(m, sizeof m, 1, f) == 1;
+            if (ok) img->runs.push_back(Run{m[0], m[1], (uint8_t)(m[2] & 0xff), (char)((m[2] >> 8) & 0xff)});
+        }
+        img->n_blocks = (int64_t)hdr[4];
+        img->padded_bases = (int64_t)hdr[5];
+        img->total_bases = (int64_t)hdr[6];
+        if (ok) {
+            img->planes.resize((size_t)(2 * img->n_blocks));
+            ok = img->planes.empty() || fread(img->planes.data(), 8, img->planes.size(), f) == img->planes.size();
+        }
+    } catch (const std::exception &e) {
+        fclose(f);
+        delete img;
+        set_error("cannot load %s: %s", path, e.what());
+        return GUIDO_ERR_NOMEM;
     }
     fclose(f);
     if (!ok) { delete img; set_error("truncated image %s", path); return GUIDO_ERR_IO; }

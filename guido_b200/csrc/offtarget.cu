@@ -1064,17 +1064,24 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const 
             for (int h = 0; h < 2; h++) {
                 const uint32_t t = t0 + 32u * h + lane;
                 if (t < total) a.ent[start + t] = make_uint2((rec[h].x & ~kCoreMulti) | bias[h], rec[h].y);
-                uint32_t mm = __ballot_sync(kFull, (rec[h].x & kCoreMulti) != 0u);
-                while (mm) {
-                    const int src = __ffs((int)mm) - 1;
-                    mm &= mm - 1u;
-                    const uint32_t k2 = __shfl_sync(kFull, key2[h], src), bs = __shfl_sync(kFull, bias[h], src);
-                    const uint32_t c0 = __ldg(&a.core_start[k2]), cnt = __ldg(&a.core_start[k2 + 1]) - c0;
-                    for (uint32_t g = 1 + lane; g < cnt; g += 32) {
-                        const uint2 G = __ldg(&a.sorted[c0 + g]);
-                        a.ent[ext + g - 1] = make_uint2(G.x | bs, G.y);
+                const bool multi = (rec[h].x & kCoreMulti) != 0u;
+                if (__any_sync(kFull, multi)) {
+                    // every flagged lane fetches its core's segment bounds at once; a scan over the
+                    // extra guides (segment size - 1) places them behind the regular entries
+                    uint32_t c0 = 0, extra = 0;
+                    if (multi) { c0 = __ldg(&a.core_start[key2[h]]); extra = __ldg(&a.core_start[key2[h] + 1]) - c0 - 1u; }
+                    uint32_t inc = extra;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t u = __shfl_up_sync(kFull, inc, d);
+                        if (lane >= (uint32_t)d) inc += u;
                     }
-                    ext += cnt - 1;
+                    const uint32_t at = ext + inc - extra;
+                    for (uint32_t g = 0; g < extra; g++) {
+                        const uint2 G = __ldg(&a.sorted[c0 + 1u + g]);
+                        a.ent[at + g] = make_uint2(G.x | bias[h], G.y);
+                    }
+                    ext += __shfl_sync(kFull, inc, 31);
                 }
             }
         }

@@ -95,6 +95,58 @@ int concat_hits_device(DeviceState *ds, const guido_ot_hit *d_gathered, int n_pa
     return GUIDO_OK;
 }
 
+// The same merge on the 8-byte wire format (half the NVLink bytes): a rank packs its hits behind a
+// header word that holds its count -- the count is read on the device, so the step needs no host
+// round trip -- and the gathered parts are copied back to back.
+__global__ void __launch_bounds__(256) pack_send_kernel(const guido_ot_hit *hits, const unsigned long long *count, uint64_t cap,
+                                                         unsigned long long *send) {
+    const unsigned long long n = min(*count, (unsigned long long)cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) send[0] = *count;
+    const uint4 *src = reinterpret_cast<const uint4 *>(hits);
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+        const uint4 h = src[i];
+        send[1 + i] = ((unsigned long long)h.x << 33) | ((unsigned long long)h.y << 1) | (h.z >> 31);
+    }
+}
+
+__global__ void __launch_bounds__(256) concat_packed_kernel(const unsigned long long *gathered, int n_parts, unsigned long long stride,
+                                                             unsigned long long *out, unsigned long long cap, unsigned long long *total) {
+    __shared__ unsigned long long s_off[65];
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int r = 0; r < n_parts; r++) {
+            unsigned long long c = gathered[(size_t)r * stride];
+            if (c > stride - 1) c = stride - 1;  // a part that overflowed its slot: the caller re-runs with a larger stride
+            s_off[r] = run;
+            run += c;
+        }
+        s_off[n_parts] = run;
+        if (blockIdx.x == 0) *total = run;
+    }
+    __syncthreads();
+    for (int r = 0; r < n_parts; r++) {
+        const unsigned long long n = s_off[r + 1] - s_off[r];
+        const unsigned long long *src = gathered + (size_t)r * stride + 1;
+        for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256ull)
+            if (s_off[r] + i < cap) out[s_off[r] + i] = src[i];
+    }
+}
+
+int pack_send_device(DeviceState *ds, const guido_ot_hit *d_hits, const unsigned long long *d_count, uint64_t cap,
+                     unsigned long long *d_send, cudaStream_t stream) {
+    pack_send_kernel<<<ds->sm_count * 8, 256, 0, stream>>>(d_hits, d_count, cap, d_send);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
+int concat_packed_device(DeviceState *ds, const unsigned long long *d_gathered, int n_parts, uint64_t stride,
+                         unsigned long long *d_out, uint64_t cap, unsigned long long *d_total, cudaStream_t stream) {
+    if (n_parts < 1 || n_parts > 64 || stride < 1) { set_error("bad part count or stride"); return GUIDO_ERR_ARG; }
+    concat_packed_kernel<<<ds->sm_count * 4, 256, 0, stream>>>(d_gathered, n_parts, stride, d_out, cap, d_total);
+    GUIDO_CUDA(cudaGetLastError());
+    return GUIDO_OK;
+}
+
 __global__ void __launch_bounds__(256) mark_guides_kernel(const guido_ot_hit *hits, uint64_t n, uint8_t *flags) {
     for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull)
         flags[hits[i].guide] = 1;

@@ -263,10 +263,47 @@ class Locus:
         return _guides_to_dataframe(self.guides)
 
     def guides_to_csv(self, filename):
-        _guides_to_csv(self.guides, filename)
+        if not filename:  # reference locus.py:694-700
+            raise ValueError("Filename required to save CSV with gRNAs.")
+        return _guides_to_csv(self.guides, filename)
 
     def guides_to_bed(self, filename):
-        _guides_to_bed(self.guides, filename)
+        if not filename:  # reference locus.py:702-707
+            raise ValueError("Filename required to save BED with gRNAs.")
+        return _guides_to_bed(self.guides, filename)
+
+    # ------------------------------------------------------------------ layers (host-side, outside the hot path)
+    def add_layer(self, name, layer_data, layer_pos=None, apply_to_guides=True, is_variation=False):
+        """Per-base layer of the locus; clipped to every guide's 23 bases like the reference
+        (locus.py:515-557, 409-415).  Variation layers (``is_variation`` with ``layer_pos``) need
+        scikit-allel statistics that are outside this package's scope."""
+        self._layers[name] = layer_data
+        if not apply_to_guides:
+            raise ValueError("No guides to apply the data to.")  # (the reference raises on this branch as well)
+        if len(self.guides) > 0:
+            if is_variation and layer_pos:
+                raise NotImplementedError("variation layers (scikit-allel statistics, reference locus.py:433-503) are "
+                                          "outside the scope of guido_b200")
+            if layer_data.shape[0] != self.length:
+                raise ValueError(f"Layer and locus not the same lenght ({layer_data.shape[0]}, {self.length}).")
+            for g in self.guides:
+                ix = g.guide_start - self.start
+                g.add_layer(name, layer_data[ix:ix + 23])
+
+    def rank_guides(self, *args, **kwargs):
+        """TOPSIS ranking over guide layers (reference locus.py:622-688) needs the external ``mcdm``
+        package and is outside the scope of guido_b200."""
+        raise NotImplementedError("rank_guides (mcdm / TOPSIS) is outside the scope of guido_b200")
+
+    def guides_detailed_table(self, filename):
+        """The Jinja report of the reference (helpers.py:95-107) is outside the scope of guido_b200."""
+        if not filename:
+            raise ValueError("Filename required to save CSV with gRNAs.")
+        raise NotImplementedError("guides_detailed_table (Jinja template report) is outside the scope of guido_b200")
+
+    def add_azimuth_score(self):
+        """Azimuth score of every guide (reference locus.py:718-727); see Guide.add_azimuth_score."""
+        return [g.add_azimuth_score() for g in self.guides]
 
 
 # ---------------------------------------------------------------------- locus factories

@@ -48,16 +48,22 @@ def patterns_from_tuples(rel_cut_position, sequence, tuples, length_weight):
     return [_pattern_dict(left_seq, right_seq, a, b, c, length_weight) for a, b, c in zip(ls, le, rs)]
 
 
+def _split_points(rel_cut_positions, sequences):
+    """The index at which ``sequence[:cut]`` / ``sequence[cut:]`` split the sequence, with Python's
+    slice semantics (a negative cut counts from the end, an out-of-range one clamps) -- what the
+    reference's two slices do (mmej.py:13-14).  Shared by both batch entry points.  Each side of the
+    split may hold at most 255 letters (the kernel's position bytes); longer flanks raise ValueError
+    in the C layer, where the reference would carry on."""
+    return [len(seq[:int(c)]) for seq, c in zip(sequences, rel_cut_positions)]
+
+
 def generate_mmej_patterns_batch(rel_cut_positions, sequences, length_weight, device=None, stats=None):
     """One GPU call for many cut sites; returns a list with, per site, the reference's result of
     ``generate_mmej_patterns`` (a list of pattern dicts, or None when there is no candidate)."""
     sequences = list(sequences)
-    cuts = [int(c) for c in rel_cut_positions]
+    cuts = _split_points(rel_cut_positions, sequences)
     if not sequences:
         return []
-    for c in cuts:
-        if c < 0:
-            raise ValueError("negative cut positions are not supported")
     tuples, offsets, n_cand = _native.mmej_batch(sequences, cuts, device=device, stats=stats)
     out = []
     for g, (seq, cut) in enumerate(zip(sequences, cuts)):
@@ -79,7 +85,7 @@ def top_patterns_batch(rel_cut_positions, sequences, length_weight, n_patterns, 
     (A 150-bp window keeps ~240 patterns; guido keeps 5.)
     """
     sequences = list(sequences)
-    cuts = [int(c) for c in rel_cut_positions]
+    cuts = _split_points(rel_cut_positions, sequences)
     if not sequences:
         return []
     tuples, offsets, n_cand = _native.mmej_batch(sequences, cuts, device=device, stats=stats)

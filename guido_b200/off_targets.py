@@ -2,8 +2,13 @@
 
 ``run_bowtie`` keeps its name, signature and return format, but no bowtie runs: the guides are
 searched against the genome image resident in HBM by ``guido_offtarget_search`` (C-ABI), which
-reports exactly the alignments bowtie 1 ``-n/-l/-e -a -y`` would report and guido would keep
-(off_targets.py:151-158,169-199).  ``genome_index_path`` is the image path that ``Genome.build``
+reports the alignments that bowtie 1 ``-n/-l/-e -a -y`` reports ACCORDING TO THE BOWTIE 1 MANUAL
+(seed = the first ``-l`` read bases with at most ``-n`` mismatches, 30 per mismatch against ``-e``,
+a read N mismatches everything, no alignment over ambiguous reference bases) and that guido keeps
+(off_targets.py:151-158,169-199).  bowtie 1.3.1 itself is not available where this package was
+built, so that reading of the rule is pinned against the oracle only ("parity unpinned",
+DESIGN.md section 2); ``tools/compare_with_bowtie.py`` diffs it against a real bowtie where one is
+installed.  ``genome_index_path`` is the image path that ``Genome.build``
 stores in ``Genome.bowtie_index``; ``threads`` and ``bowtie_path`` are accepted and ignored.
 """
 import os

@@ -218,6 +218,14 @@ int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t 
  * Under the merge of the per-shard bowtie outputs a multi-GPU run_bowtie needs. */
 int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride,
                           void *d_out, int64_t cap, void *d_total, void *stream);
+/* The same merge on the 8-byte wire format (half the bytes over NVLink): guido_hits_pack_send_dev
+ * writes *d_count (device u64) into d_send[0] and min(*d_count, cap) packed records behind it;
+ * after the all-gather of the `stride`-word slots guido_packed_concat_dev copies the parts back to
+ * back (cut parts: as above).  Everything is ordered on `stream`; no host read in between. */
+int guido_hits_pack_send_dev(guido_image *img, const void *d_hits, const void *d_count, int64_t cap, void *d_send,
+                             void *stream);
+int guido_packed_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride, void *d_out,
+                            int64_t cap, void *d_total, void *stream);
 /* device-resident guido_ot_hit records -> the 8-byte wire format of guido_offtarget_search_packed */
 int guido_hits_pack_dev(guido_image *img, const void *d_hits, int64_t n_hits, void *d_out, void *stream);
 /* Genome-side index of the off-target search, the counterpart of the `bowtie-build` index files

@@ -171,3 +171,40 @@ def test_bucket_counts_by_convolution_equal_histogram(native, monkeypatch, cl, c
         merged = np.concatenate(parts)
         merged = merged[np.lexsort((merged["hi"] >> 31, merged["gpos"], merged["guide"]))]
         assert np.array_equal(merged, want)
+
+
+def test_packed_slots_concat(native):
+    """merge on the 8-byte wire format: pack behind a header word (count read on the device), slots
+    laid out as an all-gather would leave them, concat -> the packed form of the host call's list;
+    a slot that is too small is cut and shows in its header"""
+    import torch
+    img, protos = _case(native, seed=31, n=400)
+    want, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False, packed=True)
+    dev = torch.device("cuda", int(img.info.device))
+    s = torch.cuda.current_stream(dev).cuda_stream
+    d_guides = torch.from_numpy(native.encode_guides(protos).view(np.int32)).to(dev)
+    parts, counts = [], []
+    for ix in range(2):           # the two halves of the key space, as two ranks would hold them
+        img.site_table_partition(ix, 2)
+        d_hits = torch.empty((len(want) + 8, 4), dtype=torch.int32, device=dev)
+        d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        img.offtarget_search_dev(d_guides.data_ptr(), len(protos), "NGG", 10, 2, 4, native.OT_TABLE, d_hits.data_ptr(),
+                                 d_hits.shape[0], d_count.data_ptr(), s)
+        parts.append((d_hits, d_count)); counts.append(int(d_count.item()))
+    img.site_table_partition(0, 1)
+    assert sum(counts) == len(want) and min(counts) > 0
+    for stride in (max(counts) + 1, max(counts) + 50, min(counts) // 2):
+        d_gath = torch.full((2 * stride,), -1, dtype=torch.int64, device=dev)
+        for r, (d_hits, d_count) in enumerate(parts):
+            img.pack_send_dev(d_hits.data_ptr(), d_count.data_ptr(), stride - 1, d_gath[r * stride:].data_ptr(), s)
+        d_out = torch.empty(2 * stride, dtype=torch.int64, device=dev)
+        d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        img.concat_packed_dev(d_gath.data_ptr(), 2, stride, d_out.data_ptr(), d_out.shape[0], d_total.data_ptr(), s)
+        heads = d_gath[::stride].cpu().numpy()
+        assert heads.tolist() == counts
+        total = int(d_total.item())
+        if stride > max(counts):
+            assert total == len(want)
+            assert np.array_equal(np.sort(d_out[:total].cpu().numpy().view(np.uint64)), want)
+        else:
+            assert total == 2 * (stride - 1)   # both parts cut: the caller sees counts > stride - 1 in the headers

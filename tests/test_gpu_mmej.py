@@ -99,3 +99,33 @@ def test_mmej_sites_on_the_resident_image(native, oracle):
     assert np.array_equal(off1, off2) and np.array_equal(nc1, nc2) and np.array_equal(t1, t2)
     assert any(set(w) - set("ACGT") for w in windows) or not bad
     _check(native, oracle, windows[:25], cuts[:25].tolist())
+
+
+def test_mmej_cut_positions_follow_slice_semantics(native):
+    """a negative or out-of-range cut splits the sequence where Python's sequence[:cut] / sequence[cut:]
+    do (reference mmej.py:13-14), in both batch entry points"""
+    from guido_b200 import mmej
+    rng = np.random.default_rng(8)
+    seq = util.random_dna(rng, 140)
+    for cut, same_as in ((-30, 110), (-500, 0), (500, 140)):
+        assert mmej.generate_mmej_patterns(cut, seq, 20) == mmej.generate_mmej_patterns(same_as, seq, 20)
+        assert mmej.top_patterns_batch([cut], [seq], 20, 5) == mmej.top_patterns_batch([same_as], [seq], 20, 5)
+    assert mmej.generate_mmej_patterns(-30, seq, 20) is not None
+
+
+def test_locus_layer_methods(native):
+    import guido_b200 as guido
+    rng = np.random.default_rng(9)
+    loc = guido.Locus(sequence=util.random_dna(rng, 400), name="c", start=101)
+    loc.find_guides()
+    data = np.arange(400)
+    loc.add_layer("pos", data)
+    g = loc.guides[0]
+    assert np.array_equal(g.layer("pos"), data[g.guide_start - 101:g.guide_start - 101 + 23])
+    with pytest.raises(ValueError):
+        loc.add_layer("short", np.arange(10))
+    with pytest.raises(ValueError):
+        loc.guides_to_csv("")
+    with pytest.raises(NotImplementedError):
+        loc.rank_guides()
+    assert callable(loc.add_azimuth_score) and callable(loc.guides_detailed_table)

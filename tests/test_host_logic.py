@@ -282,3 +282,34 @@ def test_annotate_intervals_matches_brute_force(tmp_path):
         assert o.feature[k] == expect
     assert len(annotate_intervals(df, [], [], [])) == 0
     assert list(annotate_intervals(df.iloc[:0], ["chr1"], [5], [28]).feature) == ["intergenic"]
+
+
+def test_image_load_rejects_corrupt_headers(tmp_path):
+    """a .g2b whose header counts do not fit the file is refused with an error, not an abort"""
+    from guido_b200 import _native as N
+    img = N.Image.from_seqs([("c1", "ACGT" * 500 + "NNNN" + "GATTACA" * 30)])
+    p = tmp_path / "g.g2b"
+    img.save(str(p))
+    raw = bytearray(p.read_bytes())
+    for word, value in ((2, 1 << 60), (3, 1 << 40), (4, 1 << 50), (5, 1 << 33)):
+        bad = bytearray(raw)
+        bad[8 * word:8 * word + 8] = int(value).to_bytes(8, "little")
+        q = tmp_path / f"bad{word}.g2b"
+        q.write_bytes(bytes(bad))
+        with pytest.raises(Exception):
+            N.Image.load(str(q))
+    (tmp_path / "short.g2b").write_bytes(bytes(raw[:len(raw) // 2]))
+    with pytest.raises(Exception):
+        N.Image.load(str(tmp_path / "short.g2b"))
+    assert N.Image.load(str(p)).fetch(0, 0, 8) == "ACGTACGT"
+
+
+def test_fasta_stray_carriage_returns(tmp_path):
+    """CR bytes are skipped wherever they stand (Windows line ends, a stray CR inside a line): the contig
+    length and the packed bases agree"""
+    from guido_b200 import _native as N
+    fa = tmp_path / "cr.fa"
+    fa.write_bytes(b">c1 desc\r\nACGT\rACGT\r\nGGCC\r\n>c2\nTTTT\r\n")
+    img = N.Image.from_fasta(str(fa))
+    assert [(n, l) for n, l, _ in img.contigs] == [("c1", 12), ("c2", 4)]
+    assert img.fetch(0, 0, 12) == "ACGTACGTGGCC" and img.fetch(1, 0, 4) == "TTTT"
