@@ -483,8 +483,8 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
             del os.environ["GUIDO_OT_OVERLAP"]
 
     # end to end through the public API, host buffers in and out.  One GPU:
-    # guido_offtarget_search_packed (letters up, search, device sort, key-presence flags, one copy of the
-    # 8-byte records into pinned host memory).  Several GPUs: parallel.DeviceMerge -- letters up, search,
+    # guido_offtarget_search_csr (letters up, search, device sort, key-presence flags, the hit list as CSR
+    # by guide -- 4.1 bytes per hit -- into pinned host memory).  Several GPUs: parallel.DeviceMerge -- letters up, search,
     # one NCCL all-gather, device concat + sort, then every rank copies ITS 1/N of the packed list into a
     # host segment shared by the ranks (all PCIe links busy instead of one).
     merge = None
@@ -497,7 +497,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
             h = merge.search(guides_u8, pam=PAM, algo=algo, to_host="shared", **OT_KW)
             return 20 * n_guides, 8 * len(h) // R.world + 8 * (R.world + 2)
         st = N.Stats()
-        img.offtarget_search(guides_u8, pam=PAM, algo=algo, want_raw_flags=True, stats=st, pinned=True, packed=True, **OT_KW)
+        img.offtarget_search_csr(guides_u8, pam=PAM, algo=algo, want_raw_flags=True, stats=st, pinned=True, **OT_KW)
         return int(st.bytes_h2d), int(st.bytes_d2h)
 
     e2e_ms, (h2d, d2h) = R.wall(e2e, 3)
@@ -896,8 +896,9 @@ def main():
                        "site_table": r["table"]},
             "e2e": {"value": args.guides / (r["e2e_ms"] * 1e-3), "unit": "guides/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "what": ("guido_offtarget_search_packed: 20 letters per guide up; search, device sort, key-presence flags; "
-                             "8-byte hit records + 1 flag byte per guide down into pinned host memory" if world == 1 else
+                    "what": ("guido_offtarget_search_csr: 20 letters per guide up; search, device sort, key-presence flags; the hit "
+                             "list as CSR by guide (4-byte position + 1 strand bit per hit, 4-byte offset + 1 flag byte per guide) "
+                             "down into pinned host memory" if world == 1 else
                              "parallel.DeviceMerge: letters up on every rank; search, one all-gather, concat + sort on every GPU; "
                              "every rank copies its 1/N of the 8-byte records into a host segment shared by the ranks")},
             "roofline": {"bound": "hbm", "achieved": r["kernel_gbs_per_gpu"], "peak": peak, "unit": "GB/s",

@@ -71,6 +71,8 @@ _SIGNATURES = {
                                               _P(_i64), _vp, _P(Stats)]),
     "guido_offtarget_search_packed": (ctypes.c_int, [_vp, _cp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _i64,
                                                      _P(_i64), _vp, _P(Stats)]),
+    "guido_offtarget_search_csr": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp,
+                                                  _P(_i64), _vp, _P(Stats)]),
     "guido_hits_expand": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "guido_offtarget_search_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp,
                                                   _i64, _vp, _vp]),
@@ -427,6 +429,48 @@ class Image:
             check(rc)
             self._ot_hint = nh.value + nh.value // 16 + 16  # right-size the next call's buffer
             return hits[:nh.value], flags
+
+    def offtarget_search_csr(self, protos, pam="NGG", core_length=10, core_mismatches=2, total_mismatches=4,
+                             algo=OT_AUTO, want_raw_flags=True, stats=None, pinned=False):
+        """The search with the hit list as CSR by guide -- 4.1 bytes per hit over PCIe instead of 8 or 16:
+        returns (offsets int64[n + 1], gpos uint32[n_hits], strand_bits uint32[ceil(n_hits / 32)], raw_flags).
+        Hits offsets[g] .. offsets[g + 1] belong to guide g, ordered by (position, strand);
+        ``csr_to_packed`` / ``expand_hits`` rebuild the other formats on the host."""
+        if isinstance(protos, np.ndarray):
+            keep = np.ascontiguousarray(protos, dtype=np.uint8)   # letters are read in place: no copy of the guide set
+            blob, n = keep.ctypes.data, protos.shape[0]
+        else:
+            protos = list(protos)
+            n = len(protos)
+            for p in protos:
+                if len(p) != 20:
+                    raise ValueError(f"protospacer must be 20 nt, got {len(p)}: {p!r}")
+            blob = "".join(protos).encode()
+        flags = np.zeros(n, np.uint8) if want_raw_flags else None
+        st = stats if stats is not None else Stats()
+        cap = max(4096, 32 * n, getattr(self, "_ot_hint", 0))
+        offsets = np.empty(n + 1, np.int64)
+        while True:
+            gpos = self._pinned("csr_gpos", cap, np.uint32) if pinned else np.empty(cap, np.uint32)
+            bits = self._pinned("csr_bits", cap // 32 + 1, np.uint32) if pinned else np.empty(cap // 32 + 1, np.uint32)
+            nh = ctypes.c_int64()
+            rc = lib().guido_offtarget_search_csr(self._h, blob, n, pam.encode(), core_length, core_mismatches, total_mismatches,
+                                                  algo, gpos.ctypes.data, bits.ctypes.data, cap, offsets.ctypes.data,
+                                                  ctypes.byref(nh), _ptr(flags), ctypes.byref(st))
+            if rc == ERR_CAPACITY:
+                cap = nh.value
+                continue
+            check(rc)
+            self._ot_hint = nh.value + nh.value // 16 + 16
+            return offsets, gpos[:nh.value], bits[:(nh.value + 31) // 32], flags
+
+    @staticmethod
+    def csr_to_packed(offsets, gpos, strand_bits):
+        """CSR hit list -> uint64 ``guide << 33 | gpos << 1 | strand`` (the packed format, same order)."""
+        n = len(gpos)
+        guide = np.repeat(np.arange(len(offsets) - 1, dtype=np.uint64), np.diff(offsets))
+        strand = (np.unpackbits(np.ascontiguousarray(strand_bits).view(np.uint8), bitorder="little")[:n]).astype(np.uint64)
+        return (guide << np.uint64(33)) | (gpos.astype(np.uint64) << np.uint64(1)) | strand
 
     def expand_hits(self, packed, pam_len=3):
         """uint64 packed hits -> structured records (window planes cut from the host image)."""

@@ -616,11 +616,15 @@ int guido_offtarget_raw_flags(guido_image *img, const char *protos, int64_t n_gu
 
 }  // extern "C"
 
-// `packed`: hits_out receives 8-byte records (guide << 33 | gpos << 1 | strand) instead of guido_ot_hit
+// what goes to the host: guido_ot_hit records, 8-byte records (guide << 33 | gpos << 1 | strand), or CSR by
+// guide (hits_out = positions, plus strand bits and per-guide offsets)
+enum HitFormat { kHitsFull = 0, kHitsPacked = 1, kHitsCsr = 2 };
+
 static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
                                  int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
-                                 void *hits_out, bool packed, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
-                                 guido_stats *stats) {
+                                 void *hits_out, HitFormat fmt, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
+                                 guido_stats *stats, uint32_t *csr_strand = nullptr, int64_t *csr_offsets = nullptr) {
+    const bool packed = fmt == kHitsPacked;
     int rc = need_device(img);
     if (rc) return rc;
     OtParams op;
@@ -697,8 +701,24 @@ static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n
     if ((rc = sort_hits_device(ds, (guido_ot_hit *)ds->d_out[0], found, n_guides, st, &launches))) return rc;
     if (trace) { cudaStreamSynchronize(st); lap("sort done"); }
     int64_t ncopy = std::min<int64_t>((int64_t)found, std::max<int64_t>(cap, 0));
-    const int64_t rec_bytes = packed ? 8 : (int64_t)sizeof(guido_ot_hit);
-    if (ncopy && packed) {
+    const int64_t rec_bytes = packed ? 8 : fmt == kHitsCsr ? 4 : (int64_t)sizeof(guido_ot_hit);
+    int64_t csr_extra = 0;
+    if (fmt == kHitsCsr) {
+        // positions, strand bits and per-guide offsets are cut out of the sorted records on the device
+        // (the sort's scratch is free again); the offsets travel as 32-bit words and are widened here
+        const int64_t n_words = (ncopy + 31) / 32, n_off = n_guides + 1;
+        if ((rc = ensure_bytes(&ds->d_out[1], &ds->out_cap[1], (ncopy + n_words + n_off + 16) * 4))) return rc;
+        if ((rc = ensure_pinned(ds, n_off * 4))) return rc;
+        uint32_t *d_gpos = (uint32_t *)ds->d_out[1], *d_bits = d_gpos + ncopy, *d_off = d_bits + n_words;
+        if ((rc = csr_hits_device(ds, (const guido_ot_hit *)ds->d_out[0], (uint64_t)ncopy, (uint32_t)n_guides, d_gpos, d_bits, d_off, st))) return rc;
+        launches += 1;
+        if (ncopy) {
+            GUIDO_CUDA(cudaMemcpyAsync(hits_out, d_gpos, (size_t)ncopy * 4, cudaMemcpyDeviceToHost, st));
+            GUIDO_CUDA(cudaMemcpyAsync(csr_strand, d_bits, (size_t)n_words * 4, cudaMemcpyDeviceToHost, st));
+        }
+        GUIDO_CUDA(cudaMemcpyAsync(ds->h_pinned, d_off, (size_t)n_off * 4, cudaMemcpyDeviceToHost, st));
+        csr_extra = n_words * 4 + n_off * 4;
+    } else if (ncopy && packed) {
         // the sort's scratch (d_out[1]) is free again: pack into it
         if ((rc = ensure_bytes(&ds->d_out[1], &ds->out_cap[1], ncopy * 8))) return rc;
         if ((rc = pack_hits_device(ds, (const guido_ot_hit *)ds->d_out[0], (uint64_t)ncopy, (unsigned long long *)ds->d_out[1], st))) return rc;
@@ -707,7 +727,7 @@ static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n
     } else if (ncopy) {
         GUIDO_CUDA(cudaMemcpyAsync(hits_out, ds->d_out[0], (size_t)ncopy * sizeof(guido_ot_hit), cudaMemcpyDeviceToHost, st));
     }
-    int64_t d2h = 16 + ncopy * rec_bytes, h2d = kProto * n_guides;
+    int64_t d2h = 16 + ncopy * rec_bytes + csr_extra, h2d = kProto * n_guides;
     if (raw_flags && n_guides > 0) {
         // a valid hit is a raw alignment: mark the guides that own one (on the device -- walking
         // 1e7 hit records on the host costs more than the search)
@@ -721,6 +741,10 @@ static int offtarget_search_impl(guido_image *img, const char *protos, int64_t n
     }
     GUIDO_CUDA(cudaEventRecord(ds->ev[3], st));
     GUIDO_CUDA(cudaStreamSynchronize(st));
+    if (fmt == kHitsCsr) {
+        const uint32_t *off32 = (const uint32_t *)ds->h_pinned;
+        for (int64_t g = 0; g <= n_guides; g++) csr_offsets[g] = off32[g];
+    }
     lap("copy done");
     if ((int64_t)found > cap) {
         set_error("output capacity too small: need %lld hits", (long long)found);
@@ -761,7 +785,7 @@ int guido_offtarget_search(guido_image *img, const char *protos, int64_t n_guide
                            guido_ot_hit *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                            guido_stats *stats) {
     GUIDO_API_RANGE();
-    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, false, cap, n_hits,
+    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, kHitsFull, cap, n_hits,
                                  raw_flags, stats);
 }
 
@@ -770,8 +794,18 @@ int guido_offtarget_search_packed(guido_image *img, const char *protos, int64_t 
                                   uint64_t *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                                   guido_stats *stats) {
     GUIDO_API_RANGE();
-    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, true, cap, n_hits,
+    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, hits, kHitsPacked, cap, n_hits,
                                  raw_flags, stats);
+}
+
+int guido_offtarget_search_csr(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                               int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                               uint32_t *gpos, uint32_t *strand_bits, int64_t cap, int64_t *guide_offsets, int64_t *n_hits,
+                               uint8_t *raw_flags, guido_stats *stats) {
+    GUIDO_API_RANGE();
+    if (!guide_offsets || (cap > 0 && (!gpos || !strand_bits))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    return offtarget_search_impl(img, protos, n_guides, pam, core_len, core_mm, total_mm, algo, gpos, kHitsCsr, cap, n_hits,
+                                 raw_flags, stats, strand_bits, guide_offsets);
 }
 
 }  // extern "C"

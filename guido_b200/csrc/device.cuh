@@ -125,6 +125,8 @@ int encode_guides_device(DeviceState *ds, const char *d_letters, int64_t n, uint
 int pack_hits_device(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, unsigned long long *d_out, cudaStream_t stream);
 int concat_hits_device(DeviceState *ds, const guido_ot_hit *d_gathered, int n_parts, uint64_t stride, guido_ot_hit *d_out,
                        uint64_t cap, unsigned long long *d_total, cudaStream_t stream);
+int csr_hits_device(DeviceState *ds, const guido_ot_hit *d_hits, uint64_t n, uint32_t n_guides, uint32_t *d_gpos, uint32_t *d_strand,
+                    uint32_t *d_offsets, cudaStream_t stream);
 int pack_send_device(DeviceState *ds, const guido_ot_hit *d_hits, const unsigned long long *d_count, uint64_t cap,
                      unsigned long long *d_send, cudaStream_t stream);
 int concat_packed_device(DeviceState *ds, const unsigned long long *d_gathered, int n_parts, uint64_t stride,

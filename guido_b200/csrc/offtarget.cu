@@ -944,9 +944,7 @@ constexpr int kGatherSub = 4;                            // CTAs per B tile: 256
 
 struct GatherArgs {
     const uint32_t *present;     // bit `key` set: some guide has this core (key = hi plane << 10 | lo plane)
-    const uint2 *core_rec;       // per occupied core: {distal letters (| kCoreMulti), guide} of the first guide filed under it
-    const uint32_t *core_start;  // n_buckets + 1: first guide of each core in `sorted`
-    const uint2 *sorted;         // guides in core order: {distal letters, guide}
+    const uint2 *core_rec;       // per occupied core: {distal letters, guide} of the guide that stands for it
     const uint32_t *ent_off;     // n_buckets + 1: first entry of each bucket (even) | pad flag
     uint2 *ent;
     const uint32_t *probe;       // kGatherMaxVar words: row slot << 10 | A-half hi mask << 5 | A-half lo mask
@@ -954,9 +952,8 @@ struct GatherArgs {
     const uint32_t *row_mask;    // kGatherMaxRows words: B-half hi mask << 5 | lo mask of each row
     uint32_t n_rows;
     uint32_t tile_lo;            // first B tile of this launch (tile = B-half hi bits << 5 | lo bits)
-    unsigned long long *err;     // += buckets whose gathered size differs from the scanned size
+    unsigned long long *err;     // += buckets with more occupied neighbour cores than entries (never expected)
 };
-constexpr uint32_t kCoreMulti = 1u << 31;  // core_rec.x: several guides share this core
 
 __global__ void __launch_bounds__(256) core_present_kernel(const uint32_t *level0, uint32_t n_buckets, uint32_t *present) {
     const uint32_t k = blockIdx.x * 256u + threadIdx.x;
@@ -964,28 +961,49 @@ __global__ void __launch_bounds__(256) core_present_kernel(const uint32_t *level
     if ((threadIdx.x & 31) == 0 && k < n_buckets) present[k >> 5] = w;
 }
 
-// guides -> core order; core_start[] = exclusive scan of the core histogram, cursor[] a copy of it
-// (scan_fixup_kernel's second output).  The guide that lands first in a core's segment becomes the
-// core's record, flagged when the core holds more.
-__global__ void __launch_bounds__(256) core_sort_kernel(const uint2 *guides, uint32_t n_guides, int cl, int dl,
-                                                        const uint32_t *core_start, uint32_t *cursor, uint2 *sorted, uint2 *core_rec) {
+// One guide per occupied core stands for the core (whichever claims it first): its record is what
+// the gather copies.  The other guides of a shared core (5 % of 100 k guides) are listed as extras.
+__global__ void __launch_bounds__(256) core_claim_kernel(const uint2 *guides, uint32_t n_guides, int cl, int dl, uint32_t *claim,
+                                                         uint2 *core_rec, uint32_t *extras, uint32_t *n_extras) {
     const uint32_t g = blockIdx.x * 256u + threadIdx.x;
     if (g >= n_guides) return;
     const uint2 G = __ldg(&guides[g]);
     const uint32_t cmask = (1u << cl) - 1, dmask = (1u << dl) - 1;
     const uint32_t key = (((G.x >> dl) & cmask) << cl) | ((G.y >> dl) & cmask);
-    const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
-    const uint2 rec = make_uint2(spread_bits(dlo) | (spread_bits(dh) << 1), g);
-    const uint32_t c0 = core_start[key], cnt = core_start[key + 1] - c0;
-    const uint32_t pos = atomicAdd(&cursor[key], 1u);
-    sorted[pos] = rec;
-    if (pos == c0) core_rec[key] = make_uint2(rec.x | (cnt > 1u ? kCoreMulti : 0u), g);  // the core's first guide stands for it
+    if (atomicAdd(&claim[key], 1u) == 0u) {
+        const uint32_t dh = G.x & dmask, dlo = G.y & dmask;
+        core_rec[key] = make_uint2(spread_bits(dlo) | (spread_bits(dh) << 1), g);
+    } else {
+        extras[atomicAdd(n_extras, 1u)] = g;
+    }
+}
+
+// The extras are filed the round-1 way -- one warp per guide over the variant list, one returning
+// atomic per entry -- but from the END of every bucket backwards (back[] starts at the bucket ends),
+// behind the entries the gather writes from the front.
+__global__ void __launch_bounds__(256) idx_extras_kernel(const IdxArgs a, const uint32_t *extras, const uint32_t *n_extras) {
+    const uint32_t cmask = (1u << a.cl) - 1, dmask = (1u << a.dl) - 1;
+    const uint32_t lane = threadIdx.x & 31, warps = gridDim.x * 8u, n = *n_extras;
+    uint2 *ent = reinterpret_cast<uint2 *>(a.keys);
+    for (uint32_t x = blockIdx.x * 8u + (threadIdx.x >> 5); x < n; x += warps) {
+        const uint32_t g = __ldg(&extras[x]);
+        const uint2 G = __ldg(&a.guides[g]);
+        const uint32_t ch = (G.x >> a.dl) & cmask, cl_ = (G.y >> a.dl) & cmask;
+        const uint32_t letters = spread_bits(G.y & dmask) | (spread_bits(G.x & dmask) << 1);
+        for (uint32_t v = lane; v < a.n_variants; v += 32) {
+            const uint32_t var = __ldg(&a.variants[v]);
+            const uint32_t xh = var & 0xffff, xl = var >> 16;
+            const uint32_t key = ((ch ^ xh) << a.cl) | (cl_ ^ xl);
+            if (a.part_on && (key >> a.part_shift) != a.part_ix) continue;
+            const uint32_t pos = atomicSub(&a.back[key], 1u) - 1u;
+            ent[pos] = make_uint2(letters | (min((uint32_t)__popc(xh | xl) + a.cbias, 15u) << 20), g);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const GatherArgs a) {
     __shared__ uint32_t s_rows[(kGatherMaxRows + 1) * 32];
     __shared__ uint32_t s_var[kGatherMaxVar];
-    __shared__ uint16_t s_list[kGatherWarps][kGatherMaxVar];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = a.tile_lo + blockIdx.x / kGatherSub, sub = blockIdx.x % kGatherSub;
     const uint32_t hiB = tile >> 5, loB = tile & 31u;
@@ -996,36 +1014,40 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const 
             const uint32_t rm = __ldg(&a.row_mask[row]);
             w = __ldg(&a.present[((hiB ^ (rm >> 5)) << 10) | (hiA << 5) | (loB ^ (rm & 31u))]);
         }
-        s_rows[(row << 5) | (hiA ^ (row & 31u))] = w;  // swizzled: the probes of a round hit different banks
+        // swizzled (the probes of a round hit different banks) and bit-reversed (a rotate by the
+        // probe's bit index brings its bit to the top, where one funnel shift files it)
+        s_rows[(row << 5) | (hiA ^ (row & 31u))] = __brev(w);
     }
     for (uint32_t x = threadIdx.x; x < (uint32_t)kGatherMaxVar; x += kGatherWarps * 32) s_var[x] = __ldg(&a.var_mask[x]);
     uint32_t pk[kGatherPerLane];
 #pragma unroll
     for (int r = 0; r < kGatherPerLane; r++) pk[r] = __ldg(&a.probe[lane * kGatherPerLane + r]);
     __syncthreads();
-    uint16_t *list = s_list[warp];
+    const uint32_t *my_var = s_var + lane * kGatherPerLane;
     constexpr uint32_t kPerCta = 1024 / kGatherSub;
-    auto key_of = [&](uint32_t b) {
-        const uint32_t abits = sub * kPerCta + b;  // hi plane bits << 5 | lo plane bits of the A half
-        return (hiB << 15) | ((abits >> 5) << 10) | (loB << 5) | (abits & 31u);
-    };
+    const uint32_t key_fixed = (hiB << 15) | (loB << 5);
     unsigned long long bad = 0;
-    uint32_t v0 = __ldg(&a.ent_off[key_of(warp)]), v1 = __ldg(&a.ent_off[key_of(warp) + 1]);
+    // bucket b of the CTA: A half = hi plane bits << 5 | lo plane bits
+    uint32_t abits = sub * kPerCta + warp;
+    uint32_t key = key_fixed | ((abits >> 5) << 10) | (abits & 31u);
+    uint32_t v0 = __ldg(&a.ent_off[key]), v1 = __ldg(&a.ent_off[key + 1]);
     for (uint32_t b = warp; b < kPerCta; b += kGatherWarps) {
-        const uint32_t abits = sub * kPerCta + b;
-        const uint32_t key = key_of(b);
         const uint32_t start = v0 & ~1u, size = (v1 & ~1u) - start - (v0 & 1u);
+        const uint32_t abits_now = abits, key_now = key;
+        abits += kGatherWarps;
+        key = key_fixed | ((abits >> 5) << 10) | (abits & 31u);
         if (b + kGatherWarps < kPerCta) {  // the next bucket's bounds travel while this one is gathered
-            v0 = __ldg(&a.ent_off[key_of(b + kGatherWarps)]);
-            v1 = __ldg(&a.ent_off[key_of(b + kGatherWarps) + 1]);
+            v0 = __ldg(&a.ent_off[key]);
+            v1 = __ldg(&a.ent_off[key + 1]);
         }
-        uint32_t found = 0;
+        uint32_t found = 0;  // probe r ends up at bit 13 - r
 #pragma unroll
         for (int r = 0; r < kGatherPerLane; r++) {
-            const uint32_t t = pk[r] ^ abits;
-            found |= (__funnelshift_r(s_rows[t >> 5], 0u, t) & 1u) << r;  // the shift uses t & 31
+            const uint32_t t = pk[r] ^ abits_now;
+            const uint32_t w = s_rows[t >> 5];
+            found = __funnelshift_l(__funnelshift_l(w, w, t), found, 1);  // rotate by t & 31, then shift the top bit in
         }
-        // occupied neighbours in variant order -> list
+        // place of the lane's first entry = occupied neighbours of the lower lanes (variant order)
         const uint32_t n = (uint32_t)__popc(found);
         uint32_t inc = n;
 #pragma unroll
@@ -1033,61 +1055,27 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const 
             const uint32_t t = __shfl_up_sync(kFull, inc, d);
             if (lane >= (uint32_t)d) inc += t;
         }
-        const uint32_t total = __shfl_sync(kFull, inc, 31);
-        uint32_t at = inc - n;
+        if (lane == 31 && inc > size) bad++;
+        uint2 *dst = a.ent + start + (inc - n);
+        // the records of the occupied cores -> the bucket; up to four loads in flight per lane
         while (found) {
-            const uint32_t r = (uint32_t)__ffs((int)found) - 1u;
-            found &= found - 1u;
-            list[at++] = (uint16_t)(lane * kGatherPerLane + r);
-        }
-        __syncwarp();
-        // their guides -> the bucket.  Entry i of the list becomes entry i of the bucket: the record of
-        // its core IS a guide (the first one filed under that core), so there are no ranks to compute.
-        // The few cores that hold more guides (5 % for 100 k guides) are flagged; their other guides
-        // are appended behind the `total` regular entries, one flagged core at a time.
-        uint32_t ext = start + total;
-        for (uint32_t t0 = 0; t0 < total; t0 += 64) {
-            uint2 rec[2];
-            uint32_t key2[2], bias[2];
+            uint2 rec[4];
+            uint32_t bias[4];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t t = t0 + 32u * h + lane;
-                rec[h] = make_uint2(0u, 0u); key2[h] = 0; bias[h] = 0;
-                if (t < total) {
-                    const uint32_t m = s_var[list[t]];
-                    key2[h] = key ^ (m & 0xfffffu);
-                    rec[h] = __ldg(&a.core_rec[key2[h]]);
-                    bias[h] = m & 0xf00000u;
+            for (int i = 0; i < 4; i++) {
+                rec[i] = make_uint2(0u, 0u); bias[i] = 0xffffffffu;
+                if (found) {
+                    const uint32_t bit = 31u - (uint32_t)__clz((int)found);
+                    found ^= 1u << bit;
+                    const uint32_t m = my_var[(kGatherPerLane - 1) - bit];
+                    rec[i] = __ldg(&a.core_rec[key_now ^ (m & 0xfffffu)]);
+                    bias[i] = m & 0xf00000u;
                 }
             }
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t t = t0 + 32u * h + lane;
-                if (t < total) a.ent[start + t] = make_uint2((rec[h].x & ~kCoreMulti) | bias[h], rec[h].y);
-                const bool multi = (rec[h].x & kCoreMulti) != 0u;
-                if (__any_sync(kFull, multi)) {
-                    // every flagged lane fetches its core's segment bounds at once; a scan over the
-                    // extra guides (segment size - 1) places them behind the regular entries
-                    uint32_t c0 = 0, extra = 0;
-                    if (multi) { c0 = __ldg(&a.core_start[key2[h]]); extra = __ldg(&a.core_start[key2[h] + 1]) - c0 - 1u; }
-                    uint32_t inc = extra;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t u = __shfl_up_sync(kFull, inc, d);
-                        if (lane >= (uint32_t)d) inc += u;
-                    }
-                    const uint32_t at = ext + inc - extra;
-                    for (uint32_t g = 0; g < extra; g++) {
-                        const uint2 G = __ldg(&a.sorted[c0 + 1u + g]);
-                        a.ent[at + g] = make_uint2(G.x | bias[h], G.y);
-                    }
-                    ext += __shfl_sync(kFull, inc, 31);
-                }
-            }
+            for (int i = 0; i < 4; i++)
+                if (bias[i] != 0xffffffffu) *dst++ = make_uint2(rec[i].x | bias[i], rec[i].y);
         }
-        const uint32_t dst0 = ext;
-        __syncwarp();  // the list is rewritten for the next bucket
-        if (lane == 0 && dst0 - start != size) bad++;
     }
     if (bad) atomicAdd(a.err, bad);
 }
@@ -1142,8 +1130,8 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const char *build_mode = getenv("GUIDO_IDX_BUILD");
     const bool gather = entries && dp_counts && cl == 10 && variants.size() <= (size_t)kGatherMaxVar &&
                         !(build_mode && build_mode[0] == 's');
-    // gather scratch behind the levels: [present n_buckets/32][probe][var_mask][row_mask 128][sorted 2 n_guides][core_rec 2 n_buckets]
-    const int64_t gather_words = gather ? (int64_t)n_buckets / 32 + 2 * kGatherMaxVar + 128 + 2 * n_guides + 2 + 2 * (int64_t)n_buckets : 0;
+    // gather scratch behind the levels: [present n_buckets/32][probe][var_mask][row_mask 128][extras n_guides + counter][core_rec 2 n_buckets]
+    const int64_t gather_words = gather ? (int64_t)n_buckets / 32 + 2 * kGatherMaxVar + 128 + n_guides + 4 + 2 * (int64_t)n_buckets : 0;
     const int64_t bucket_words = (int64_t)n_scan + 2 * (int64_t)n_buckets + n_scan_blocks + (int64_t)variants.size() + 16 + level_words +
                                  gather_words;
     int rc;
@@ -1271,24 +1259,28 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     if (entries && !gather) idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
     GatherArgs ga;
     if (gather) {
-        // guides in core order: the exact core histogram (level 0 of the convolution) is scanned in
-        // place -> first guide of each core, `fill` serves as the scatter cursor
+        // one guide per occupied core is claimed as the core's record; the others (cores shared by
+        // several guides) are scattered from the bucket ends backwards
         uint32_t *levels = d_var + ((variants.size() + 15) & ~(size_t)15);
         uint32_t *present = levels + level_words, *d_probe = present + n_buckets / 32, *d_gvar = d_probe + kGatherMaxVar,
                  *d_row = d_gvar + kGatherMaxVar;
-        uint2 *sorted = reinterpret_cast<uint2 *>(d_row + 128 + (((uintptr_t)(d_row + 128) >> 2) & 1u));
-        uint2 *core_rec = sorted + n_guides;  // n_buckets records, only read where `present` is set
+        uint32_t *extras = d_row + 128, *n_extras = extras + n_guides;
+        uint2 *core_rec = reinterpret_cast<uint2 *>(n_extras + 2 + (((uintptr_t)(n_extras + 2) >> 2) & 1u));
+        uint32_t *claim = fill;  // n_buckets words, free in gather mode
         GUIDO_CUDA(cudaMemcpyAsync(d_probe, g_probe.data(), kGatherMaxVar * 4, cudaMemcpyHostToDevice, stream));
         GUIDO_CUDA(cudaMemcpyAsync(d_gvar, g_var.data(), kGatherMaxVar * 4, cudaMemcpyHostToDevice, stream));
         GUIDO_CUDA(cudaMemcpyAsync(d_row, g_row.data(), g_row.size() * 4, cudaMemcpyHostToDevice, stream));
+        GUIDO_CUDA(cudaMemsetAsync(claim, 0, (size_t)n_buckets * 4, stream));
+        GUIDO_CUDA(cudaMemsetAsync(n_extras, 0, 4, stream));
         core_present_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(levels, n_buckets, present);
-        if ((rc = exclusive_scan_u32(levels, n_scan, sums, fill, stream))) return rc;
-        core_sort_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, levels, fill, sorted,
-                                                                                 core_rec);
-        ga.present = present; ga.core_rec = core_rec; ga.core_start = levels; ga.sorted = sorted; ga.ent_off = counts;
+        core_claim_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, claim, core_rec,
+                                                                                  extras, n_extras);
+        idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
+        idx_extras_kernel<<<bgrid, 256, 0, stream>>>(ia, extras, n_extras);
+        ga.present = present; ga.core_rec = core_rec; ga.ent_off = counts;
         ga.ent = reinterpret_cast<uint2 *>(keys); ga.probe = d_probe; ga.var_mask = d_gvar; ga.row_mask = d_row;
         ga.n_rows = (uint32_t)g_row.size(); ga.tile_lo = 0; ga.err = ds->d_counts + 3;
-        if (n_launches) *n_launches += 5;
+        if (n_launches) *n_launches += 4;
     }
     // walk buckets warp-wide when they are large; GUIDO_OT_WIDE=0/1 overrides (tuning, tests)
     const char *force = getenv("GUIDO_OT_WIDE");

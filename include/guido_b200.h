@@ -182,6 +182,17 @@ int guido_offtarget_search_packed(guido_image *img, const char *protos, int64_t 
                                   int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
                                   uint64_t *hits, int64_t cap, int64_t *n_hits, uint8_t *raw_flags,
                                   guido_stats *stats);
+
+/* The same search with the hit list as CSR by guide, 4.1 bytes per hit on the wire: gpos[i] (cap
+ * elements) = global window start of hit i, bit i of strand_bits (cap / 32 + 1 words) = its strand,
+ * hits guide_offsets[g] .. guide_offsets[g + 1] belong to guide g (n_guides + 1 entries), inside a
+ * guide ordered by (position, strand) -- the order of the other two formats.  What
+ * run_bowtie's per-guide dict (guido/off_targets.py:201-225) is built from; guido_hits_expand turns
+ * guide << 33 | gpos << 1 | strand back into full records. */
+int guido_offtarget_search_csr(guido_image *img, const char *protos, int64_t n_guides, const char *pam,
+                               int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t algo,
+                               uint32_t *gpos, uint32_t *strand_bits, int64_t cap, int64_t *guide_offsets,
+                               int64_t *n_hits, uint8_t *raw_flags, guido_stats *stats);
 /* packed records -> guido_ot_hit records, planes cut from the HOST copy of the image exactly as the
  * kernels cut them from HBM (host-only; pam_len = length of the PAM the search used).  Feeds the
  * record building of run_bowtie (guido/off_targets.py:201-225). */

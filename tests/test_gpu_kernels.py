@@ -493,3 +493,24 @@ def test_pam_scan_one_pass_equals_two_pass(native, monkeypatch, pam, mode):
                                             rv.ctypes.data, cap, ctypes.byref(nr), None)
     assert rc == native.ERR_CAPACITY and nf.value == len(fw2) and nr.value == len(rv2)
     assert np.all(fw[cap:] == 0xdeadbeef) and np.all(rv[cap:] == 0xdeadbeef)
+
+
+@pytest.mark.parametrize("n_guides", [0, 1, 333])
+def test_offtarget_csr_format(native, n_guides):
+    """CSR by guide (positions + strand bits + per-guide offsets) holds exactly the packed hit list,
+    including guides without hits at either end and an empty guide set"""
+    contigs = util.synthetic_contigs(52, [220000, 40000], n_runs=3)
+    rng = np.random.default_rng(29)
+    img = native.Image.from_seqs(contigs).upload()
+    protos = _protos_from_genome(rng, contigs, n_guides, mutate=2) if n_guides else []
+    if n_guides > 10:
+        protos[0] = "ACGTTGCAACGTTGCAACGT"      # (most sampled guides have no NGG site anyway: many empty segments)
+        protos[-1] = "TTTTTTTTTTGGGGGGGGGG"
+    for algo in (native.OT_TABLE, native.OT_SCAN):
+        packed, f1 = img.offtarget_search(protos, algo=algo, packed=True)
+        offs, gpos, bits, f2 = img.offtarget_search_csr(protos, algo=algo)
+        assert offs[0] == 0 and offs[-1] == len(packed) == len(gpos) and np.all(np.diff(offs) >= 0)
+        assert np.array_equal(native.Image.csr_to_packed(offs, gpos, bits), packed)
+        assert np.array_equal(f1, f2)
+    if n_guides > 10:
+        assert len(packed) > 0
