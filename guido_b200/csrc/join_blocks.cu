@@ -66,7 +66,7 @@ struct __align__(16) BjStage {
 struct __align__(16) BjWarpSmem {
     BjStage st[2];
     uint4 meta[kBjGroupMax];                     // per bucket of the ticket: {first block, blocks, first entry, entries}
-    uint4 q[kBjQueue];                           // parked results: {hit bits of windows 0..31, 32..63, entry, block}
+    uint4 q[kBjQueue];                           // parked results: {hit bits of windows 0..31, 32..63, guide, block}
     unsigned long long bar[2];                   // mbarriers: "stage s is full"
 };
 
@@ -173,7 +173,7 @@ __device__ __noinline__ uint32_t bj_flush(const BjArgs &a, BjWarpSmem &ws, uint3
         uint4 s0 = make_uint4(0, 0, 0, 0);
         uint32_t r0 = v.x, r1 = v.y;
         if (n) {  // the common case is one hit in the result
-            guide = __ldg(&a.ent[v.z]).y;
+            guide = v.z;
             const uint32_t first = r0 ? (uint32_t)__ffs((int)r0) - 1u : 32u + (uint32_t)__ffs((int)r1) - 1u;
             s0 = __ldg(&a.slots[(size_t)v.w * 64u + first]);
             if (r0) r0 &= r0 - 1u; else r1 &= r1 - 1u;
@@ -217,8 +217,11 @@ __device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const B
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     const bool valid = r_ix < R;
     const uint32_t e = e_first + (valid ? r_ix : 0u);
-    uint32_t w = 15u << 20;  // bias 15 never hits
-    if (valid) w = e_rel + r_ix < (uint32_t)kBjCapEnt ? st.ent[e_rel + r_ix].x : __ldg(&a.ent[e]).x;
+    // the lane's entry: letters | bias, and the guide it stands for (kept for the hit records: the
+    // flush does not have to fetch it again from global memory)
+    uint2 ent = make_uint2(15u << 20, 0u);  // bias 15 never hits
+    if (valid) ent = e_rel + r_ix < (uint32_t)kBjCapEnt ? st.ent[e_rel + r_ix] : __ldg(&a.ent[e]);
+    const uint32_t w = ent.x;
     LaneKey k;
 #pragma unroll
     for (int j = 0; j < 10; j++) k.p[j] = st.blk + s_ix * (kBjBlockWords / 2) + ((w >> (2 * j)) & 3u);
@@ -242,7 +245,7 @@ __device__ __forceinline__ void bj_pass(const BjArgs &a, BjWarpSmem &ws, const B
         const bool has = (rx | ry) != 0u;
         const uint32_t hm = __ballot_sync(kFull, has);
         if (hm) {
-            if (has) ws.q[qn + (uint32_t)__popc(hm & lt)] = make_uint4(rx, ry, e, gblk0 + it * S + s_ix);
+            if (has) ws.q[qn + (uint32_t)__popc(hm & lt)] = make_uint4(rx, ry, ent.y, gblk0 + it * S + s_ix);
             qn += (uint32_t)__popc(hm);
             if (qn >= 32u) { __syncwarp(); qn = bj_flush(a, ws, qn, false); }
         }

@@ -457,15 +457,20 @@ __global__ void __launch_bounds__(kMmejWarps * 32) mmej_fast_kernel(const FastAr
                     bool alive = j < first + n_k;
                     const uint32_t tg = ((alive ? cand[j] : 0u) ^ kTupleFlip) | kTupleGuard;
                     const uint32_t in_smem = min(first, (uint32_t)kFastParents);
-                    for (uint32_t i = 0; i < in_smem; i += 4) {  // (entries past `first` in the last group are this class's own: never a superset)
+                    // y = ~(tg - parent) & guard is zero iff the parent contains the candidate: four parents
+                    // per 128-bit load, one unsigned minimum tree and one compare per group; the vote that
+                    // ends the scan early (every lane already eliminated) runs every fourth group
+                    const uint32_t full = in_smem & ~3u;
+                    uint32_t i = 0;
+                    for (; i < full; i += 4) {
                         const uint4 p = *reinterpret_cast<const uint4 *>(&s.parents[i]);
-                        const bool h0 = ((tg - p.x) & kTupleGuard) == kTupleGuard;
-                        const bool h1 = ((tg - p.y) & kTupleGuard) == kTupleGuard && i + 1 < first;
-                        const bool h2 = ((tg - p.z) & kTupleGuard) == kTupleGuard && i + 2 < first;
-                        const bool h3 = ((tg - p.w) & kTupleGuard) == kTupleGuard && i + 3 < first;
-                        alive = alive && !(h0 | h1 | h2 | h3);
-                        if (!__any_sync(kFullMask, alive)) break;
+                        const uint32_t y = min(min(~(tg - p.x) & kTupleGuard, ~(tg - p.y) & kTupleGuard),
+                                               min(~(tg - p.z) & kTupleGuard, ~(tg - p.w) & kTupleGuard));
+                        alive = alive && y != 0u;
+                        if ((i & 12u) == 12u && !__any_sync(kFullMask, alive)) { i = in_smem; break; }
                     }
+                    for (; i < in_smem; i++)  // the last, partial group
+                        alive = alive && (~(tg - s.parents[i]) & kTupleGuard) != 0u;
                     for (uint32_t i = in_smem; i < first; i++) {
                         const uint32_t pp = cand[i] ^ kTupleFlip;
                         alive = alive && ((tg - pp) & kTupleGuard) != kTupleGuard;

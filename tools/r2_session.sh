@@ -18,14 +18,14 @@ if want ncu; then
   $B --no-pam --steps 2 --warmup 3 > gpurun_out/plain_ot.json 2> gpurun_out/plain_ot.err || { echo plain ot failed; exit 1; }
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2_launches_bench.csv \
       $B --no-pam --steps 2 --warmup 3 > gpurun_out/ncu_list.log 2>&1
-  GUIDO_OT_OVERLAP=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ot_join_blocks -s 3 -c 1 -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ot_join_blocks|idx_gather" -s 6 -c 2 -f \
       -o gpurun_out/r2_join $B --no-pam --steps 1 --warmup 3 > gpurun_out/ncu_join.log 2>&1
   $B --workload pam --genome agam --steps 4 --warmup 3 > gpurun_out/plain_pam.json 2> gpurun_out/plain_pam.err || { echo plain pam failed; exit 1; }
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_pam_launches.csv \
       $B --workload pam --genome agam --steps 2 --warmup 3 > gpurun_out/ncu_pam_list.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:pam_onepass -s 6 -c 1 -f -o gpurun_out/r2_pam_onepass \
       $B --workload pam --genome agam --steps 4 --warmup 3 > gpurun_out/ncu_pam_full.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mmej_kernel -s 1 -c 1 -f -o gpurun_out/r2_mmej \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mmej_fast_kernel -s 1 -c 1 -f -o gpurun_out/r2_mmej \
       $B --workload mmej --steps 1 --warmup 1 > gpurun_out/ncu_mmej.log 2>&1
   ls -la gpurun_out | tail -14
 fi
