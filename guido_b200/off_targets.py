@@ -103,15 +103,23 @@ def records_from_hits(guides, hits, raw_flags, image, pam):
         # Upstream quirk, reproduced: with a PAM pattern without N a perfect alignment reaches
         # _parse_mismatches("") and run_bowtie dies there (off_targets.py:73).
         raise ValueError("not enough values to unpack (expected 2, got 1)")
-    for h in range(len(hits)):
+    # every guide that owns a hit has a key (off_targets.py:183-184) ...
+    for ix in np.unique(hits["guide"]).tolist():
+        out.setdefault(int(ix), [])
+    # ... but guido keeps an alignment only on another chromosome (off_targets.py:199), and only if it
+    # carries at least one mismatch entry: both tests are done for all hits at once, the Python loop
+    # below sees the survivors only (a locus' hits are mostly the guides' own sites)
+    name_ix = {n: i for i, n in enumerate(names)}
+    g_chrom = np.array([name_ix.get(str(G.guide_chrom), -1) for G in guides], dtype=np.int64)
+    g_start = np.array([int(G.guide_start) for G in guides], dtype=np.int64)
+    hg = hits["guide"].astype(np.int64)
+    keep = (g_chrom[hg] != contig_ix) & (g_start[hg] != offset + 1)
+    if not ambiguous_pam:
+        keep &= differs.any(axis=1)
+    for h in np.nonzero(keep)[0].tolist():
         ix = int(hits["guide"][h])
-        G = guides[ix]
         chrom = names[int(contig_ix[h])]
         start = int(offset[h])
-        out.setdefault(ix, [])
-        # guido keeps an alignment only on another chromosome (off_targets.py:199)
-        if not (str(G.guide_chrom) != chrom and int(G.guide_start) != start + 1):
-            continue
         window = letters[h].tobytes().decode()
         mismatches = {}
         for k in reversed(ambiguous_pam):       # descending position = ascending bowtie offset

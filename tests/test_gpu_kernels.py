@@ -496,7 +496,7 @@ def test_pam_scan_one_pass_equals_two_pass(native, monkeypatch, pam, mode):
 
 
 @pytest.mark.parametrize("n_guides", [0, 1, 333])
-def test_offtarget_csr_format(native, n_guides):
+def test_offtarget_csr_format(native, monkeypatch, n_guides):
     """CSR by guide (positions + strand bits + per-guide offsets) holds exactly the packed hit list,
     including guides without hits at either end and an empty guide set"""
     contigs = util.synthetic_contigs(52, [220000, 40000], n_runs=3)
@@ -514,3 +514,12 @@ def test_offtarget_csr_format(native, n_guides):
         assert np.array_equal(f1, f2)
     if n_guides > 10:
         assert len(packed) > 0
+        # the 8-byte records are sorted by the segmented sort or, for guides with very long lists, by the
+        # key-only radix sort (GUIDO_SORT=radix forces it): same list; and it is the full records' order
+        monkeypatch.setenv("GUIDO_SORT", "radix")
+        p2, _ = img.offtarget_search(protos, algo=native.OT_TABLE, packed=True)
+        o2, g2, b2, _ = img.offtarget_search_csr(protos, algo=native.OT_TABLE)
+        monkeypatch.delenv("GUIDO_SORT")
+        full, _ = img.offtarget_search(protos, algo=native.OT_TABLE)
+        assert np.array_equal(p2, packed) and np.array_equal(o2, offs) and np.array_equal(g2, gpos) and np.array_equal(b2, bits)
+        assert np.array_equal(img.expand_hits(packed), full)
