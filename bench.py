@@ -423,38 +423,94 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
                                  d_hits.data_ptr(), cap, d_count.data_ptr(), R.stream.cuda_stream)
 
     stride = 0
+    n_slices = 1
+    merge_how = None
     if R.world > 1:
-        # the merge's slot per rank is sized from a first search (the largest per-rank count + 10 %):
-        # a slot that is cut shows in its header, the check after the timed region raises
-        search()
-        stride = int(R.allmax(float(d_count.item())) * 1.1) + 4096
-        d_send = torch.empty(stride, dtype=torch.int64, device=R.dev)
-        d_gath = torch.empty(R.world * stride, dtype=torch.int64, device=R.dev)
-        d_merged = torch.empty(R.world * stride, dtype=torch.int64, device=R.dev)
+        # The merge: every rank searches its key range in n_slices slices; behind the join of a slice its
+        # hits are packed to the 8-byte wire format behind a header word (count, read on the device), and a
+        # second stream copies that slot straight into every rank's receive buffer (CUDA IPC peer buffers:
+        # copy engines over NVLink, no SM needed) WHILE the next slice is searched -- an NCCL all-gather's
+        # kernels would queue behind the join, which fills every SM.  One tiny all-reduce orders the step,
+        # one concat makes the list contiguous.  No host round trip inside the step.  The slot per
+        # (slice, rank) is sized from a first search (largest count + 10 %): a slot that is cut shows in
+        # its header, the check after the timed region raises.  GUIDO_BENCH_MERGE=nccl: one padded NCCL
+        # all-gather per slice instead of the peer copies.
+        sliced_ok = algo in (N.OT_AUTO, N.OT_TABLE) and table is not None
+        n_slices = int(os.environ.get("GUIDO_BENCH_SLICES", "2")) if sliced_ok else 1
+        while n_slices > 1 and n_slices * R.world > 32:   # a slice is a whole number of 1/32s of the key space
+            n_slices //= 2
+        slice_cap = cap // n_slices
+        d_counts = torch.zeros(n_slices, dtype=torch.int64, device=R.dev)
+        events = [torch.cuda.Event() for _ in range(n_slices)]
+        for e in events:
+            e.record(R.stream)
+        done = torch.cuda.Event()
+
+        def search_slices(d_send=None):
+            if sliced_ok:
+                img.offtarget_search_sliced_dev(d_guides.data_ptr(), n_guides, PAM, OT_KW["core_length"], OT_KW["core_mismatches"],
+                                                OT_KW["total_mismatches"], n_slices, d_hits.data_ptr(), slice_cap,
+                                                d_counts.data_ptr(), [e.cuda_event for e in events], R.stream.cuda_stream,
+                                                d_send.data_ptr() if d_send is not None else None, stride)
+            else:
+                search()
+                d_counts.copy_(d_count)
+                if d_send is not None:
+                    img.pack_send_dev(d_hits.data_ptr(), d_count.data_ptr(), stride - 1, d_send.data_ptr(), R.stream.cuda_stream)
+                events[0].record(R.stream)
+
+        search_slices()
+        stride = int(R.allmax(float(d_counts.max().item())) * 1.1) + 4096
+        d_send = torch.empty((n_slices, stride), dtype=torch.int64, device=R.dev)
+        d_merged = torch.empty(n_slices * R.world * stride, dtype=torch.int64, device=R.dev)
+        pg = None
+        if os.environ.get("GUIDO_BENCH_MERGE", "peer") != "nccl":
+            from guido_b200.parallel import PeerGather
+            try:
+                pg = PeerGather(R.dev, n_slices, stride)   # (raises on every rank or on none)
+            except RuntimeError as exc:  # no peer access between these GPUs: the collective does it
+                if R.rank == 0:
+                    print(f"{exc}; merging with NCCL all-gathers", file=sys.stderr)
+        merge_how = "peer copies (CUDA IPC, copy engines)" if pg is not None else "NCCL all-gather"
+        comm = pg.stream if pg is not None else torch.cuda.Stream(device=R.dev)
+        d_gath = None if pg is not None else torch.empty((n_slices, R.world * stride), dtype=torch.int64, device=R.dev)
+        gath_ptr = pg.local if pg is not None else d_gath.data_ptr()
 
     def step():
-        search()
-        if R.world > 1:
-            # merge of the per-GPU hit lists on the 8-byte wire format (guide << 33 | position << 1 |
-            # strand): the count rides in the header word, ONE padded all-gather over NVLink, concat
-            # on the device -- no host round trip inside the step
-            img.pack_send_dev(d_hits.data_ptr(), d_count.data_ptr(), stride - 1, d_send.data_ptr(), R.stream.cuda_stream)
-            dist.all_gather_into_tensor(d_gath, d_send)
-            img.concat_packed_dev(d_gath.data_ptr(), R.world, stride, d_merged.data_ptr(), d_merged.shape[0],
-                                  d_total.data_ptr(), R.stream.cuda_stream)
-            return launches_per_search + 2
-        return launches_per_search
+        if R.world == 1:
+            search()
+            return launches_per_search
+        search_slices(d_send)
+        if pg is not None:
+            for k in range(n_slices):
+                pg.send(k, d_send[k].data_ptr(), after=events[k])
+            pg.fence()
+            done.record(comm)
+        else:
+            with torch.cuda.stream(comm):
+                for k in range(n_slices):
+                    comm.wait_event(events[k])
+                    dist.all_gather_into_tensor(d_gath[k], d_send[k])
+                done.record(comm)
+        R.stream.wait_event(done)
+        img.concat_packed_dev(gath_ptr, n_slices * R.world, stride, d_merged.data_ptr(), d_merged.shape[0],
+                              d_total.data_ptr(), R.stream.cuda_stream)
+        return launches_per_search + n_slices + 1
 
     ms_step, launches, clocks = R.timed(step, steps, warmup)
     kt = img.kernel_times(steps)
     region_ms = R.allmax(float(np.mean(kt)))
     kernel_ms = region_ms
-    n_rank = int(d_count.item())
-    if n_rank > cap:
-        raise RuntimeError(f"hit buffer too small: {n_rank} > {cap}")
     if R.world > 1:
-        if n_rank > stride - 1:
-            raise RuntimeError(f"merge slot too small: {n_rank} > {stride - 1}")
+        per_slice = d_counts.cpu().tolist()
+        n_rank = int(sum(per_slice))
+        if max(per_slice) > min(stride - 1, slice_cap):
+            raise RuntimeError(f"merge slot too small: {max(per_slice)} > {min(stride - 1, slice_cap)}")
+    else:
+        n_rank = int(d_count.item())
+        if n_rank > cap:
+            raise RuntimeError(f"hit buffer too small: {n_rank} > {cap}")
+    if R.world > 1:
         hits = int(d_total.item())
         checksum = hits_checksum(torch, d_merged, hits)
     else:
@@ -471,16 +527,20 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
         os.environ["GUIDO_OT_OVERLAP"] = "0"
         try:
             for _ in range(2):
-                step()
+                search()
             torch.cuda.synchronize()
             for _ in range(steps):
                 R.flush.zero_()  # cold L2, like the timed steps
-                step()
+                search()
             torch.cuda.synchronize()
             kt = img.kernel_times(steps)
             kernel_ms = R.allmax(float(np.mean(kt)))
         finally:
             del os.environ["GUIDO_OT_OVERLAP"]
+
+    if R.world > 1 and pg is not None:
+        R.barrier()   # nobody copies into a buffer that is being released
+        pg.close()
 
     # end to end through the public API, host buffers in and out.  One GPU:
     # guido_offtarget_search_csr (letters up, search, device sort, key-presence flags, the hit list as CSR
@@ -530,7 +590,7 @@ def run_offtarget(R, img, guides_u8, algo, steps, warmup):
     return {"ms_per_step": ms_step, "launches": launches, "clocks": clocks, "hits": hits, "checksum": checksum, "table": table,
             "kernel_ms": kernel_ms, "region_ms": region_ms, "kernel_gbs_per_gpu": alg_bytes_rank / (kernel_ms * 1e-3) / 1e9,
             "alg_bytes_rank": alg_bytes_rank, "sites": int(R.allsum(sites)), "visited": int(R.allsum(visited)),
-            "pairs_scan": float(st.n_pairs) if not use_index else None, "blocks": blocks,
+            "pairs_scan": float(st.n_pairs) if not use_index else None, "blocks": blocks, "merge": merge_how, "n_slices": n_slices,
             "e2e_ms": e2e_ms, "h2d": h2d, "d2h": d2h}
 
 
@@ -890,6 +950,7 @@ def main():
                                        "(count in a header record) + device concat"
                                        if key_sharded else
                                        f"genome sharded x{world}, guides replicated, one padded NCCL all-gather of the hit lists"),
+                       "merge": (f"{r['n_slices']} key slices per rank; {r['merge']}" if world > 1 else None),
                        "hits": r["hits"], "hits_checksum": f"{r['checksum']:016x}",
                        "windows": r["sites"], "index_keys_compared": r["visited"],
                        "site_table": r["table"]},

@@ -46,6 +46,11 @@ _SIGNATURES = {
     "guido_device_count": (ctypes.c_int, []),
     "guido_host_alloc": (ctypes.c_int, [_i64, _P(_vp)]),
     "guido_host_free": (ctypes.c_int, [_vp]),
+    "guido_peer_alloc": (ctypes.c_int, [_i32, _i64, _P(_vp), _vp]),
+    "guido_peer_open": (ctypes.c_int, [_i32, _vp, _P(_vp)]),
+    "guido_peer_close": (ctypes.c_int, [_vp]),
+    "guido_peer_free": (ctypes.c_int, [_vp]),
+    "guido_copy_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     "guido_kernel_times": (ctypes.c_int, [_vp, _vp, _i32, _P(_i32)]),
     "guido_image_from_fasta": (ctypes.c_int, [_cp, _P(_vp)]),
     "guido_image_from_seqs": (ctypes.c_int, [_i32, _P(_cp), _P(_cp), _P(_i64), _P(_vp)]),
@@ -80,6 +85,8 @@ _SIGNATURES = {
     "guido_hits_sort_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "guido_hits_concat_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
     "guido_hits_pack_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "guido_offtarget_search_sliced_dev": (ctypes.c_int, [_vp, _vp, _i64, _cp, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp,
+                                                         _i64, _vp]),
     "guido_hits_pack_send_dev": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "guido_packed_concat_dev": (ctypes.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp]),
     "guido_encode_guides_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
@@ -496,6 +503,19 @@ class Image:
         check(lib().guido_offtarget_search_dev(self._h, d_guides, n_guides, pam.encode(), core_length,
                                                core_mismatches, total_mismatches, algo, d_hits, cap,
                                                d_count, stream))
+
+    def offtarget_search_sliced_dev(self, d_guides, n_guides, pam, core_length, core_mismatches, total_mismatches,
+                                    n_slices, d_hits, cap_per_slice, d_counts, events=None, stream=0, d_send=None,
+                                    send_stride=0):
+        """the table search slice by slice of the key range: hits of slice s at d_hits + s * cap_per_slice records,
+        count in d_counts[s]; events: raw cudaEvent_t handles (ints), recorded behind each slice's join (and behind
+        its packing into d_send + s * send_stride words when d_send is given)"""
+        ev = None
+        if events is not None:
+            ev = (ctypes.c_void_p * n_slices)(*[ctypes.c_void_p(int(e)) for e in events])
+        check(lib().guido_offtarget_search_sliced_dev(self._h, d_guides, n_guides, pam.encode(), core_length, core_mismatches,
+                                                      total_mismatches, n_slices, d_hits, cap_per_slice, d_counts, ev, d_send,
+                                                      send_stride, stream))
 
     def encode_guides_dev(self, d_letters, n_guides, d_out, d_bad=None, stream=0):
         """n x 20 letters in HBM -> n x {hi, lo} plane words in HBM; asynchronous"""

@@ -255,6 +255,54 @@ int guido_host_free(void *p) {
     return GUIDO_OK;
 }
 
+// ---- peer buffers: device memory another process on the node can write into (CUDA IPC) -----------
+int guido_peer_alloc(int32_t device, int64_t bytes, void **d_ptr, void *handle64) {
+    GUIDO_API_RANGE();
+    if (bytes < 0 || !d_ptr || !handle64) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C-ABI promises a 64-byte handle");
+    GUIDO_CUDA(cudaSetDevice(device));
+    *d_ptr = nullptr;
+    GUIDO_CUDA(cudaMalloc(d_ptr, (size_t)std::max<int64_t>(bytes, 256)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr); *d_ptr = nullptr;
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return GUIDO_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return GUIDO_OK;
+}
+
+int guido_peer_open(int32_t device, const void *handle64, void **d_ptr) {
+    GUIDO_API_RANGE();
+    if (!handle64 || !d_ptr) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    GUIDO_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GUIDO_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GUIDO_OK;
+}
+
+int guido_peer_close(void *d_ptr) {
+    GUIDO_API_RANGE();
+    if (d_ptr) GUIDO_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return GUIDO_OK;
+}
+
+int guido_peer_free(void *d_ptr) {
+    GUIDO_API_RANGE();
+    if (d_ptr) GUIDO_CUDA(cudaFree(d_ptr));
+    return GUIDO_OK;
+}
+
+int guido_copy_dev(void *dst, const void *src, int64_t bytes, void *stream) {
+    GUIDO_API_RANGE();
+    if (bytes < 0 || (bytes && (!dst || !src))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    if (bytes) GUIDO_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return GUIDO_OK;
+}
+
 int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t *n) {
     GUIDO_API_RANGE();
     if (!img || !img->dev || !out_ms || !n) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
@@ -497,6 +545,37 @@ int guido_offtarget_search_dev(guido_image *img, const void *d_guides, int64_t n
                                (uint64_t)cap, (unsigned long long *)d_count, nullptr, st, nullptr);
     return launch_ot_scan(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
                           (uint64_t)cap, (unsigned long long *)d_count, nullptr, nullptr, st, nullptr);
+}
+
+int guido_offtarget_search_sliced_dev(guido_image *img, const void *d_guides, int64_t n_guides, const char *pam,
+                                      int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t n_slices,
+                                      void *d_hits, int64_t cap_per_slice, void *d_counts, void *const *events,
+                                      void *d_send, int64_t send_stride, void *stream) {
+    GUIDO_API_RANGE();
+    int rc = need_device(img);
+    if (rc) return rc;
+    if (n_slices < 1 || n_slices > 8 || (n_slices & (n_slices - 1)) || cap_per_slice < 0 || !d_counts) {
+        set_error("n_slices must be 1, 2, 4 or 8"); return GUIDO_ERR_ARG;
+    }
+    OtParams op;
+    if ((rc = make_ot_params(pam, core_len, core_mm, total_mm, false, &op))) return rc;
+    DeviceState *ds = img->dev;
+    ScanRange r{(uint32_t)ds->shard_lo, (uint32_t)ds->shard_hi, (uint32_t)img->padded_bases, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    int algo = GUIDO_OT_TABLE;
+    if ((rc = resolve_ot_algo(img, op, r, n_guides, algo, st, &algo))) return rc;
+    if (algo != GUIDO_OT_TABLE) { set_error("the sliced search needs the PAM-site table"); return GUIDO_ERR_ARG; }
+    GUIDO_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n_slices * sizeof(unsigned long long), st));
+    OtSlices sl;
+    cudaEvent_t ev[8] = {};
+    sl.n = n_slices;
+    if (events) { for (int s = 0; s < n_slices; s++) ev[s] = (cudaEvent_t)events[s]; sl.events = ev; }
+    if (d_send) {
+        if (send_stride < 2) { set_error("send_stride must hold the header word and at least one record"); return GUIDO_ERR_ARG; }
+        sl.send = (unsigned long long *)d_send; sl.send_stride = (uint64_t)send_stride;
+    }
+    return launch_ot_join(ds, view_of(ds), op, r, (const uint2 *)d_guides, n_guides, (guido_ot_hit *)d_hits,
+                          (uint64_t)cap_per_slice, (unsigned long long *)d_counts, nullptr, st, nullptr, &sl);
 }
 
 int guido_encode_guides_dev(guido_image *img, const void *d_letters, int64_t n_guides, void *d_out, void *d_bad,

@@ -144,9 +144,22 @@ int launch_ot_index(DeviceState *ds, const PlanesView &pv, const OtParams &op, c
 int ensure_site_table(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
                       cudaStream_t stream, bool *built);
 void release_site_table(DeviceState *ds);
+// Optional: the handle's key range is cut into n equal slices that are indexed and joined one after the
+// other; slice s writes its hits to d_hits + s * cap (cap records each), its count to d_count[s], and
+// events[s] is recorded on the stream behind its join -- a caller can start sending slice s while the
+// later slices are still being searched.
+struct OtSlices {
+    int n = 1;
+    cudaEvent_t *events = nullptr;
+    // optional: behind the join of slice s its hits are packed into the 8-byte wire format at
+    // send + s * send_stride words (header word = count, then at most send_stride - 1 records), BEFORE
+    // events[s] is recorded: what remains for the caller's second stream are copies
+    unsigned long long *send = nullptr;
+    uint64_t send_stride = 0;
+};
 int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
                    unsigned long long *d_count, unsigned long long *d_site_count,
-                   cudaStream_t stream, int *n_launches);
+                   cudaStream_t stream, int *n_launches, const OtSlices *slices = nullptr);
 
 }  // namespace guido

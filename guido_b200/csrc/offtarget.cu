@@ -1108,7 +1108,8 @@ bool ot_index_applicable(const OtParams &op, int64_t n_guides) {
 // share of the key space this handle's site table covers); 0 / 0 = everything
 static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d_guides, int64_t n_guides,
                              bool entries, int part_bits, int part_ix, cudaStream_t stream, int *n_launches,
-                             OtIndex *out, const std::function<int(uint32_t, uint32_t)> *after_slice = nullptr) {
+                             OtIndex *out, const std::function<int(uint32_t, uint32_t)> *after_slice = nullptr,
+                             int min_slice_bits = 0) {
     if (!ot_index_applicable(op, n_guides)) {
         set_error("seed index needs 6 <= core_length <= 12, core_mismatches <= 3 and < 1.5e9 index entries");
         return GUIDO_ERR_ARG;
@@ -1155,7 +1156,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     const uint64_t used_slots = std::min<uint64_t>(n_slots, n_entries + (uint64_t)(pad / 2) * n_buckets);
     const char *smb = getenv("GUIDO_IDX_SLICE_MB");  // tuning knob
     const uint64_t slice_bytes = (uint64_t)(smb ? std::max(1, atoi(smb)) : 64) << 20;
-    int slice_bits = part_bits;  // a partition is a union of slices
+    int slice_bits = std::min(5, std::max(part_bits, min_slice_bits));  // a partition is a union of slices
     // (the gather writes whole lines in bucket order and needs no slices: one launch, then one join)
     while (!gather && slice_bits < 5 && slice_bits < cl && ((used_slots * 8) >> slice_bits) > slice_bytes) slice_bits++;
     // gather tables.  Lane l owns the probe slots 14 l .. 14 l + 13 and the compacted list follows slot
@@ -1461,10 +1462,22 @@ static bool ot_blocks_applicable(const DeviceState *ds, const OtParams &op, int6
 int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, const ScanRange &r,
                    const uint2 *d_guides, int64_t n_guides, guido_ot_hit *d_hits, uint64_t cap,
                    unsigned long long *d_count, unsigned long long *d_site_count,
-                   cudaStream_t stream, int *n_launches) {
-    if (r.hi <= r.lo || n_guides == 0) return GUIDO_OK;
+                   cudaStream_t stream, int *n_launches, const OtSlices *slices) {
+    const int n_out = slices && slices->n > 1 ? slices->n : 1;
+    auto record_all = [&]() -> int {  // nothing (more) to search: every slice is complete
+        for (int s = 0; slices && s < n_out; s++) {
+            if (slices->send) {
+                int rc = pack_send_device(ds, d_hits + (size_t)s * cap, d_count + s, slices->send_stride - 1,
+                                          slices->send + (size_t)s * slices->send_stride, stream);
+                if (rc) return rc;
+            }
+            if (slices->events) GUIDO_CUDA(cudaEventRecord(slices->events[s], stream));
+        }
+        return GUIDO_OK;
+    };
+    if (r.hi <= r.lo || n_guides == 0) return record_all();
     if (!site_table_matches(ds, op)) { set_error("PAM-site table was not built for these parameters"); return GUIDO_ERR_ARG; }
-    if (ds->site_n == 0) return GUIDO_OK;
+    if (ds->site_n == 0) return record_all();
     OtScanArgs a;
     const bool blocks = ot_blocks_applicable(ds, op, n_guides);
     a.pv = pv; a.op = op; a.r = r;
@@ -1519,8 +1532,34 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
     // GUIDO_OT_OVERLAP=0 (measurement knob): everything on the caller's stream, ONE join launch over
     // the whole table after the index is complete -- guido_kernel_times then reports the join
     // kernel timed alone (bench.py's roofline pass); the results are the same either way.
+    if (slices && blocks && (n_out & (n_out - 1)) == 0 && part_bits + __builtin_ctz((unsigned)n_out) <= 5) {
+        // sliced output: index and join slice after slice on the caller's stream; a slice's hits, count and
+        // event are complete before the next slice starts
+        int slice_bits = part_bits + __builtin_ctz((unsigned)n_out);
+        const uint32_t keys_per_out = part_keys / (uint32_t)n_out;
+        const std::function<int(uint32_t, uint32_t)> join_slice = [&](uint32_t key_lo, uint32_t key_hi) -> int {
+            const uint32_t s_ix = (key_lo - part_lo) / keys_per_out;
+            bj.hits = d_hits + (size_t)s_ix * cap;
+            bj.count = d_count + s_ix;
+            if (n_joins == 0) kev_begin(ds, stream);  // guido_kernel_times: first join launch .. last join done
+            int rc = join_keys(key_lo, key_hi, stream);
+            if (rc) return rc;
+            if ((key_hi - part_lo) % keys_per_out == 0) {  // the slice is complete
+                if (slices->send && (rc = pack_send_device(ds, d_hits + (size_t)s_ix * cap, d_count + s_ix, slices->send_stride - 1,
+                                                           slices->send + (size_t)s_ix * slices->send_stride, stream))) return rc;
+                if (slices->events) GUIDO_CUDA(cudaEventRecord(slices->events[s_ix], stream));
+            }
+            return GUIDO_OK;
+        };
+        int rc = build_guide_index(ds, op, d_guides, n_guides, blocks, part_bits, ds->site_part_ix, stream, n_launches, &a.ix,
+                                   &join_slice, slice_bits);
+        if (n_joins) kev_end(ds, stream);
+        if (rc) return rc;
+        if (n_launches) *n_launches += n_joins;
+        return GUIDO_OK;
+    }
     const char *ov = getenv("GUIDO_OT_OVERLAP");
-    if (ov && atoi(ov) == 0) {
+    if (slices || (ov && atoi(ov) == 0)) {  // (slices that cannot be honoured: everything lands in slice 0)
         int rc = build_guide_index(ds, op, d_guides, n_guides, blocks, part_bits, ds->site_part_ix, stream, n_launches, &a.ix);
         if (rc) return rc;
         kev_begin(ds, stream);
@@ -1528,7 +1567,7 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
         kev_end(ds, stream);
         if (rc) return rc;
         if (n_launches) *n_launches += n_joins;
-        return GUIDO_OK;
+        return record_all();
     }
     if (!ds->build_stream) {
         int lo_prio = 0, hi_prio = 0;

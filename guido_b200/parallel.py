@@ -51,6 +51,96 @@ def all_gather_hits(hits, group=None, device=None):
     return canonical_order(np.ascontiguousarray(merged).view(_native.OT_HIT_DTYPE).reshape(-1))
 
 
+class PeerGather:
+    """All-gather of fixed-size slots WITHOUT a collective: every rank owns a receive buffer of
+    ``n_slots x world x slot_words`` 8-byte words that the other ranks of the node map through CUDA IPC
+    (``guido_peer_alloc`` / ``guido_peer_open``), and ``send(slot, src)`` copies this rank's part straight
+    into every rank's buffer with ``world`` device-to-device copies on a stream of its own.  Between GPUs
+    those copies run on the copy engines over NVLink: they need no SM, so they proceed next to a kernel
+    that occupies every SM (the off-target join does) -- an NCCL all-gather's kernels would queue
+    behind it.  ``fence()`` orders the step: one 1-element all-reduce behind this rank's copies; when it
+    completes on a rank, every rank's copies into that rank's buffer have completed.
+
+    The layout is the one ``guido_packed_concat_dev`` reads: slot k, rank r at word
+    ``(k * world + r) * slot_words``, header word first."""
+
+    def __init__(self, device, n_slots, slot_words, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", device) if isinstance(device, int) else device
+        self.n_slots, self.slot_words = int(n_slots), int(slot_words)
+        self.words = self.n_slots * self.world * self.slot_words
+        lib = _native.lib()
+        self._lib = lib
+        # every rank takes part in every collective below whatever happens to it locally: a rank that
+        # cannot allocate or map says so in the agreement at the end, and then ALL ranks raise
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        err = None
+        if lib.guido_peer_alloc(self.dev.index, self.words * 8, ctypes.byref(ptr), handle) != 0:
+            err = _native.last_error()
+        self.local = ptr.value
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.dev)
+        handles = torch.empty((self.world, 64), dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(handles, mine, group=group)
+        good = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)
+        self.peers = [None] * self.world
+        if int(good.item()):
+            for r, h in enumerate(handles.cpu().numpy()):
+                if r == self.rank:
+                    self.peers[r] = self.local
+                    continue
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_uint8 * 64)(*h.tolist())
+                if lib.guido_peer_open(self.dev.index, buf, ctypes.byref(p)) != 0:
+                    err = _native.last_error()
+                    break
+                self.peers[r] = p.value
+        good = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(good, op=dist.ReduceOp.MIN, group=group)
+        if not int(good.item()):
+            self.close()
+            raise RuntimeError(f"peer buffers are not available on this node: {err or 'another rank failed'}")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        # one stream per destination: the copies to different ranks run on different copy engines
+        self.lanes = [torch.cuda.Stream(device=self.dev) for _ in range(self.world)]
+        self.lane_done = [torch.cuda.Event() for _ in range(self.world)]
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+
+    def send(self, slot, src_ptr, after=None):
+        """this rank's ``slot_words`` words at ``src_ptr`` -> its place in every rank's buffer; the copies start
+        behind the event ``after`` (the data is ready), one stream per destination"""
+        at = (slot * self.world + self.rank) * self.slot_words * 8
+        for r in range(self.world):
+            dst = (self.rank + r) % self.world   # start with the own buffer, then round the ring
+            lane = self.lanes[dst]
+            if after is not None:
+                lane.wait_event(after)
+            _native.check(self._lib.guido_copy_dev(self.peers[dst] + at, src_ptr, self.slot_words * 8, lane.cuda_stream))
+
+    def fence(self):
+        """behind it (on self.stream), every rank's sends issued before ITS fence have landed everywhere"""
+        import torch
+        import torch.distributed as dist
+        for lane, ev in zip(self.lanes, self.lane_done):
+            ev.record(lane)
+            self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.token, group=self.group)
+
+    def close(self):
+        lib = self._lib
+        for r, p in enumerate(self.peers):
+            if r != self.rank and p:
+                lib.guido_peer_close(p)
+        if self.local:
+            lib.guido_peer_free(self.local)
+        self.peers, self.local = [], None
+
+
 class DeviceMerge:
     """Off-target search of this rank's share + merge of all ranks' hits without leaving the GPUs
     (NCCL process group).  The letters go up once and are packed on the device, the hits stay in

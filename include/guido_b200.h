@@ -94,6 +94,17 @@ int guido_device_count(void);
  * slower).  Pinning is process-wide, so no device needs to be selected. */
 int guido_host_alloc(int64_t bytes, void **out);
 int guido_host_free(void *p);
+/* Peer buffers (multi-GPU merge over NVLink without a collective): device memory that the other
+ * ranks of the node can write into.  guido_peer_alloc returns the pointer and a 64-byte handle
+ * (cudaIpcMemHandle_t) to pass to the other processes; guido_peer_open maps a peer's buffer into
+ * this process (peer access is enabled on first use); guido_copy_dev is an asynchronous
+ * device-to-device copy on `stream` -- between GPUs it runs on the copy engines, next to kernels.
+ * Under the merge of the per-shard bowtie outputs a multi-GPU run_bowtie needs. */
+int guido_peer_alloc(int32_t device, int64_t bytes, void **d_ptr, void *handle64);
+int guido_peer_open(int32_t device, const void *handle64, void **d_ptr);
+int guido_peer_close(void *d_ptr);
+int guido_peer_free(void *d_ptr);
+int guido_copy_dev(void *dst, const void *src, int64_t bytes, void *stream);
 
 /* device time (ms, CUDA events on the launching stream) of the DOMINANT kernel of the last calls on
  * this handle -- PAM count+fill, or the off-target search kernel -- oldest first, up to 64 kept.
@@ -229,6 +240,19 @@ int guido_hits_sort_dev(guido_image *img, void *d_hits, int64_t n_hits, int64_t 
  * Under the merge of the per-shard bowtie outputs a multi-GPU run_bowtie needs. */
 int guido_hits_concat_dev(guido_image *img, const void *d_gathered, int32_t n_parts, int64_t stride,
                           void *d_out, int64_t cap, void *d_total, void *stream);
+/* guido_offtarget_search_dev with the handle's key range cut into n_slices (1, 2, 4, 8) equal slices
+ * that are indexed and joined one after the other: slice s writes its hits to d_hits + s *
+ * cap_per_slice records and its count to d_counts[s] (device u64 x n_slices), and events[s] (a
+ * cudaEvent_t each; may be NULL) is recorded on `stream` behind its join -- a multi-GPU caller starts
+ * the all-gather of slice s on a second stream while the later slices are still being searched.
+ * d_send (may be NULL): behind its join, slice s is also packed into the 8-byte wire format at d_send +
+ * s * send_stride words (guido_hits_pack_send_dev: header word = count) BEFORE events[s] is recorded, so
+ * that only copies are left for the second stream (kernels would queue behind the join, which fills
+ * every SM).  The union of the slices is the hit list of guido_offtarget_search_dev (GUIDO_OT_TABLE only). */
+int guido_offtarget_search_sliced_dev(guido_image *img, const void *d_guides, int64_t n_guides, const char *pam,
+                                      int32_t core_len, int32_t core_mm, int32_t total_mm, int32_t n_slices,
+                                      void *d_hits, int64_t cap_per_slice, void *d_counts, void *const *events,
+                                      void *d_send, int64_t send_stride, void *stream);
 /* The same merge on the 8-byte wire format (half the bytes over NVLink): guido_hits_pack_send_dev
  * writes *d_count (device u64) into d_send[0] and min(*d_count, cap) packed records behind it;
  * after the all-gather of the `stride`-word slots guido_packed_concat_dev copies the parts back to

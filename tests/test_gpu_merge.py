@@ -208,3 +208,38 @@ def test_packed_slots_concat(native):
             assert np.array_equal(np.sort(d_out[:total].cpu().numpy().view(np.uint64)), want)
         else:
             assert total == 2 * (stride - 1)   # both parts cut: the caller sees counts > stride - 1 in the headers
+
+
+@pytest.mark.parametrize("n_slices", [1, 2, 4])
+def test_sliced_search_union_and_events(native, monkeypatch, n_slices):
+    """the key range searched slice by slice (hits, count and event per slice) = the search in one go;
+    also on a partitioned handle and when the block join is not applicable (everything in slice 0)"""
+    import torch
+    img, protos = _case(native, seed=37, n=500)
+    dev = torch.device("cuda", int(img.info.device))
+    s = torch.cuda.current_stream(dev)
+    d_guides = torch.from_numpy(native.encode_guides(protos).view(np.int32)).to(dev)
+    for blocks, part in (("1", None), ("1", (1, 2)), ("0", None)):
+        monkeypatch.setenv("GUIDO_OT_BLOCKS", blocks)
+        if part:
+            img.site_table_partition(*part)
+        want, _ = img.offtarget_search(protos, algo=native.OT_TABLE, want_raw_flags=False)
+        cap = len(want) + 16
+        d_hits = torch.zeros((n_slices * cap, 4), dtype=torch.int32, device=dev)
+        d_counts = torch.full((n_slices,), -1, dtype=torch.int64, device=dev)
+        events = [torch.cuda.Event() for _ in range(n_slices)]
+        for e in events:
+            e.record(s)     # (creates the handle)
+        img.offtarget_search_sliced_dev(d_guides.data_ptr(), len(protos), "NGG", 10, 2, 4, n_slices, d_hits.data_ptr(), cap,
+                                        d_counts.data_ptr(), [e.cuda_event for e in events], s.cuda_stream)
+        for e in events:
+            e.synchronize()
+        counts = d_counts.cpu().numpy()
+        assert counts.sum() == len(want) and (counts >= 0).all()
+        if blocks == "1" and n_slices > 1:
+            assert (counts > 0).all()
+        got = np.concatenate([d_hits[k * cap:k * cap + int(c)].cpu().numpy().view(native.OT_HIT_DTYPE).reshape(-1)
+                              for k, c in enumerate(counts)])
+        got = got[np.lexsort((got["hi"] >> 31, got["gpos"], got["guide"]))]
+        assert np.array_equal(got, want)
+        img.site_table_partition(0, 1)

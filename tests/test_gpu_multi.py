@@ -57,3 +57,50 @@ def test_two_gpu_sharded_search_equals_one_gpu(tmp_path, partition):
     assert np.array_equal(out["hits"].view(_native.OT_HIT_DTYPE).reshape(-1), whole)
     assert np.array_equal(out["flags"], wflags)
     assert np.array_equal(out["fw"], wfw) and np.array_equal(out["rv"], wrv)
+
+
+PEER_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from guido_b200 import parallel
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"])); torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+n_slots, words = 3, 1000
+pg = parallel.PeerGather(dev, n_slots, words)
+ok = True
+for rep in range(3):
+    src = [torch.arange(words, dtype=torch.int64, device=dev) + 1000000 * rank + 1000 * k + rep for k in range(n_slots)]
+    torch.cuda.synchronize()
+    ready = torch.cuda.Event(); ready.record(torch.cuda.current_stream())
+    for k in range(n_slots):
+        pg.send(k, src[k].data_ptr(), after=ready if k % 2 else None)
+    pg.fence()
+    pg.stream.synchronize()
+    got = torch.empty(pg.words, dtype=torch.int64, device=dev)
+    from guido_b200 import _native as N
+    N.check(N.lib().guido_copy_dev(got.data_ptr(), pg.local, pg.words * 8, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy().reshape(n_slots, world, words)
+    for k in range(n_slots):
+        for r in range(world):
+            ok &= bool(np.array_equal(got[k, r], np.arange(words) + 1000000 * r + 1000 * k + rep))
+    dist.barrier()
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    open(sys.argv[2], "w").write("ok" if int(flag.item()) else "mismatch")
+dist.barrier(); pg.close(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(_native.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_gather_fills_every_ranks_buffer(tmp_path):
+    """slots copied into the other ranks' receive buffers (CUDA IPC) land where an all-gather would put them"""
+    (tmp_path / "worker.py").write_text(PEER_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29535", str(tmp_path / "worker.py"), ROOT, str(tmp_path / "out.txt")]
+    subprocess.run(cmd, check=True, timeout=300)
+    assert (tmp_path / "out.txt").read_text() == "ok"
