@@ -132,11 +132,25 @@ class Locus:
                                 strand, rel_cut, start + cut))
         return out
 
+    @staticmethod
+    def _long_pam(pam):
+        """A PAM of more than 8 letters does not fit the device matcher -- and cannot give a guide anyway:
+        the reference keeps a match only if its guide is 23 letters long, i.e. for 3-letter PAMs
+        (locus.py:316).  Its letters are still checked like the reference's iupac_dict lookup
+        (KeyError for a letter outside the table, locus.py:178); the result is "no match"."""
+        if len(pam) <= 8:
+            return False
+        for c in pam:
+            _native.pam_scan_seq("", c)   # raises KeyError for a letter outside the IUPAC table
+        return True
+
     def _find_guides_in_interval(self, sequence, start, pam):
         """Every guide whose PAM lies in ``sequence`` (coordinate of sequence[0] = ``start``):
         forward-strand guides by ascending PAM position, then reverse-strand ones; guides whose
         23-mer holds an N are dropped (locus.py:158-211).  The PAM scan runs on the GPU."""
         fwd_seq = sequence.upper()
+        if self._long_pam(pam):
+            return []
         pams_fw, pams_rv = _native.pam_scan_seq(fwd_seq, pam)
         return self._guides_from_pam_positions(fwd_seq, start, pam, pams_fw.tolist(), pams_rv.tolist())
 
@@ -144,6 +158,8 @@ class Locus:
         """PAM starts of both strands relative to the locus start.  A locus cut from a built genome
         is scanned in place on the genome image in HBM (``guido_pam_scan_region``: no sequence
         traffic at all); any other sequence goes to the device for the call (``guido_pam_scan_seq``)."""
+        if self._long_pam(pam):
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
         region = self._image_region
         if region is not None and self.genome is not None and getattr(self.genome, "bowtie_index", None):
             try:

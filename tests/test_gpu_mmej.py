@@ -129,3 +129,14 @@ def test_locus_layer_methods(native):
     with pytest.raises(NotImplementedError):
         loc.rank_guides()
     assert callable(loc.add_azimuth_score) and callable(loc.guides_detailed_table)
+
+
+def test_find_guides_with_a_pam_longer_than_the_matcher(native):
+    """a PAM of more than 8 letters gives no guides (the reference keeps 23-letter guides only) instead of
+    an error from the C layer; an unknown letter is still a KeyError"""
+    import guido_b200 as guido
+    rng = np.random.default_rng(10)
+    loc = guido.Locus(sequence=util.random_dna(rng, 300), name="c", start=1)
+    assert loc.find_guides(pam="NGGNGGNGG") == [] or len(loc.guides) == 0
+    with pytest.raises(KeyError):
+        loc.find_guides(pam="NGGNGGNGGZ")
