@@ -72,7 +72,7 @@ struct DeviceState {
     // second stream + events: the guide index is built slice by slice while the join already
     // works on the slices that are ready (launch_ot_join)
     cudaStream_t build_stream = nullptr, join_stream = nullptr;
-    cudaEvent_t ev_slice[34] = {};
+    cudaEvent_t ev_slice[36] = {};  // [0..33]: slices of the overlapped schedule; [34], [35]: the extras of the gathered index
 };
 
 int device_init(DeviceState *ds, int device);

@@ -1080,6 +1080,17 @@ __global__ void __launch_bounds__(kGatherWarps * 32, 5) idx_gather_kernel(const 
     if (bad) atomicAdd(a.err, bad);
 }
 
+// second and third stream of a handle (+ their events), created on first use
+static int ensure_side_streams(DeviceState *ds) {
+    if (ds->build_stream) return GUIDO_OK;
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    GUIDO_CUDA(cudaStreamCreateWithPriority(&ds->build_stream, cudaStreamNonBlocking, hi_prio));
+    GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->join_stream, cudaStreamNonBlocking));
+    for (auto &e : ds->ev_slice) GUIDO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return GUIDO_OK;
+}
+
 static void enumerate_variants(int cl, int cm, std::vector<uint32_t> *out) {
     // all (xh, xl) with popc(xh | xl) <= cm over cl positions; per chosen position 3 substitutions
     out->clear();
@@ -1259,6 +1270,7 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
     scan_fixup_kernel<<<n_scan_blocks, 1024, 0, stream>>>(counts, n_scan, sums, gather ? nullptr : fill, ia.pad_mask);
     if (entries && !gather) idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
     GatherArgs ga;
+    bool extras_on_side = false;
     if (gather) {
         // one guide per occupied core is claimed as the core's record; the others (cores shared by
         // several guides) are scattered from the bucket ends backwards
@@ -1277,7 +1289,15 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
         core_claim_kernel<<<(unsigned)((n_guides + 255) / 256), 256, 0, stream>>>(d_guides, (uint32_t)n_guides, cl, dl, claim, core_rec,
                                                                                   extras, n_extras);
         idx_back_cursor_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(counts, n_buckets, ia.pad_mask, back);
-        idx_extras_kernel<<<bgrid, 256, 0, stream>>>(ia, extras, n_extras);
+        // the extras are few (one warp per guide, a chain of 14 atomics each): they run on a side stream
+        // next to the gather, which writes the fronts of the buckets; the join waits for both
+        if ((rc = ensure_side_streams(ds))) return rc;
+        cudaStream_t side = stream == ds->build_stream ? ds->join_stream : ds->build_stream;
+        GUIDO_CUDA(cudaEventRecord(ds->ev_slice[34], stream));
+        GUIDO_CUDA(cudaStreamWaitEvent(side, ds->ev_slice[34], 0));
+        idx_extras_kernel<<<bgrid, 256, 0, side>>>(ia, extras, n_extras);
+        GUIDO_CUDA(cudaEventRecord(ds->ev_slice[35], side));
+        extras_on_side = true;
         ga.present = present; ga.core_rec = core_rec; ga.ent_off = counts;
         ga.ent = reinterpret_cast<uint2 *>(keys); ga.probe = d_probe; ga.var_mask = d_gvar; ga.row_mask = d_row;
         ga.n_rows = (uint32_t)g_row.size(); ga.tile_lo = 0; ga.err = ds->d_counts + 3;
@@ -1300,6 +1320,10 @@ static int build_guide_index(DeviceState *ds, const OtParams &op, const uint2 *d
             const uint32_t tiles = 1024u >> slice_bits;
             ga.tile_lo = p * tiles;
             idx_gather_kernel<<<tiles * kGatherSub, kGatherWarps * 32, 0, stream>>>(ga);
+            if (extras_on_side) {  // (once: the extras cover every slice)
+                GUIDO_CUDA(cudaStreamWaitEvent(stream, ds->ev_slice[35], 0));
+                extras_on_side = false;
+            }
         } else {
             idx_build_kernel<true><<<bgrid, 256, 0, stream>>>(ia);
         }
@@ -1569,13 +1593,7 @@ int launch_ot_join(DeviceState *ds, const PlanesView &pv, const OtParams &op, co
         if (n_launches) *n_launches += n_joins;
         return record_all();
     }
-    if (!ds->build_stream) {
-        int lo_prio = 0, hi_prio = 0;
-        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-        GUIDO_CUDA(cudaStreamCreateWithPriority(&ds->build_stream, cudaStreamNonBlocking, hi_prio));
-        GUIDO_CUDA(cudaStreamCreateWithFlags(&ds->join_stream, cudaStreamNonBlocking));
-        for (auto &e : ds->ev_slice) GUIDO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    { int rc = ensure_side_streams(ds); if (rc) return rc; }
     // joins alternate between the caller's stream and a sibling, so the tail of one slice's join
     // (its last, partly filled wave of CTAs) runs next to the head of the following one
     cudaStream_t sb = ds->build_stream, sj = ds->join_stream;
