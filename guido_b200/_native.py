@@ -51,6 +51,8 @@ _SIGNATURES = {
     "guido_peer_close": (ctypes.c_int, [_vp]),
     "guido_peer_free": (ctypes.c_int, [_vp]),
     "guido_copy_dev": (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    "guido_peer_send": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _i64, _vp]),
+    "guido_streams_join": (ctypes.c_int, [_vp, _vp, _i32, _vp]),
     "guido_kernel_times": (ctypes.c_int, [_vp, _vp, _i32, _P(_i32)]),
     "guido_image_from_fasta": (ctypes.c_int, [_cp, _P(_vp)]),
     "guido_image_from_seqs": (ctypes.c_int, [_i32, _P(_cp), _P(_cp), _P(_i64), _P(_vp)]),

@@ -303,6 +303,29 @@ int guido_copy_dev(void *dst, const void *src, int64_t bytes, void *stream) {
     return GUIDO_OK;
 }
 
+int guido_peer_send(void *const *dst_ptrs, void *const *streams, int32_t n, int32_t first, int64_t at_bytes, const void *src,
+                    int64_t bytes, void *after_event) {
+    GUIDO_API_RANGE();
+    if (n < 0 || (n && (!dst_ptrs || !streams)) || bytes < 0 || at_bytes < 0) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    for (int32_t k = 0; k < n && bytes; k++) {
+        const int32_t r = (first + k) % n;  // start with `first` (the own buffer), then round the ring
+        cudaStream_t st = (cudaStream_t)streams[r];
+        if (after_event) GUIDO_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)after_event, 0));
+        GUIDO_CUDA(cudaMemcpyAsync((char *)dst_ptrs[r] + at_bytes, src, (size_t)bytes, cudaMemcpyDefault, st));
+    }
+    return GUIDO_OK;
+}
+
+int guido_streams_join(void *const *streams, void *const *events, int32_t n, void *onto_stream) {
+    GUIDO_API_RANGE();
+    if (n < 0 || (n && (!streams || !events))) { set_error("bad arguments"); return GUIDO_ERR_ARG; }
+    for (int32_t k = 0; k < n; k++) {
+        GUIDO_CUDA(cudaEventRecord((cudaEvent_t)events[k], (cudaStream_t)streams[k]));
+        GUIDO_CUDA(cudaStreamWaitEvent((cudaStream_t)onto_stream, (cudaEvent_t)events[k], 0));
+    }
+    return GUIDO_OK;
+}
+
 int guido_kernel_times(guido_image *img, double *out_ms, int32_t max_n, int32_t *n) {
     GUIDO_API_RANGE();
     if (!img || !img->dev || !out_ms || !n) { set_error("bad arguments"); return GUIDO_ERR_ARG; }

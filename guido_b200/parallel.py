@@ -109,25 +109,25 @@ class PeerGather:
         self.lanes = [torch.cuda.Stream(device=self.dev) for _ in range(self.world)]
         self.lane_done = [torch.cuda.Event() for _ in range(self.world)]
         self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        for ev, lane in zip(self.lane_done, self.lanes):
+            ev.record(lane)   # (creates the handles)
+        # raw handles for the one-call-per-slot C entry points
+        self._c_peers = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(p) for p in self.peers])
+        self._c_lanes = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(l.cuda_stream) for l in self.lanes])
+        self._c_done = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(e.cuda_event) for e in self.lane_done])
 
     def send(self, slot, src_ptr, after=None):
         """this rank's ``slot_words`` words at ``src_ptr`` -> its place in every rank's buffer; the copies start
         behind the event ``after`` (the data is ready), one stream per destination"""
         at = (slot * self.world + self.rank) * self.slot_words * 8
-        for r in range(self.world):
-            dst = (self.rank + r) % self.world   # start with the own buffer, then round the ring
-            lane = self.lanes[dst]
-            if after is not None:
-                lane.wait_event(after)
-            _native.check(self._lib.guido_copy_dev(self.peers[dst] + at, src_ptr, self.slot_words * 8, lane.cuda_stream))
+        _native.check(self._lib.guido_peer_send(self._c_peers, self._c_lanes, self.world, self.rank, at, src_ptr,
+                                                self.slot_words * 8, after.cuda_event if after is not None else None))
 
     def fence(self):
         """behind it (on self.stream), every rank's sends issued before ITS fence have landed everywhere"""
         import torch
         import torch.distributed as dist
-        for lane, ev in zip(self.lanes, self.lane_done):
-            ev.record(lane)
-            self.stream.wait_event(ev)
+        _native.check(self._lib.guido_streams_join(self._c_lanes, self._c_done, self.world, self.stream.cuda_stream))
         with torch.cuda.stream(self.stream):
             dist.all_reduce(self.token, group=self.group)
 

@@ -105,6 +105,14 @@ int guido_peer_open(int32_t device, const void *handle64, void **d_ptr);
 int guido_peer_close(void *d_ptr);
 int guido_peer_free(void *d_ptr);
 int guido_copy_dev(void *dst, const void *src, int64_t bytes, void *stream);
+/* One call for the n copies of a peer exchange: `bytes` from src to dst_ptrs[r] + at_bytes on streams[r]
+ * (cudaStream_t each), r = first, first + 1, ... round the ring, each behind after_event (a
+ * cudaEvent_t; may be NULL).  guido_streams_join records events[k] on streams[k] and makes
+ * onto_stream wait for all of them.  (A step of a few hundred microseconds cannot afford one
+ * Python-level call per copy.) */
+int guido_peer_send(void *const *dst_ptrs, void *const *streams, int32_t n, int32_t first, int64_t at_bytes,
+                    const void *src, int64_t bytes, void *after_event);
+int guido_streams_join(void *const *streams, void *const *events, int32_t n, void *onto_stream);
 
 /* device time (ms, CUDA events on the launching stream) of the DOMINANT kernel of the last calls on
  * this handle -- PAM count+fill, or the off-target search kernel -- oldest first, up to 64 kept.
