@@ -89,22 +89,56 @@ def top_patterns_batch(rel_cut_positions, sequences, length_weight, n_patterns, 
     if not sequences:
         return []
     tuples, offsets, n_cand = _native.mmej_batch(sequences, cuts, device=device, stats=stats)
-    lf = np.array([round(1 / math.exp(d / length_weight), 3) for d in range(512)], dtype=np.float64)
+    winners = _top_indices(tuples, offsets, sequences, cuts, length_weight, n_patterns)
     out = []
     for g, (seq, cut) in enumerate(zip(sequences, cuts)):
         if n_cand[g] == 0:
             out.append(None)
             continue
-        t = tuples[offsets[g]:offsets[g + 1]]
-        ls, le, rs = _unpack(t)
         left_seq, right_seq = seq[:cut], seq[cut:]
-        b = np.frombuffer(left_seq.encode(), dtype=np.uint8)
-        cum = np.concatenate(([0], np.cumsum((b == 71) | (b == 67))))
-        gc = cum[le] - cum[ls]
-        del_len = (len(left_seq) - ls) + rs
-        score = (100 * lf[del_len]) * (((le - ls) - gc) + (gc * 2))
-        best = np.argsort(-score, kind="stable")[:n_patterns]
-        out.append([_pattern_dict(left_seq, right_seq, ls[i], le[i], rs[i], length_weight) for i in best])
+        ls, le, rs = _unpack(tuples[winners[g]])
+        out.append([_pattern_dict(left_seq, right_seq, a, b, c, length_weight) for a, b, c in zip(ls, le, rs)])
+    return out
+
+
+def _top_indices(tuples, offsets, sequences, cuts, length_weight, n_patterns):
+    """Per window, the indices (into ``tuples``) of its ``n_patterns`` best candidates in the order
+    ``sorted(key=-score)`` gives (stable: ties keep candidate order).  All windows at once: the scores
+    are one vectorised expression over every kept candidate -- the reference's, term by term, in
+    float64 -- and the winners are taken by n_patterns rounds of "first maximum of every segment"."""
+    n_win = len(sequences)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    counts = np.diff(offsets)
+    total = int(offsets[-1])
+    if total == 0 or n_patterns <= 0:
+        return [np.zeros(0, np.int64) for _ in range(n_win)]
+    ls, le, rs = _unpack(tuples[:total])
+    g = np.repeat(np.arange(n_win), counts)
+    left_len = np.asarray(cuts, dtype=np.int64)
+    # G/C prefix sums over the concatenated left flanks
+    cat = np.frombuffer("".join(seq[:cut] for seq, cut in zip(sequences, cuts)).encode(), dtype=np.uint8)
+    cum = np.concatenate(([0], np.cumsum((cat == 71) | (cat == 67))))
+    loff = np.concatenate(([0], np.cumsum(left_len)))[:-1]
+    gc = cum[loff[g] + le] - cum[loff[g] + ls]
+    del_len = (left_len[g] - ls) + rs
+    lf = np.array([round(1 / math.exp(d / length_weight), 3) for d in range(int(del_len.max()) + 1)], dtype=np.float64)
+    work = (100 * lf[del_len]) * (((le - ls) - gc) + (gc * 2))
+    nonempty = np.nonzero(counts > 0)[0]
+    seg_starts = offsets[:-1][nonempty]
+    seg_counts = counts[nonempty]
+    position = np.arange(total)
+    picks = np.full((len(nonempty), n_patterns), -1, dtype=np.int64)
+    for k in range(n_patterns):
+        seg_max = np.maximum.reduceat(work, seg_starts)
+        first = np.minimum.reduceat(np.where(work == np.repeat(seg_max, seg_counts), position, total), seg_starts)
+        live = seg_max != -np.inf            # windows with fewer than k + 1 candidates are exhausted
+        picks[live, k] = first[live]
+        work[first[live]] = -np.inf
+        if not live.any():
+            break
+    out = [np.zeros(0, np.int64) for _ in range(n_win)]
+    for row, w in zip(picks, nonempty.tolist()):
+        out[w] = row[row >= 0]
     return out
 
 

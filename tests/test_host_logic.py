@@ -313,3 +313,24 @@ def test_fasta_stray_carriage_returns(tmp_path):
     img = N.Image.from_fasta(str(fa))
     assert [(n, l) for n, l, _ in img.contigs] == [("c1", 12), ("c2", 4)]
     assert img.fetch(0, 0, 12) == "ACGTACGTGGCC" and img.fetch(1, 0, 4) == "TTTT"
+
+
+def test_top_patterns_vectorised_equals_sorted(monkeypatch):
+    """top_patterns_batch (all windows scored at once, winners by rounds of first-maximum per segment) ==
+    sorted(generate_mmej_patterns(...), key=-score)[:n] per window: ties keep candidate order, windows with
+    fewer than n candidates, windows without any"""
+    from guido_b200 import mmej
+    monkeypatch.setattr(_native, "mmej_batch", fakes.fake_mmej_batch)
+    rng = np.random.default_rng(12)
+    windows = [util.random_dna(rng, int(n)) for n in rng.integers(8, 160, size=40)]
+    windows += ["ACGT" * 20, "AAAAAAAAAACCCCCCCCCC", "AC", "", "ACGTTGCA" * 10]
+    cuts = [len(w) // 2 for w in windows]
+    cuts[3] = 5
+    for n_top in (1, 5, 1000):
+        got = mmej.top_patterns_batch(cuts, windows, 20, n_top)
+        for w, c, g in zip(windows, cuts, got):
+            full = mmej.generate_mmej_patterns(c, w, 20)
+            if full is None:
+                assert g is None
+            else:
+                assert g == sorted(full, key=lambda x: -x["pattern_score"])[:n_top]
