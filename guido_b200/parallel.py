@@ -6,8 +6,13 @@ contiguous, 65536-base aligned chunks (``guido_shard_bounds``); rank r uploads c
 256-base halo and owns the PAM starts inside it, so no window is reported twice and none is lost.
 Guides are replicated.  The only exchange is the merge of the per-rank result lists:
 
-* off-target hits: all-gather of the counts, then of the (padded) 16-byte records -- NCCL over
-  NVLink when the tensors live on the GPUs, gloo for the CPU tests;
+* off-target hits: ONE padded all-gather of fixed-size slots whose first record carries the rank's
+  count (``DeviceMerge``: search, gather, concat and sort stay on the GPUs; NCCL over NVLink), or,
+  without any collective, copies into receive buffers the ranks of a node share through CUDA IPC
+  (``PeerGather``: copy engines, next to a search that fills every SM); ``all_gather_hits`` is the
+  host-array form (counts, then padded records) that also runs on gloo for the CPU tests.
+  ``ShardedGenome(partition="key")`` splits the core-key space of the PAM-site table instead of the
+  genome, so the per-search guide index is built in N parts instead of N times;
 * PAM positions: the per-rank lists are globally ordered by construction (rank order = genome
   order), so the merge is a concatenation.
 
