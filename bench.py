@@ -612,6 +612,30 @@ def exon_set(lens, seed=1006, n_genes=5000):
     return np.array(exons, dtype=np.int64)
 
 
+def window_starts_in_exons(fw, rv, P, ex_lo, ex_end, run_lo, run_hi, flank=75):
+    """Start of the 2 x flank window around every cut that lies in an exon and whose window is N-free; PAM
+    positions fw / rv ascending (uint32), '+' sites first.
+
+    The reference's geometry (guides.py:53-67): '+' cut = p - 3, '-' cut = p + P + 3.  A cut belongs to
+    the last exon that starts at or before it, if it lies inside it: with the exons sorted these are the
+    disjoint intervals [ex_lo[k], ex_end[k]) (ex_end = min(exon end, next exon start)), and the PAM
+    positions whose cut falls inside are index ranges found by 2 x n_exons binary searches -- the host
+    touches the ~8 % of the sites it keeps, not all of them.  Windows that touch a non-ACGT run are left
+    out (the CPU arm skips guides with "N" in locus_seq): cut - flank < run end and cut + flank > run
+    start, i.e. run_lo = run start - flank < cut < run end + flank = run_hi."""
+    parts = []
+    for pos, shift in ((fw, -3), (rv, P + 3)):
+        first = np.searchsorted(pos, (ex_lo - shift).astype(np.uint32), side="left")
+        last = np.searchsorted(pos, (ex_end - shift).astype(np.uint32), side="left")
+        n_in = last - first
+        ix = np.repeat(first - (np.cumsum(n_in) - n_in), n_in) + np.arange(int(n_in.sum()))
+        cut = pos[ix].astype(np.int64) + shift
+        r = np.searchsorted(run_hi, cut, side="right")           # first run whose reach ends behind the cut
+        cut = cut[(r >= len(run_lo)) | (run_lo[np.minimum(r, len(run_lo) - 1)] >= cut)]
+        parts.append(cut - flank)
+    return np.concatenate(parts)
+
+
 def run_mmej(R, args):
     """TTTV scan of a 100 Mb genome + MMEJ enumeration for every guide whose cut lies in an exon"""
     N, torch = R.N, R.torch
@@ -635,23 +659,7 @@ def run_mmej(R, args):
         t_a = time.perf_counter()
         fw, rv = img.pam_scan_genome(pam, N.SCAN_GUIDE, pinned=True)
         t_b = time.perf_counter()
-        # the reference's geometry (guides.py:53-67): '+' cut = p - 3, '-' cut = p + P + 3.  A cut belongs
-        # to the last exon that starts at or before it, if it lies inside it: with the exons sorted these
-        # are disjoint intervals [lo_k, min(hi_k, lo_k+1)), and the (sorted) PAM positions whose cut falls
-        # inside are index ranges found by 2 x 27 k binary searches -- the host touches the ~8 % of the
-        # sites it keeps, not all 2.3 M.  Windows that touch a non-ACGT run are left out (the CPU arm
-        # skips guides with "N" in locus_seq): cut - 75 < run end and cut + 75 > run start.
-        lo_parts = []
-        for pos, shift in ((fw, -3), (rv, P + 3)):
-            first = np.searchsorted(pos, (ex_lo - shift).astype(np.uint32), side="left")
-            last = np.searchsorted(pos, (ex_end - shift).astype(np.uint32), side="left")
-            n_in = last - first
-            ix = np.repeat(first - (np.cumsum(n_in) - n_in), n_in) + np.arange(int(n_in.sum()))
-            cut = pos[ix].astype(np.int64) + shift
-            r = np.searchsorted(run_hi, cut, side="right")           # first run whose reach ends behind the cut
-            cut = cut[(r >= len(run_lo)) | (run_lo[np.minimum(r, len(run_lo) - 1)] >= cut)]
-            lo_parts.append(cut - 75)
-        lo = np.concatenate(lo_parts)
+        lo = window_starts_in_exons(fw, rv, P, ex_lo, ex_end, run_lo, run_hi)
         n_sites = len(fw) + len(rv)
         st = N.Stats()
         t_c = time.perf_counter()

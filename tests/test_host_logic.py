@@ -334,3 +334,35 @@ def test_top_patterns_vectorised_equals_sorted(monkeypatch):
                 assert g is None
             else:
                 assert g == sorted(full, key=lambda x: -x["pattern_score"])[:n_top]
+
+
+def test_bench_exon_window_filter_equals_the_per_site_definition():
+    """bench.py's configs[4] site filter (index ranges per exon, run test on the survivors) keeps exactly
+    the sites the per-site rule keeps, in the same order"""
+    import bench
+    rng = np.random.default_rng(14)
+    P = 4
+    for trial in range(12):
+        fw = np.sort(rng.choice(300000, size=7000, replace=False)).astype(np.uint32) + 100
+        rv = np.sort(rng.choice(300000, size=7000, replace=False)).astype(np.uint32) + 100
+        ex_lo = np.sort(rng.integers(500, 299000, size=400)).astype(np.int64)
+        ex_hi = ex_lo + rng.integers(50, 900, size=400)
+        st = np.sort(rng.choice(300000, size=15, replace=False)).astype(np.int64)
+        en = st + rng.integers(1, 400, size=15)
+        keep = [0]
+        for i in range(1, len(st)):
+            if st[i] > en[keep[-1]]:
+                keep.append(i)
+        st, en = st[keep], en[keep]
+        ex_end = np.minimum(ex_hi, np.append(ex_lo[1:], np.iinfo(np.int64).max))
+        got = bench.window_starts_in_exons(fw, rv, P, ex_lo, ex_end, st - 75, en + 75)
+        want = []
+        for cut in np.concatenate([fw.astype(np.int64) - 3, rv.astype(np.int64) + P + 3]).tolist():
+            k = int(np.searchsorted(ex_lo, cut, side="right")) - 1
+            if k < 0 or cut >= ex_hi[k]:
+                continue
+            lo = cut - 75
+            if any(e > lo and s < lo + 150 for s, e in zip(st.tolist(), en.tolist())):
+                continue
+            want.append(lo)
+        assert got.tolist() == want
