@@ -80,3 +80,46 @@ def test_offtarget_postprocessing_differential(ref, oracle, pam, kw):
     for ix in mine:
         assert sorted(want[ix], key=key) == mine[ix]
     assert sum(len(v) for v in mine.values()) > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_package_host_logic_differential(ref, monkeypatch, seed):
+    """guido_b200's host side (Guide geometry, interval handling, sorting / naming, MMEJ pattern dicts, scores,
+    top-n and the out-of-frame layer) with the device entry points replaced by the oracle-backed fakes ==
+    the live reference on the same random inputs"""
+    import guido_b200 as guido
+    from guido_b200 import _native
+    from tests import fakes
+    monkeypatch.setattr(_native, "pam_scan_seq", fakes.fake_pam_scan_seq)
+    monkeypatch.setattr(_native, "mmej_batch", fakes.fake_mmej_batch)
+    rng = np.random.default_rng(seed + 4000)
+    n = int(rng.integers(60, 1500))
+    pam = ["NGG", "NAG", "NGN", "NNN", "YGG", "NGG"][seed]
+    flank = int(rng.integers(0, 60))
+    start = int(rng.integers(1, 10**5))
+    seq = util.synthetic_contigs(seed + 700, [n], n_runs=1, run_len=(1, 10), lower_frac=0.2)[0][1]
+    want_loc = ref.Locus(sequence=seq, name="chrQ", start=start)
+    mine_loc = guido.Locus(sequence=seq, name="chrQ", start=start)
+    want = want_loc.find_guides(pam=pam, min_flanking_length=flank)
+    mine = mine_loc.find_guides(pam=pam, min_flanking_length=flank)
+    assert len(mine) == len(want)
+    for a, b in zip(mine, want):
+        assert a.id == b.id
+        for k in ATTRS:
+            assert getattr(a, k) == getattr(b, k), k
+    if not want:
+        return
+    n_top, lw = int(rng.integers(1, 8)), float(rng.choice([20, 10]))
+    try:
+        want_loc.simulate_end_joining(n_patterns=n_top, length_weight=lw)
+        failed = None
+    except TypeError as exc:      # upstream: a guide without any MMEJ pattern
+        failed = exc
+    if failed is not None:
+        with pytest.raises(TypeError):
+            mine_loc.simulate_end_joining(n_patterns=n_top, length_weight=lw)
+        return
+    mine_loc.simulate_end_joining(n_patterns=n_top, length_weight=lw)
+    for a, b in zip(mine_loc.guides, want_loc.guides):
+        assert a.mmej_patterns == b.mmej_patterns
+        assert a.layers == b.layers
